@@ -1,0 +1,349 @@
+// bfm_kernels.cuh - sm_100a device code of the brute-force Hamming matcher.
+//
+// What is computed (cv2.BFMatcher(NORM_HAMMING) semantics; the call sites
+// this replaces are reference slam/tracking.py:56,121):
+//   D[i][j] = popcount(q[i] XOR t[j]) over 256 bits
+//   row state[i]  = the two smallest packed keys (D[i][j] << 22 | j) over the allowed j
+//   col key[j]    = the smallest packed key (D[i][j] << 22 | i) over the allowed i   (cross-check)
+// A single unsigned min over the packed key reproduces cv2's order "distance, then lowest index",
+// so every reduction stage (registers, warp REDUX, shared memory, global atomics, multi-GPU) is
+// the same associative/commutative min and the result is independent of how work is split.
+//
+// Mapping to the machine: this is an integer-pipe kernel (LOP3 + POPC + IADD3/IMAD + VIMNMX),
+// not a tensor-core one.  Each thread keeps R query descriptors (8 x u32 each) in registers,
+// the CTA streams a range of train descriptors through shared memory in 4 KB chunks that a
+// single thread fetches with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered),
+// and every lane reads the same train words (LDS.128 broadcast, conflict free).  HBM traffic is
+// ~1e-2 bytes per pair; the bound is the POPC issue rate.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bfm {
+
+constexpr int DIST_SHIFT = 22;
+constexpr uint32_t IDX_MASK = (1u << DIST_SHIFT) - 1u;
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;      // empty slot
+constexpr uint32_t KEY_DEAD = 0x80000000u;      // any key >= this is "no candidate" (distance field >= 512)
+constexpr uint32_t DIST_MASKED = 512u;          // OR-ed into a masked pair's distance
+constexpr int TT = 128;                         // train rows per shared-memory chunk (4 KB)
+
+// One work item: a block of BQ = NT*R query rows against a contiguous range of train rows of
+// the same problem.  Built on the host by the planner (bfm_api.cu: plan_segments).
+struct __align__(16) Segment {
+    int32_t q_row0;    // first query row (global row in the query array)
+    int32_t q_valid;   // rows of this block that exist (1..BQ)
+    int32_t q_local0;  // index of q_row0 inside its problem (cv2 queryIdx of the first row)
+    int32_t out_row0;  // output row of the first query of the block
+    int32_t t_row0;    // first train row (global row in the train array)
+    int32_t t_count;   // train rows in this segment (>= 1)
+    int32_t t_local0;  // index of t_row0 inside its problem (cv2 trainIdx)
+    int32_t col0;      // first column-key slot of this segment's problem (cross-check)
+};
+
+struct ScanParams {
+    const uint4 *q;                  // [rows][2] 16-byte halves of the 32-byte descriptors
+    const uint4 *t;
+    const Segment *segs;
+    unsigned long long *rowstate;    // [out rows] (best key << 32) | second key
+    uint32_t *colkeys;               // [sum of problem train rows] (cross-check), problem base = Segment::col0
+    const uint8_t *mask;             // dense mask (single problem): [q_local][mask_stride]
+    long long mask_stride;
+    const float2 *q_xy;              // window: pixel coordinates per query / train row
+    const float2 *t_xy;
+    float radius;
+};
+
+// ---- PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// ---- 256-bit Hamming distance ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// PM = POPC instructions issued per pair.  PM == 8 is the plain XOR+POPC form; the others run a
+// carry-save adder (Harley-Seal) tree on LOP3 first, trading quarter-rate POPCs for full-rate
+// logic ops.  All variants return the exact popcount of the 256-bit XOR.
+template <int PM>
+__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint32_t (&t)[8]) {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = q[i] ^ t[i];
+    if constexpr (PM == 8) {
+        return (__popc(x[0]) + __popc(x[1]) + __popc(x[2])) + (__popc(x[3]) + __popc(x[4]) + __popc(x[5])) +
+               (__popc(x[6]) + __popc(x[7]));
+    } else {
+        const uint32_t s0 = xor3(x[0], x[1], x[2]), c0 = maj3(x[0], x[1], x[2]);
+        const uint32_t s1 = xor3(x[3], x[4], x[5]), c1 = maj3(x[3], x[4], x[5]);
+        if constexpr (PM == 6) {
+            return (__popc(s0) + __popc(s1) + __popc(x[6])) + __popc(x[7]) + 2u * (__popc(c0) + __popc(c1));
+        } else {
+            const uint32_t s2 = xor3(s0, s1, x[6]), c2 = maj3(s0, s1, x[6]);
+            if constexpr (PM == 5) {
+                return (__popc(s2) + __popc(x[7])) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
+            } else {  // PM == 4
+                const uint32_t s3 = xor3(c0, c1, c2), c3 = maj3(c0, c1, c2);
+                return (__popc(s2) + __popc(x[7])) + 2u * __popc(s3) + 4u * __popc(c3);
+            }
+        }
+    }
+}
+
+// ---- the distance-scan kernel --------------------------------------------------------------------
+// R     queries per thread (register tile)
+// K     1 or 2 neighbours tracked per query
+// CROSS also reduce the per-train column key (cross-check); K must be 1
+// MASK  0 none, 1 dense uint8 mask, 2 projection window
+// PM    POPCs per pair (8 / 6 / 5 / 4)
+// NT    threads per CTA
+template <int R, int K, bool CROSS, int MASK, int PM, int NT>
+__global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
+    constexpr int NW = NT / 32;
+    __shared__ __align__(128) uint4 s_t[2][TT * 2];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ float2 s_xy[MASK == 2 ? 2 : 1][MASK == 2 ? TT : 1];
+    __shared__ uint32_t s_col[CROSS ? NW : 1][CROSS ? TT : 1];
+
+    const Segment sg = p.segs[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    // -- this thread's R query descriptors (two coalesced 16-byte loads each) ---------------------
+    uint32_t qw[R][8];
+    uint32_t ibias[R];          // CROSS: low bits of the column key (query index), dead bit if row absent
+    bool valid[R];
+    float qx[R], qy[R];
+    const uint8_t *mrow[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int lr = r * NT + tid;
+        valid[r] = lr < sg.q_valid;
+        const int row = sg.q_row0 + (valid[r] ? lr : 0);
+        const uint4 a = __ldg(p.q + 2 * (size_t)row);
+        const uint4 b = __ldg(p.q + 2 * (size_t)row + 1);
+        qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
+        qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
+        ibias[r] = (uint32_t)(sg.q_local0 + lr);
+        if (MASK == 0 && !valid[r]) ibias[r] = KEY_DEAD;
+        if (MASK == 2) {
+            const float2 xy = __ldg(p.q_xy + row);
+            // an absent row gets NaN coordinates: every window compare is false
+            qx[r] = valid[r] ? xy.x : __int_as_float(0x7fc00000);
+            qy[r] = xy.y;
+        }
+        if (MASK == 1) mrow[r] = p.mask + (size_t)(sg.q_local0 + (valid[r] ? lr : 0)) * (size_t)p.mask_stride;
+    }
+
+    uint32_t b1[R], b2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { b1[r] = KEY_NONE; b2[r] = KEY_NONE; }
+
+    // -- double-buffered TMA pipeline over the segment's train rows -------------------------------
+    const int nchunks = (sg.t_count + TT - 1) / TT;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    if (MASK == 2) {
+        for (int j = tid; j < min(TT, sg.t_count); j += NT) s_xy[0][j] = __ldg(p.t_xy + sg.t_row0 + j);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)min(TT, sg.t_count) * 32u;
+        mbar_expect_tx(&s_bar[0], bytes);
+        bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)sg.t_row0, bytes, &s_bar[0]);
+    }
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        const int n = min(TT, sg.t_count - c * TT);
+        if (c + 1 < nchunks) {
+            // buffer b^1 was released by the __syncthreads that closed iteration c-1
+            const int n1 = min(TT, sg.t_count - (c + 1) * TT);
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar[b ^ 1], (uint32_t)n1 * 32u);
+                bulk_g2s(&s_t[b ^ 1][0], p.t + 2 * (size_t)(sg.t_row0 + (c + 1) * TT), (uint32_t)n1 * 32u, &s_bar[b ^ 1]);
+            }
+            if (MASK == 2) {
+                for (int j = tid; j < n1; j += NT) s_xy[b ^ 1][j] = __ldg(p.t_xy + sg.t_row0 + (c + 1) * TT + j);
+            }
+        }
+        mbar_wait(&s_bar[b], (uint32_t)((c >> 1) & 1));
+
+        const uint32_t jbase = (uint32_t)(sg.t_local0 + c * TT);
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) {
+            const uint4 ta = s_t[b][2 * j];
+            const uint4 tb = s_t[b][2 * j + 1];
+            const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+            float2 txy;
+            if (MASK == 2) txy = s_xy[b][j];
+            const uint32_t jj = jbase + (uint32_t)j;
+            uint32_t ck = KEY_NONE;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                uint32_t d = hamming256<PM>(qw[r], tw);
+                if (MASK == 1) {
+                    const bool ok = valid[r] && (__ldg(mrow[r] + jj) != 0);
+                    d = ok ? d : (d | DIST_MASKED);
+                }
+                if (MASK == 2) {
+                    const bool ok = (fabsf(qx[r] - txy.x) < p.radius) && (fabsf(qy[r] - txy.y) < p.radius);
+                    d = ok ? d : (d | DIST_MASKED);
+                }
+                const uint32_t key = (d << DIST_SHIFT) + jj;
+                if (K == 2) b2[r] = min(b2[r], max(b1[r], key));
+                b1[r] = min(b1[r], key);
+                if (CROSS) ck = min(ck, (d << DIST_SHIFT) + ibias[r]);
+            }
+            if (CROSS) {
+                ck = __reduce_min_sync(0xffffffffu, ck);
+                if (lane == 0) s_col[warp][j] = ck;
+            }
+        }
+        if (CROSS) {
+            __syncthreads();
+            for (int j = tid; j < n; j += NT) {
+                uint32_t m = s_col[0][j];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) m = min(m, s_col[w][j]);
+                if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)sg.col0 + sg.t_local0 + c * TT + j, m);
+            }
+        }
+        __syncthreads();
+    }
+
+    // -- commit: associative min-merge into the global row state ---------------------------------
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (!valid[r] || b1[r] >= KEY_DEAD) continue;
+        unsigned long long *addr = p.rowstate + (size_t)(sg.out_row0 + r * NT + tid);
+        if (K == 1) {
+            atomicMin(addr, ((unsigned long long)b1[r] << 32) | 0xFFFFFFFFull);
+        } else {
+            const uint32_t n2 = b2[r] >= KEY_DEAD ? KEY_NONE : b2[r];
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(addr);
+            while (true) {
+                const uint32_t o1 = (uint32_t)(old >> 32), o2 = (uint32_t)old;
+                const uint32_t m1 = min(o1, b1[r]);
+                const uint32_t m2 = min(max(o1, b1[r]), min(o2, n2));
+                const unsigned long long want = ((unsigned long long)m1 << 32) | m2;
+                if (want == old) break;
+                const unsigned long long seen = atomicCAS(addr, old, want);
+                if (seen == old) break;
+                old = seen;
+            }
+        }
+    }
+}
+
+// ---- finalize: decode keys, cross-check / ratio / distance gate, ordered compaction -----------------
+struct Problem {   // mirrors bfm_problem_t; `col0` (reserved there) = first column-key slot
+    int32_t q_begin, q_count, t_begin, t_count, out_begin, col0;
+};
+
+struct FinalizeParams {
+    const unsigned long long *rowstate;
+    const uint32_t *colkeys;
+    const Problem *problems;
+    int32_t k;             // columns of the knn table (1 or 2 on this path)
+    int32_t cross_check;
+    int32_t max_distance;  // < 0 off
+    int32_t use_ratio;
+    double ratio;
+    int32_t *knn_idx, *knn_dist;                 // nullable
+    int32_t *m_query, *m_train, *m_dist, *m_count;  // nullable (all or none)
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) bfm_finalize_kernel(const FinalizeParams p) {
+    __shared__ int s_warp[NT / 32];
+    __shared__ int s_running;
+    const Problem pr = p.problems[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_running = 0;
+    __syncthreads();
+    for (int base = 0; base < pr.q_count; base += NT) {
+        const int i = base + tid;
+        const bool in = i < pr.q_count;
+        uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
+        if (in) {
+            const unsigned long long st = p.rowstate[(size_t)pr.out_begin + i];
+            k1 = (uint32_t)(st >> 32);
+            k2 = (uint32_t)st;
+        }
+        const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
+        const int idx1 = has1 ? (int)(k1 & IDX_MASK) : -1, d1 = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
+        const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
+        if (in && p.knn_idx) {
+            const size_t o = ((size_t)pr.out_begin + i) * (size_t)p.k;
+            p.knn_idx[o] = idx1;
+            p.knn_dist[o] = d1;
+            if (p.k > 1) { p.knn_idx[o + 1] = idx2; p.knn_dist[o + 1] = d2; }
+        }
+        if (p.m_count) {
+            bool keep = in && has1;
+            if (keep && p.cross_check)
+                keep = p.colkeys[(size_t)pr.col0 + idx1] == (((uint32_t)d1 << DIST_SHIFT) | (uint32_t)i);
+            if (keep && p.use_ratio) keep = has2 && ((double)d1 < p.ratio * (double)d2);
+            if (keep && p.max_distance >= 0) keep = d1 <= p.max_distance;
+            // ordered (ascending queryIdx) compaction: ballot inside the warp, scan across warps
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_warp[warp] = __popc(bal);
+            __syncthreads();
+            int before = s_running;
+            for (int w = 0; w < warp; ++w) before += s_warp[w];
+            if (keep) {
+                const size_t o = (size_t)pr.out_begin + before + __popc(bal & ((1u << lane) - 1u));
+                p.m_query[o] = i;
+                p.m_train[o] = idx1;
+                p.m_dist[o] = d1;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < NT / 32; ++w) tot += s_warp[w];
+                s_running += tot;
+            }
+            __syncthreads();
+        }
+    }
+    if (p.m_count && tid == 0) p.m_count[blockIdx.x] = s_running;
+}
+
+}  // namespace bfm

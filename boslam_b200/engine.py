@@ -1,0 +1,462 @@
+"""Host side of the matcher: a thin, typed layer over the C ABI (include/bfm.h).
+
+``Engine`` owns one ``bfm_handle_t`` (own CUDA stream + workspace).  Inputs are either numpy
+arrays (host path: pinned staging + H2D/D2H inside the call) or CUDA ``torch.Tensor`` s (device
+path: zero-copy via ``data_ptr`` on torch's current stream).  All arithmetic happens in the CUDA
+library; nothing here computes distances.
+
+The array API mirrors what the reference's call sites do with cv2 (reference
+``slam/tracking.py:56-60,119-126``): ``match`` -> (queryIdx, trainIdx, distance) in ascending
+queryIdx order, with the caller-side filters (distance gate, ratio test) optionally fused.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+import weakref
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+
+DESC_BYTES = 32
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def _check_desc_np(a, name: str) -> np.ndarray:
+    """cv2 raises on non-uint8 descriptors; so do we.  Non-contiguous is accepted."""
+    a = np.asarray(a)
+    if a.dtype != np.uint8:
+        raise TypeError(f"{name}: descriptors must be uint8 (got {a.dtype}), as cv2.NORM_HAMMING requires")
+    if a.ndim != 2 or a.shape[1] != DESC_BYTES:
+        if a.ndim == 2 and a.shape[0] == 0:
+            return np.zeros((0, DESC_BYTES), np.uint8)
+        raise ValueError(f"{name}: expected uint8[N, {DESC_BYTES}] ORB descriptors, got shape {a.shape}")
+    if not a.flags.c_contiguous or (a.ctypes.data & 15):
+        a = np.ascontiguousarray(a)
+        if a.ctypes.data & 15:  # pragma: no cover - numpy allocations are 16-byte aligned
+            b = np.empty(a.shape[0] * DESC_BYTES + 16, np.uint8)
+            off = (-b.ctypes.data) & 15
+            b = b[off:off + a.size].reshape(a.shape)
+            b[...] = a
+            a = b
+    return a
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy array (``.array``)."""
+
+    def __init__(self, shape, dtype=np.uint8):
+        self._lib = _ffi.lib()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = ctypes.c_void_p()
+        _ffi.check(None, self._lib.bfm_host_alloc(max(n, 1), ctypes.byref(p)))
+        self._ptr = p.value
+        raw = (ctypes.c_uint8 * max(n, 1)).from_address(self._ptr)
+        self.array = np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._fin = weakref.finalize(self, self._lib.bfm_host_free, ctypes.c_void_p(self._ptr))
+
+    def free(self):
+        self.array = None
+        self._fin()
+
+
+class BatchResult:
+    """Matches of a batch of problems, packed.  ``counts[p]`` matches of problem p start at
+    ``offsets[p]`` in ``query_idx`` / ``train_idx`` / ``distance`` (problem-local indices)."""
+
+    __slots__ = ("query_idx", "train_idx", "distance", "counts", "offsets")
+
+    def __init__(self, query_idx, train_idx, distance, counts, offsets):
+        self.query_idx, self.train_idx, self.distance = query_idx, train_idx, distance
+        self.counts, self.offsets = counts, offsets
+
+    def __len__(self):
+        return len(self.counts)
+
+    def __getitem__(self, p):
+        b, n = int(self.offsets[p]), int(self.counts[p])
+        return self.query_idx[b:b + n], self.train_idx[b:b + n], self.distance[b:b + n]
+
+    def __iter__(self):
+        for p in range(len(self)):
+            yield self[p]
+
+
+def make_problems(q_counts: Sequence[int], t_counts: Sequence[int], shared_query: bool = False) -> np.ndarray:
+    """Problem table int32[P, 6] (q_begin, q_count, t_begin, t_count, out_begin, 0) for problems
+    stored back to back.  With ``shared_query`` every problem reads query rows [0, q_counts[0])."""
+    P = len(t_counts)
+    tab = np.zeros((P, 6), np.int32)
+    qc = np.asarray(q_counts, np.int64)
+    tc = np.asarray(t_counts, np.int64)
+    tab[:, 1] = qc
+    tab[:, 3] = tc
+    tab[:, 2] = np.concatenate([[0], np.cumsum(tc)[:-1]]) if P else 0
+    out = np.concatenate([[0], np.cumsum(qc)[:-1]]) if P else np.zeros(0, np.int64)
+    tab[:, 4] = out
+    tab[:, 0] = 0 if shared_query else out
+    return tab
+
+
+class Engine:
+    """One matcher instance = one CUDA stream + workspace on one B200."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _ffi.lib()
+        h = ctypes.c_void_p()
+        rc = self._lib.bfm_create(int(device), ctypes.byref(h))
+        if rc != _ffi.BFM_OK:
+            _ffi.check(None, rc)
+        self._h = h
+        self.device = int(device)
+        self._lock = threading.Lock()  # the C handle is not re-entrant
+        self._fin = weakref.finalize(self, self._lib.bfm_destroy, h)
+
+    # -- housekeeping -------------------------------------------------------------------------
+    def close(self):
+        self._fin()
+
+    def set_tuning(self, **knobs):
+        for k, v in knobs.items():
+            _ffi.check(self._h, self._lib.bfm_set_tuning(self._h, k.encode(), int(v)))
+
+    def launch_info(self) -> dict:
+        li = _ffi.LaunchInfo()
+        _ffi.check(self._h, self._lib.bfm_get_launch_info(self._h, ctypes.byref(li)))
+        return {f: getattr(li, f) for f, _ in li._fields_ if f != "reserved"}
+
+    def kernel_launch_count(self) -> int:
+        return int(self._lib.bfm_kernel_launch_count(self._h))
+
+    # -- option marshalling ---------------------------------------------------------------------
+    @staticmethod
+    def _gate(max_distance, strict):
+        if max_distance is None:
+            return -1
+        import math
+        # distances are integers: d < x  <=>  d <= ceil(x) - 1 ;  d <= x  <=>  d <= floor(x)
+        g = math.ceil(max_distance) - 1 if strict else math.floor(max_distance)
+        return max(int(g), -1) if g >= 0 else -2  # -2: nothing can pass
+
+    def _options(self, k, ratio, cross_check, max_distance, strict):
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        if cross_check and k != 1:
+            raise ValueError("cross_check requires k == 1 (cv2 asserts the same, batch_distance.cpp:303)")
+        if cross_check and ratio is not None:
+            raise ValueError("cross_check and ratio are exclusive")
+        o = _ffi.Options()
+        o.k = int(k)
+        o.cross_check = 1 if cross_check else 0
+        o.mask_kind = _ffi.MASK_NONE
+        o.ratio = float(ratio) if ratio is not None else -1.0
+        g = self._gate(max_distance, strict)
+        o.max_distance = g if g != -2 else 0
+        return o, (g == -2)
+
+    # -- core call --------------------------------------------------------------------------------
+    def _call(self, mem, q_ptr, nq, t_ptr, nt, problems: np.ndarray, n_out, opts, knn, matches, stream=None):
+        P = problems.shape[0]
+        probs = np.ascontiguousarray(problems, np.int32)
+        pp = probs.ctypes.data_as(ctypes.POINTER(_ffi.Problem))
+        ki, kd = knn if knn is not None else (None, None)
+        mq, mt, md, mc = matches if matches is not None else (None, None, None, None)
+        with self._lock:
+            rc = self._lib.bfm_match_batched(self._h, mem, q_ptr, nq, t_ptr, nt, pp, P, n_out, ctypes.byref(opts),
+                                             ki, kd, mq, mt, md, mc, stream)
+            _ffi.check(self._h, rc)
+
+    # -- numpy (host) path --------------------------------------------------------------------------
+    def _mask_args_np(self, opts, mask, window, nq, nt, keep):
+        if mask is not None and window is not None:
+            raise ValueError("give mask or window, not both")
+        if mask is not None:
+            m = np.asarray(mask)
+            if m.dtype != np.uint8 or m.shape != (nq, nt):
+                raise ValueError(f"mask must be uint8[{nq}, {nt}] (cv2 convention), got {m.dtype}{m.shape}")
+            m = np.ascontiguousarray(m)
+            keep.append(m)
+            opts.mask_kind = _ffi.MASK_DENSE
+            opts.mask = m.ctypes.data
+            opts.mask_row_stride = nt
+        if window is not None:
+            q_xy, t_xy, radius = window
+            q_xy = np.ascontiguousarray(q_xy, np.float32)
+            t_xy = np.ascontiguousarray(t_xy, np.float32)
+            if q_xy.shape != (nq, 2) or t_xy.shape != (nt, 2):
+                raise ValueError("window = (q_xy float[Q,2], t_xy float[T,2], radius)")
+            keep += [q_xy, t_xy]
+            opts.mask_kind = _ffi.MASK_WINDOW
+            opts.q_xy = q_xy.ctypes.data
+            opts.t_xy = t_xy.ctypes.data
+            opts.window_radius = float(radius)
+
+    def knn(self, query, train, k: int = 1, mask=None, window=None):
+        """cv2 ``knnMatch`` as arrays: (idx int32[Q,k], dist int32[Q,k]); -1 marks a missing neighbour."""
+        if _is_torch(query):
+            return self._knn_torch(query, train, k, mask, window)
+        q = _check_desc_np(query, "query")
+        t = _check_desc_np(train, "train")
+        nq, nt = q.shape[0], t.shape[0]
+        self._check_limits(nq, nt, k)
+        idx = np.full((nq, k), -1, np.int32)
+        dist = np.full((nq, k), -1, np.int32)
+        if nq == 0 or nt == 0:
+            return idx, dist
+        opts, _ = self._options(k, None, False, None, False)
+        keep = []
+        self._mask_args_np(opts, mask, window, nq, nt, keep)
+        probs = np.array([[0, nq, 0, nt, 0, 0]], np.int32)
+        self._call(_ffi.MEM_HOST, q.ctypes.data, nq, t.ctypes.data, nt, probs, nq, opts,
+                   (idx.ctypes.data, dist.ctypes.data), None)
+        return idx, dist
+
+    def match(self, query, train, k: int = 1, ratio: Optional[float] = None, cross_check: bool = False,
+              mask=None, window=None, max_distance=None, strict: bool = False):
+        """(queryIdx int32[M], trainIdx int32[M], distance float32[M]), ascending queryIdx.
+
+        cross_check -> cv2 ``BFMatcher(crossCheck=True).match``; ratio -> Lowe test on the 2-NN;
+        max_distance (+ strict) -> the gates of slam/tracking.py:121 (``<=``) and :57 (``<``).
+        """
+        if _is_torch(query):
+            return self._match_torch(query, train, k, ratio, cross_check, mask, window, max_distance, strict)
+        q = _check_desc_np(query, "query")
+        t = _check_desc_np(train, "train")
+        nq, nt = q.shape[0], t.shape[0]
+        self._check_limits(nq, nt, k)
+        opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
+        if nq == 0 or nt == 0 or none_pass:
+            e = np.zeros(0, np.int32)
+            return e, e.copy(), np.zeros(0, np.float32)
+        keep = []
+        self._mask_args_np(opts, mask, window, nq, nt, keep)
+        mq = np.empty(nq, np.int32)
+        mt = np.empty(nq, np.int32)
+        md = np.empty(nq, np.int32)
+        mc = np.zeros(1, np.int32)
+        probs = np.array([[0, nq, 0, nt, 0, 0]], np.int32)
+        self._call(_ffi.MEM_HOST, q.ctypes.data, nq, t.ctypes.data, nt, probs, nq, opts, None,
+                   (mq.ctypes.data, mt.ctypes.data, md.ctypes.data, mc.ctypes.data))
+        n = int(mc[0])
+        return mq[:n], mt[:n], md[:n].astype(np.float32)
+
+    @staticmethod
+    def _check_limits(nq, nt, k):
+        if nt >= _ffi.MAX_TRAIN_ROWS or nq >= _ffi.MAX_QUERY_ROWS:
+            raise ValueError("at most 2^22 - 1 rows per problem (cv2 itself stops at 2^18 - 1 train rows)")
+        if k > 2:
+            raise NotImplementedError("k > 2 is not supported by this build")
+
+    # -- batched (keyframe pairs) -----------------------------------------------------------------------
+    def match_batched(self, q_packed, t_packed, problems: np.ndarray, k: int = 1, ratio=None,
+                      cross_check: bool = False, max_distance=None, strict: bool = False, window=None,
+                      want_knn: bool = False):
+        """Batched form over packed descriptor arrays + a problem table (see :func:`make_problems`).
+
+        Returns a :class:`BatchResult` (and the dense (idx, dist) tables first if ``want_knn``).
+        This is the local-mapping / loop-closing shape: P independent (query KF, train KF) problems
+        in one launch.
+        """
+        if _is_torch(q_packed):
+            return self._match_batched_torch(q_packed, t_packed, problems, k, ratio, cross_check, max_distance,
+                                             strict, window, want_knn)
+        q = _check_desc_np(q_packed, "q_packed")
+        t = _check_desc_np(t_packed, "t_packed")
+        probs = np.ascontiguousarray(problems, np.int32)
+        if probs.ndim != 2 or probs.shape[1] != 6:
+            raise ValueError("problems must be int32[P, 6]")
+        P = probs.shape[0]
+        n_out = int((probs[:, 4] + probs[:, 1]).max()) if P else 0
+        if P and (int(probs[:, 3].max()) >= _ffi.MAX_TRAIN_ROWS or int(probs[:, 1].max()) >= _ffi.MAX_QUERY_ROWS):
+            raise ValueError("at most 2^22 - 1 rows per problem")
+        if k > 2:
+            raise NotImplementedError("k > 2 is not supported by this build")
+        opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
+        keep = []
+        if window is not None:
+            self._mask_args_np(opts, None, window, q.shape[0], t.shape[0], keep)
+        mq = np.empty(n_out, np.int32)
+        mt = np.empty(n_out, np.int32)
+        md = np.empty(n_out, np.int32)
+        mc = np.zeros(P, np.int32)
+        idx = np.full((n_out, k), -1, np.int32) if want_knn else None
+        dist = np.full((n_out, k), -1, np.int32) if want_knn else None
+        if P and n_out:
+            self._call(_ffi.MEM_HOST, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0], probs, n_out, opts,
+                       (idx.ctypes.data, dist.ctypes.data) if want_knn else None,
+                       (mq.ctypes.data, mt.ctypes.data, md.ctypes.data, mc.ctypes.data))
+        if none_pass:
+            mc[:] = 0
+        res = BatchResult(mq, mt, md.astype(np.float32), mc, probs[:, 4].copy())
+        return (idx, dist, res) if want_knn else res
+
+    def match_pairs(self, queries: Sequence, trains: Sequence, **kw):
+        """Convenience over :meth:`match_batched` for lists of per-keyframe arrays.  Identical query
+        objects are stored once (loop closing: one keyframe against many candidates)."""
+        if len(queries) != len(trains):
+            raise ValueError("queries and trains must have the same length")
+        P = len(trains)
+        if P == 0:
+            return BatchResult(*(np.zeros(0, np.int32),) * 2, np.zeros(0, np.float32), np.zeros(0, np.int32),
+                               np.zeros(0, np.int32))
+        qs = [_check_desc_np(a, "query") for a in queries]
+        ts = [_check_desc_np(a, "train") for a in trains]
+        tab = np.zeros((P, 6), np.int32)
+        q_rows, q_seen, q_list = 0, {}, []
+        for p, (a, src) in enumerate(zip(qs, queries)):
+            key = id(src)
+            if key not in q_seen:
+                q_seen[key] = q_rows
+                q_list.append(a)
+                q_rows += a.shape[0]
+            tab[p, 0], tab[p, 1] = q_seen[key], a.shape[0]
+        tc = np.array([a.shape[0] for a in ts], np.int64)
+        tab[:, 3] = tc
+        tab[:, 2] = np.concatenate([[0], np.cumsum(tc)[:-1]])
+        tab[:, 4] = np.concatenate([[0], np.cumsum(tab[:, 1].astype(np.int64))[:-1]])
+        qp = np.concatenate(q_list) if q_list else np.zeros((0, DESC_BYTES), np.uint8)
+        tp = np.concatenate(ts)
+        return self.match_batched(qp, tp, tab, **kw)
+
+    # -- torch (device) path --------------------------------------------------------------------------------
+    def _torch_prep(self, x, name):
+        import torch
+        if x.dtype != torch.uint8:
+            raise TypeError(f"{name}: descriptors must be uint8")
+        if not x.is_cuda or x.device.index != self.device:
+            raise ValueError(f"{name}: tensor must live on cuda:{self.device}")
+        if x.dim() != 2 or x.shape[1] != DESC_BYTES:
+            raise ValueError(f"{name}: expected uint8[N, {DESC_BYTES}]")
+        x = x.contiguous()
+        if x.data_ptr() & 15:
+            x = x.clone()
+        return x
+
+    def _stream(self):
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _mask_args_torch(self, opts, mask, window, nq, nt, keep):
+        import torch
+        if mask is not None and window is not None:
+            raise ValueError("give mask or window, not both")
+        if mask is not None:
+            if mask.dtype != torch.uint8 or tuple(mask.shape) != (nq, nt) or not mask.is_cuda:
+                raise ValueError(f"mask must be a CUDA uint8[{nq}, {nt}] tensor")
+            m = mask.contiguous()
+            keep.append(m)
+            opts.mask_kind, opts.mask, opts.mask_row_stride = _ffi.MASK_DENSE, m.data_ptr(), nt
+        if window is not None:
+            q_xy, t_xy, radius = window
+            q_xy = q_xy.to(torch.float32).contiguous()
+            t_xy = t_xy.to(torch.float32).contiguous()
+            if tuple(q_xy.shape) != (nq, 2) or tuple(t_xy.shape) != (nt, 2) or not q_xy.is_cuda or not t_xy.is_cuda:
+                raise ValueError("window = (q_xy float[Q,2], t_xy float[T,2], radius) as CUDA tensors")
+            keep += [q_xy, t_xy]
+            opts.mask_kind, opts.q_xy, opts.t_xy = _ffi.MASK_WINDOW, q_xy.data_ptr(), t_xy.data_ptr()
+            opts.window_radius = float(radius)
+
+    def _knn_torch(self, query, train, k, mask, window):
+        import torch
+        q = self._torch_prep(query, "query")
+        t = self._torch_prep(train, "train")
+        nq, nt = q.shape[0], t.shape[0]
+        self._check_limits(nq, nt, k)
+        idx = torch.full((nq, k), -1, dtype=torch.int32, device=q.device)
+        dist = torch.full((nq, k), -1, dtype=torch.int32, device=q.device)
+        if nq == 0 or nt == 0:
+            return idx, dist
+        opts, _ = self._options(k, None, False, None, False)
+        keep = []
+        self._mask_args_torch(opts, mask, window, nq, nt, keep)
+        probs = np.array([[0, nq, 0, nt, 0, 0]], np.int32)
+        self._call(_ffi.MEM_DEVICE, q.data_ptr(), nq, t.data_ptr(), nt, probs, nq, opts,
+                   (idx.data_ptr(), dist.data_ptr()), None, self._stream())
+        return idx, dist
+
+    def _match_torch(self, query, train, k, ratio, cross_check, mask, window, max_distance, strict):
+        import torch
+        q = self._torch_prep(query, "query")
+        t = self._torch_prep(train, "train")
+        nq, nt = q.shape[0], t.shape[0]
+        self._check_limits(nq, nt, k)
+        opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
+        dev = q.device
+        if nq == 0 or nt == 0 or none_pass:
+            e = torch.zeros(0, dtype=torch.int32, device=dev)
+            return e, e.clone(), torch.zeros(0, dtype=torch.float32, device=dev)
+        keep = []
+        self._mask_args_torch(opts, mask, window, nq, nt, keep)
+        out = torch.empty((3, nq), dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        probs = np.array([[0, nq, 0, nt, 0, 0]], np.int32)
+        self._call(_ffi.MEM_DEVICE, q.data_ptr(), nq, t.data_ptr(), nt, probs, nq, opts, None,
+                   (out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), cnt.data_ptr()), self._stream())
+        n = int(cnt.item())  # the one host sync of this call: the match count
+        return out[0, :n], out[1, :n], out[2, :n].to(torch.float32)
+
+    def match_batched_device(self, q, t, problems: np.ndarray, k=1, ratio=None, cross_check=False,
+                             max_distance=None, strict=False, window=None, want_knn=False, out=None):
+        """Fully asynchronous device form: returns padded CUDA tensors, no host sync.
+
+        out = dict(m=int32[3, n_out], count=int32[P], knn_idx=..., knn_dist=...) may be passed to
+        reuse buffers.  Matches of problem p sit at m[:, out_begin[p] : out_begin[p] + count[p]].
+        """
+        import torch
+        q = self._torch_prep(q, "q_packed")
+        t = self._torch_prep(t, "t_packed")
+        probs = np.ascontiguousarray(problems, np.int32)
+        P = probs.shape[0]
+        n_out = int((probs[:, 4] + probs[:, 1]).max()) if P else 0
+        if k > 2:
+            raise NotImplementedError("k > 2 is not supported by this build")
+        opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
+        if none_pass:
+            opts.max_distance = 0
+            opts.ratio = -1.0
+        keep = []
+        if window is not None:
+            self._mask_args_torch(opts, None, window, q.shape[0], t.shape[0], keep)
+        dev = q.device
+        if out is None:
+            out = {"m": torch.empty((3, max(n_out, 1)), dtype=torch.int32, device=dev),
+                   "count": torch.zeros(max(P, 1), dtype=torch.int32, device=dev)}
+            if want_knn:
+                out["knn_idx"] = torch.empty((max(n_out, 1), k), dtype=torch.int32, device=dev)
+                out["knn_dist"] = torch.empty((max(n_out, 1), k), dtype=torch.int32, device=dev)
+        if P and n_out:
+            m = out["m"]
+            self._call(_ffi.MEM_DEVICE, q.data_ptr(), q.shape[0], t.data_ptr(), t.shape[0], probs, n_out, opts,
+                       (out["knn_idx"].data_ptr(), out["knn_dist"].data_ptr()) if want_knn else None,
+                       (m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(), out["count"].data_ptr()), self._stream())
+        return out
+
+    def _match_batched_torch(self, q, t, problems, k, ratio, cross_check, max_distance, strict, window, want_knn):
+        out = self.match_batched_device(q, t, problems, k, ratio, cross_check, max_distance, strict, window, want_knn)
+        probs = np.ascontiguousarray(problems, np.int32)
+        m = out["m"].cpu().numpy()
+        cnt = out["count"].cpu().numpy()[:probs.shape[0]]
+        res = BatchResult(m[0], m[1], m[2].astype(np.float32), cnt, probs[:, 4].copy())
+        if want_knn:
+            return out["knn_idx"], out["knn_dist"], res
+        return res
+
+
+_default_engines = {}
+_default_lock = threading.Lock()
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Per-(thread, device) engine so concurrent callers never share a handle."""
+    key = (threading.get_ident(), int(device))
+    with _default_lock:
+        e = _default_engines.get(key)
+        if e is None:
+            e = _default_engines[key] = Engine(device)
+        return e

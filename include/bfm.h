@@ -1,0 +1,173 @@
+/*
+ * bfm.h - C ABI of the B200-native brute-force Hamming matcher (libbfm_b200.so).
+ *
+ * This is the drop-in boundary for boslam's one data-parallel hot path: everything
+ * `cv2.BFMatcher_create(cv2.NORM_HAMMING, crossCheck)` does for
+ *     reference slam/tracking.py:45      (matcher construction; same at slam/local_mapping.py:21,
+ *                                         slam/covisibility_graph.py:34, experiments/pnp_*_tracking.py:11)
+ *     reference slam/tracking.py:56      matcher.match(frame.des, kf_ref.desf())      frame <-> ref keyframe
+ *     reference slam/tracking.py:121     matcher.match(frame.des, feats)              frame <-> local map
+ *     reference experiments/pnp_one_way_tracking.py:30, pnp_two_way_tracking.py:42    frame <-> frame
+ * plus the batched keyframe-pair form the local-mapping (slam/local_mapping.py:41-44, a stub) and
+ * loop-closing (slam/loop_closing.py:13-29, stubs) workloads need.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary.
+ *   - descriptors are 256-bit ORB rows: uint8[N][32], row-major, base pointer 16-byte aligned.
+ *   - every function returns a bfm_status (0 = OK); nothing throws.  Text for the last failure
+ *     of a handle: bfm_last_error(handle) (bfm_last_error(NULL) for a failed bfm_create).
+ *   - `mem` says where the caller's buffers live:
+ *       BFM_MEM_DEVICE  all data pointers are device pointers on the handle's GPU, the call is
+ *                       asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *                       handle's own stream) and outputs are valid once the stream has drained.
+ *       BFM_MEM_HOST    all data pointers are host pointers; the call stages through pinned
+ *                       memory, runs on the handle's stream and returns after the results are
+ *                       back in the caller's buffers (this is the e2e path bench.py times).
+ *     The `problems` table and the options struct are always host memory.
+ *   - the caller owns every input and output buffer; the handle owns only its workspace.
+ *   - a handle is NOT re-entrant: one thread at a time per handle.  Different handles are
+ *     independent (own stream, own workspace), which is how boslam's two threads
+ *     (tracking in main, local mapping in a daemon thread, reference slam/main.py:37-47) use it.
+ *   - result semantics are cv2.BFMatcher's (SURVEY.md section 8(c) rules R1-R10):
+ *     distance = popcount(q XOR t); neighbours ascend by (distance, trainIdx); an unfilled
+ *     neighbour slot has idx = -1 and dist = -1; cross-check is the true mutual-nearest test
+ *     with lowest-index ties on both sides; a masked pair never competes.
+ */
+#ifndef BFM_H
+#define BFM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFM_ABI_VERSION 1
+#define BFM_DESC_BYTES 32
+/* per-problem limits of the packed (distance, index) keys the kernels reduce over;
+ * cv2 itself refuses train sets of 2^18 rows or more (matchers.cpp:860, rule R7). */
+#define BFM_MAX_TRAIN_ROWS (1 << 22)
+#define BFM_MAX_QUERY_ROWS (1 << 22)
+#define BFM_MAX_K 16
+
+typedef struct bfm_handle_s *bfm_handle_t;
+
+typedef enum bfm_status {
+    BFM_OK = 0,
+    BFM_ERR_INVALID = 1,     /* bad argument (message says which) */
+    BFM_ERR_CUDA = 2,        /* CUDA runtime error (message carries cudaGetErrorString) */
+    BFM_ERR_NOMEM = 3,
+    BFM_ERR_UNSUPPORTED = 4  /* valid in cv2 but outside this engine (e.g. k > BFM_MAX_K) */
+} bfm_status;
+
+typedef enum bfm_mem { BFM_MEM_HOST = 0, BFM_MEM_DEVICE = 1 } bfm_mem;
+
+typedef enum bfm_mask_kind {
+    BFM_MASK_NONE = 0,
+    BFM_MASK_DENSE = 1,   /* cv2-style uint8[Q][T], non-zero = allowed; single problem only */
+    BFM_MASK_WINDOW = 2   /* allowed iff |qx-tx| < r and |qy-ty| < r (float32), per-row pixel coords */
+} bfm_mask_kind;
+
+/* One (query set, train set) problem of a batch.  Rows index the caller's descriptor arrays,
+ * so several problems may share a query block (loop closing: one keyframe vs N candidates). */
+typedef struct bfm_problem {
+    int32_t q_begin;    /* first query row */
+    int32_t q_count;
+    int32_t t_begin;    /* first train row */
+    int32_t t_count;
+    int32_t out_begin;  /* first output row; problem p owns output rows [out_begin, out_begin+q_count) */
+    int32_t reserved;
+} bfm_problem_t;
+
+typedef struct bfm_options {
+    int32_t k;               /* neighbours per query, 1..BFM_MAX_K (cross_check needs k == 1) */
+    int32_t cross_check;     /* 0/1: keep only mutual nearest neighbours (cv2 crossCheck=True) */
+    int32_t mask_kind;       /* bfm_mask_kind */
+    int32_t max_distance;    /* < 0: off; else keep matches with distance <= max_distance
+                                (slam/tracking.py:121 `<= 30`; pass 29 for :57's strict `< 30`) */
+    double ratio;            /* < 0: off; else keep a row iff it has 2 neighbours and
+                                (double)d1 < ratio * (double)d2  (fp64, as the Python test does) */
+    float window_radius;     /* BFM_MASK_WINDOW */
+    int32_t reserved0;
+    const uint8_t *mask;     /* BFM_MASK_DENSE: [q_count][mask_row_stride] bytes */
+    int64_t mask_row_stride; /* bytes between mask rows (>= t_count) */
+    const float *q_xy;       /* BFM_MASK_WINDOW: float32[n_query_rows][2], same row indexing as q */
+    const float *t_xy;       /* BFM_MASK_WINDOW: float32[n_train_rows][2], same row indexing as t */
+} bfm_options_t;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int bfm_abi_version(void);
+int bfm_create(int device, bfm_handle_t *out);
+int bfm_destroy(bfm_handle_t h);
+const char *bfm_last_error(bfm_handle_t h);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+/*
+ * General batched entry point: replaces one cv2 `match` / `knnMatch` call per problem.
+ *   q, t            descriptor arrays, uint8[n_query_rows][32] / uint8[n_train_rows][32]
+ *   problems        host table of n_problems entries
+ *   n_out_rows      number of output rows (max over problems of out_begin + q_count)
+ * Outputs (each may be NULL to skip it):
+ *   knn_idx/knn_dist  int32[n_out_rows][k]: the raw k-NN table (cv2 knnMatch), -1 = no neighbour
+ *   m_query/m_train/m_dist  int32[n_out_rows]: the filtered match list of problem p is packed,
+ *                     ascending queryIdx, into [out_begin, out_begin + m_count[p]); a row is a
+ *                     match iff it has a neighbour and passes cross_check / ratio / max_distance
+ *                     (cv2 `match` + the caller-side filters of slam/tracking.py:57,121).
+ *                     m_query / m_train are problem-local indices (cv2 queryIdx / trainIdx).
+ *   m_count           int32[n_problems]
+ */
+int bfm_match_batched(bfm_handle_t h, int mem,
+                      const uint8_t *q, int32_t n_query_rows,
+                      const uint8_t *t, int32_t n_train_rows,
+                      const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
+                      const bfm_options_t *opts,
+                      int32_t *knn_idx, int32_t *knn_dist,
+                      int32_t *m_query, int32_t *m_train, int32_t *m_dist, int32_t *m_count,
+                      void *stream);
+
+/* Single-problem conveniences (what slam/tracking.py:56,121 bind to). */
+int bfm_knn(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8_t *t, int32_t nt,
+            const bfm_options_t *opts, int32_t *knn_idx, int32_t *knn_dist, void *stream);
+int bfm_match(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8_t *t, int32_t nt,
+              const bfm_options_t *opts, int32_t *m_query, int32_t *m_train, int32_t *m_dist,
+              int32_t *m_count, void *stream);
+
+/* ---- introspection / tuning (used by bench.py and the tests; not needed by a call site) --- */
+typedef struct bfm_launch_info {
+    int32_t kernels_launched;   /* CUDA kernels launched by the last call on this handle */
+    int32_t scan_grid;          /* CTAs of the distance-scan kernel */
+    int32_t scan_block;         /* threads per CTA */
+    int32_t queries_per_thread; /* register tile R */
+    int32_t popc_mode;          /* POPCs issued per pair (8 plain, 5/4 carry-save variants) */
+    int32_t segments;           /* (query block, train range) work items */
+    int32_t train_rows_per_segment;
+    int32_t reserved;
+    float scan_ms;              /* device time of the scan kernel of the last call when timing is on */
+    float total_ms;             /* device time of all kernels of the last call when timing is on */
+} bfm_launch_info_t;
+
+int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
+/* knob: "popc_mode" {0=auto,8,6,5,4}, "queries_per_thread" {0=auto,1,2,4}, "timing" {0,1},
+ *       "segment_rows" {0=auto, n}, "waves" {0=auto, n} */
+int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
+/* total kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t bfm_kernel_launch_count(bfm_handle_t h);
+
+/* Integer-pipe micro-benchmark: the roofline denominator.
+ * test: 0 POPC, 1 LOP3, 2 IADD3, 3 POPC+LOP3 1:1, 4 POPC+2xLOP3, 5 REDUX.MIN, 6 IMAD, 7 VIMNMX,
+ *       8 POPC+IMAD 1:1, 9 XOR+POPC+IADD pair loop (8:8:4, the plain per-pair mix).
+ * Writes thread-level ops per clock per SM (clock64 based), ops per second (event based) and
+ * the SM clock in MHz implied by the two. */
+int bfm_microbench(int device, int test, int iters, double *ops_per_clk_per_sm,
+                   double *ops_per_s, double *sm_mhz);
+/* Pinned (page-locked) host memory for callers that want full-rate, truly asynchronous H2D/D2H
+ * on the BFM_MEM_HOST path (bench.py's e2e leg stages its inputs in such buffers). */
+int bfm_host_alloc(uint64_t bytes, void **out);
+int bfm_host_free(void *p);
+int bfm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, int *clock_khz,
+                    char *name, int name_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFM_H */

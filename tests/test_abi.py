@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/bfm.h declares, and fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import boslam_b200 as bb
+from boslam_b200 import _ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bfm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bfm_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    L = _ffi.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/bfm.h but not exported"
+    assert sorted(_ffi.EXPORTED_SYMBOLS) == declared
+
+
+def test_abi_version_and_struct_layout():
+    L = _ffi.lib()
+    assert L.bfm_abi_version() == _ffi.ABI_VERSION
+    assert ctypes.sizeof(_ffi.Problem) == 24
+    assert ctypes.sizeof(_ffi.Options) == 64
+    assert _ffi.Options.ratio.offset == 16 and _ffi.Options.mask.offset == 32
+    assert ctypes.sizeof(_ffi.LaunchInfo) == 40
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback():
+    with pytest.raises(bb.BfmError) as ei:
+        bb.Engine(0)
+    assert "no CPU path" in str(ei.value)
+    with pytest.raises(bb.BfmError):
+        bb.match(np.zeros((4, 32), np.uint8), np.zeros((4, 32), np.uint8))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "boslam_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "import cv2" not in src, f
+
+
+def test_make_problems():
+    tab = bb.make_problems([3, 4], [5, 6])
+    assert tab.tolist() == [[0, 3, 0, 5, 0, 0], [3, 4, 5, 6, 3, 0]]
+    tab = bb.make_problems([3, 3], [5, 6], shared_query=True)
+    assert tab[:, 0].tolist() == [0, 0] and tab[:, 4].tolist() == [0, 3]
+
+
+def test_dmatch_surface():
+    m = bb.DMatch(1, 2, 0, 7.0)
+    assert (m.queryIdx, m.trainIdx, m.imgIdx, m.distance) == (1, 2, 0, 7.0)
+    assert bb.NORM_HAMMING == 6
+    mm = bb.BFMatcher_create(bb.NORM_HAMMING, crossCheck=True)  # construction needs no GPU
+    assert mm.crossCheck is True
+    with pytest.raises(ValueError):
+        bb.BFMatcher_create(4)

@@ -1,0 +1,270 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, the committed cv2 golden
+vectors and live cv2.  Bit-exact: indices and integer distances must be identical."""
+import numpy as np
+import pytest
+
+import boslam_b200 as bb
+from boslam_b200 import synth
+from oracle import c_oracle, cv2_reference as ref, hamming_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = bb.Engine(0)
+    yield e
+    e.close()
+
+
+def _eq(a, b, what=""):
+    for x, y in zip(a, b):
+        assert np.array_equal(np.asarray(x), np.asarray(y)), what
+
+
+def _names(golden):
+    return [str(n) for n in golden["names"]]
+
+
+def test_golden_vectors(eng, golden):
+    for name in _names(golden):
+        q, t = golden[f"{name}/q"], golden[f"{name}/t"]
+        for k in (1, 2):
+            idx, dist = eng.knn(q, t, k)
+            assert np.array_equal(idx, golden[f"{name}/knn{k}_idx"]), (name, k)
+            assert np.array_equal(dist, golden[f"{name}/knn{k}_dist"]), (name, k)
+        qi, ti, d = eng.match(q, t, cross_check=True)
+        _eq((qi, ti, d), (golden[f"{name}/cc_q"], golden[f"{name}/cc_t"], golden[f"{name}/cc_d"]), name)
+        idx, dist = eng.knn(q, t, 2, mask=golden[f"{name}/mask"])
+        assert np.array_equal(idx, golden[f"{name}/mknn2_idx"]), name
+        assert np.array_equal(dist, golden[f"{name}/mknn2_dist"]), name
+        rq, rt, rd = eng.match(q, t, k=2, ratio=0.8)
+        _eq((rq, rt, rd), (golden[f"{name}/ratio_q"], golden[f"{name}/ratio_t"], golden[f"{name}/ratio_d"]), name)
+
+
+@pytest.mark.parametrize("pm", [8, 6, 5, 4])
+@pytest.mark.parametrize("r", [1, 2, 4])
+def test_kernel_variants_bit_exact(eng, pm, r):
+    """Every POPC / register-tile variant must return identical results."""
+    eng.set_tuning(popc_mode=pm, queries_per_thread=r)
+    try:
+        q, t, _ = synth.correlated(700, 1300, seed=pm * 10 + r)
+        oi, od = c_oracle.knn(q, t, 2)
+        idx, dist = eng.knn(q, t, 2)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+        _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t))
+        qt, tt = synth.tie_stress(500, pm), synth.tie_stress(900, r + 100)
+        oi, od = c_oracle.knn(qt, tt, 2)
+        idx, dist = eng.knn(qt, tt, 2)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+        _eq(eng.match(qt, tt, cross_check=True), c_oracle.cross_check(qt, tt))
+    finally:
+        eng.set_tuning(popc_mode=0, queries_per_thread=0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_shapes_vs_oracle(eng, seed):
+    rng = np.random.default_rng(seed)
+    nq, nt = int(rng.integers(1, 1500)), int(rng.integers(1, 3000))
+    gens = [
+        lambda: synth.correlated(nq, nt, seed)[:2],
+        lambda: (synth.tie_stress(nq, seed), synth.tie_stress(nt, seed + 50)),
+        lambda: (synth.uniform(nq, seed), synth.duplicate_rows(max(1, nt // 3), seed)),
+    ]
+    for g in gens:
+        q, t = g()
+        for k in (1, 2):
+            oi, od = c_oracle.knn(q, t, k)
+            idx, dist = eng.knn(q, t, k)
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nq, nt, k)
+        _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t), (nq, nt))
+        _eq(eng.match(q, t, k=2, ratio=0.8), orc.match(q, t, k=2, ratio=0.8))
+        _eq(eng.match(q, t, cross_check=True, max_distance=30, strict=True),
+            orc.match(q, t, cross_check_=True, max_distance=30, strict=True))
+        _eq(eng.match(q, t, cross_check=True, max_distance=30),
+            orc.match(q, t, cross_check_=True, max_distance=30))
+
+
+@pytest.mark.skipif(not ref.HAVE_CV2, reason="cv2 not importable")
+def test_live_cv2_reference_call_shapes(eng):
+    """The reference's two live call shapes (slam/tracking.py:56-57 and :121) against live cv2."""
+    q, t, _ = synth.correlated(1000, 1000, 3)                       # BASELINE config 1
+    rq, rt, rd = ref.match(q, t, cross_check=True)
+    keep = rd < 30                                                   # slam/tracking.py:57 (strict)
+    _eq(eng.match(q, t, cross_check=True, max_distance=30, strict=True), (rq[keep], rt[keep], rd[keep]))
+    feats = synth.duplicate_rows(7000, 4)                            # local map with duplicate rows (finding 4)
+    q2 = synth.correlated(2000, len(feats), 5)[0]
+    q2[:1400] = feats[np.random.default_rng(6).integers(0, len(feats), 1400)]
+    rq, rt, rd = ref.match(q2, feats, cross_check=True)
+    keep = rd <= 30                                                  # slam/tracking.py:121 (non-strict)
+    _eq(eng.match(q2, feats, cross_check=True, max_distance=30), (rq[keep], rt[keep], rd[keep]))
+    ri, rdd = ref.knn(q2, feats, 2)
+    idx, dist = eng.knn(q2, feats, 2)
+    assert np.array_equal(idx, ri) and np.array_equal(dist, rdd)
+
+
+def test_drop_in_bfmatcher_object(eng):
+    """BFMatcher_create(...).match returns DMatch objects the call sites can consume unchanged."""
+    q, t, _ = synth.correlated(400, 600, 8)
+    m = bb.BFMatcher_create(bb.NORM_HAMMING, crossCheck=True)
+    ms = m.match(q, t)
+    ms = [_ for _ in ms if _.distance < 30]                          # slam/tracking.py:57
+    inds_f, inds_kf = zip(*((_.queryIdx, _.trainIdx) for _ in ms))   # slam/tracking.py:60
+    oq, ot, od = orc.match(q, t, cross_check_=True, max_distance=30, strict=True)
+    assert list(inds_f) == oq.tolist() and list(inds_kf) == ot.tolist()
+    assert [x.distance for x in ms] == od.astype(float).tolist() and all(x.imgIdx == 0 for x in ms)
+    assert isinstance(ms[0].distance, float)
+    m2 = bb.BFMatcher_create(bb.NORM_HAMMING)
+    rows = m2.knnMatch(q, t, k=2)
+    oi, odd = orc.knn(q, t, 2)
+    assert len(rows) == len(q)
+    assert [[d.trainIdx for d in r] for r in rows] == oi.tolist()
+    assert [[int(d.distance) for d in r] for r in rows] == odd.tolist()
+    if ref.HAVE_CV2:
+        import cv2
+        cm = cv2.BFMatcher_create(cv2.NORM_HAMMING, crossCheck=True).match(q, t)
+        mine = m.match(q, t)
+        assert [(a.queryIdx, a.trainIdx, a.imgIdx, a.distance) for a in cm] == \
+               [(a.queryIdx, a.trainIdx, a.imgIdx, a.distance) for a in mine]
+
+
+def test_masks_and_window(eng):
+    q, t, qxy, txy, _ = synth.window_scene(900, 2500, 9)
+    dense = orc.window_mask(qxy, txy, 15.0)
+    for k in (1, 2):
+        oi, od = c_oracle.knn(q, t, k, dense)
+        idx, dist = eng.knn(q, t, k, window=(qxy, txy, 15.0))
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od), k
+        idx, dist = eng.knn(q, t, k, mask=dense)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od), k
+    _eq(eng.match(q, t, k=2, ratio=0.8, window=(qxy, txy, 15.0)), orc.match(q, t, k=2, ratio=0.8, mask=dense))
+    # cross-check + mask: cv2 refuses it (R6); the numpy restatement is the oracle
+    _eq(eng.match(q, t, cross_check=True, window=(qxy, txy, 15.0)), orc.match(q, t, cross_check_=True, mask=dense))
+    _eq(eng.match(q, t, cross_check=True, mask=dense), c_oracle.cross_check(q, t, dense))
+    m255 = dense * 255                                               # R4: any non-zero allows
+    _eq(eng.knn(q, t, 2, mask=m255), eng.knn(q, t, 2, mask=dense))
+    dense[5, :] = 0                                                  # fully masked query -> no match
+    idx, _ = eng.knn(q, t, 2, mask=dense)
+    assert (idx[5] == -1).all()
+
+
+def test_edge_cases(eng):
+    e = np.zeros((0, 32), np.uint8)
+    t = synth.uniform(5, 1)
+    assert all(len(x) == 0 for x in eng.match(e, t))
+    assert all(len(x) == 0 for x in eng.match(t, e, cross_check=True))
+    idx, dist = eng.knn(t, e, 2)
+    assert idx.shape == (5, 2) and (idx == -1).all() and (dist == -1).all()
+    idx, dist = eng.knn(t, t[:1], 2)                                 # fewer than k candidates (R3)
+    assert (idx[:, 0] == 0).all() and (idx[:, 1] == -1).all() and (dist[:, 1] == -1).all()
+    assert len(eng.match(t, t[:1], k=2, ratio=0.8)[0]) == 0          # rows with < 2 neighbours are dropped
+    z = np.zeros((3, 32), np.uint8)
+    f = np.full((2, 32), 255, np.uint8)
+    idx, dist = eng.knn(z, f, 2)                                     # distance 256, the maximum
+    assert dist.tolist() == [[256, 256]] * 3 and idx.tolist() == [[0, 1]] * 3
+    with pytest.raises(TypeError):
+        eng.match(t.astype(np.float32), t)
+    with pytest.raises(ValueError):
+        eng.match(np.zeros((4, 16), np.uint8), t)
+    with pytest.raises(ValueError):
+        eng.match(t, t, k=2, cross_check=True)
+    nc = np.asfortranarray(synth.uniform(40, 2))                     # non-contiguous input is accepted (R9)
+    _eq(eng.knn(nc, t, 1), orc.knn(np.ascontiguousarray(nc), t, 1))
+    assert len(eng.match(t, t, max_distance=0, strict=True)[0]) == 0  # nothing is < 0
+
+
+def test_batched_pairs(eng):
+    rng = np.random.default_rng(21)
+    qs, ts = [], []
+    for p in range(13):                                              # ragged batch, one empty problem
+        nq, nt = int(rng.integers(1, 700)), int(rng.integers(1, 900))
+        if p == 4:
+            nt = 0
+        q, t, _ = synth.correlated(nq, max(nt, 1), 100 + p)
+        qs.append(q)
+        ts.append(t[:nt])
+    for kw, okw in (({"cross_check": True}, {"cross_check_": True}),
+                    ({"k": 2, "ratio": 0.8}, {"k": 2, "ratio": 0.8}),
+                    ({"k": 1, "max_distance": 40}, {"k": 1, "max_distance": 40})):
+        res = eng.match_pairs(qs, ts, **kw)
+        assert len(res) == 13
+        for p in range(13):
+            _eq(res[p], orc.match(qs[p], ts[p], **okw), (p, kw))
+    # shared query keyframe (loop closing shape): stored once, matched against every candidate
+    q0 = qs[0]
+    res = eng.match_pairs([q0] * 5, ts[:5], k=2, ratio=0.8)
+    for p in range(5):
+        _eq(res[p], orc.match(q0, ts[p], k=2, ratio=0.8), p)
+    res = eng.match_pairs([q0] * 5, ts[:5], cross_check=True)
+    for p in range(5):
+        _eq(res[p], orc.match(q0, ts[p], cross_check_=True), p)
+
+
+def test_batched_knn_table_config3_shape(eng):
+    """BASELINE config 3 shape, reduced: 6 pairs x (2000 x 2000), dense k=2 table + ratio list."""
+    qs, ts = synth.keyframe_pairs(6, 2000, seed=3)
+    qp, tp = np.concatenate(qs), np.concatenate(ts)
+    tab = bb.make_problems([2000] * 6, [2000] * 6)
+    idx, dist, res = eng.match_batched(qp, tp, tab, k=2, ratio=0.8, want_knn=True)
+    for p in range(6):
+        oi, od = c_oracle.knn(qs[p], ts[p], 2)
+        assert np.array_equal(idx[p * 2000:(p + 1) * 2000], oi)
+        assert np.array_equal(dist[p * 2000:(p + 1) * 2000], od)
+        _eq(res[p], orc.match(qs[p], ts[p], k=2, ratio=0.8), p)
+
+
+def test_device_tensor_path(eng):
+    torch = pytest.importorskip("torch")
+    q, t, _ = synth.correlated(800, 1700, 31)
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    idx, dist = eng.knn(qd, td, 2)
+    oi, od = c_oracle.knn(q, t, 2)
+    assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+    got = eng.match(qd, td, cross_check=True, max_distance=30)
+    _eq([g.cpu().numpy() for g in got], orc.match(q, t, cross_check_=True, max_distance=30))
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):                                       # honours torch's current stream
+        idx2, dist2 = eng.knn(qd, td, 2)
+    s.synchronize()
+    assert torch.equal(idx2, idx) and torch.equal(dist2, dist)
+
+
+def test_split_invariance_properties(eng):
+    """Size-independent properties at a larger size: any work split gives the same answer, the
+    cross-check list is the mutual subset of the 1-NN table, and swapping roles mirrors it."""
+    q, t, _ = synth.correlated(3000, 9000, 41)
+    base = eng.knn(q, t, 2)
+    for rows in (32, 100, 1000, 100000):
+        eng.set_tuning(segment_rows=rows)
+        _eq(eng.knn(q, t, 2), base, rows)
+    eng.set_tuning(segment_rows=0)
+    qi, ti, d = eng.match(q, t, cross_check=True)
+    assert np.array_equal(base[0][qi, 0], ti) and np.array_equal(base[1][qi, 0], d.astype(np.int32))
+    ti2, qi2, d2 = eng.match(t, q, cross_check=True)                 # roles swapped
+    o = np.argsort(qi2, kind="stable")
+    assert np.array_equal(qi2[o], qi) and np.array_equal(ti2[o], ti) and np.array_equal(d2[o], d)
+    rev = eng.knn(t, q, 1)
+    assert np.array_equal(rev[0][ti, 0], qi)
+
+
+def test_threads_own_handles():
+    """Two threads, two matchers (tracking + local mapping, slam/main.py:37-47), concurrently."""
+    import threading
+    q, t, _ = synth.correlated(600, 900, 51)
+    want = orc.match(q, t, cross_check_=True)
+    errs = []
+
+    def work():
+        try:
+            m = bb.BFMatcher_create(bb.NORM_HAMMING, crossCheck=True)
+            for _ in range(10):
+                ms = m.match(q, t)
+                assert [x.queryIdx for x in ms] == want[0].tolist()
+                assert [x.trainIdx for x in ms] == want[1].tolist()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work) for _ in range(2)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
