@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py - Hamming pairs/s (+ matched frames/s) of the B200 matcher vs cv2.BFMatcher on host.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W`` (under torchrun for N > 1) prints ONE
+JSON line from rank 0.  ``--impl reference`` times the reference's own implementation of the path
+(cv2.BFMatcher on the box's host cores, reference slam/tracking.py:45,56) on the same config.
+
+Workload (config.workload = "loop_closing"): BASELINE.json configs[3], the configuration the
+metric's "at 1/2/4/8 B200" is quoted on: 256 BoW-candidate keyframe pairs x (2000 x 2000) ORB
+descriptors, knn k=2 + ratio 0.8, one batched launch per step; weak scaling (every rank runs its
+own 256 pairs, then the fixed-shape match tables are all-gathered over NCCL).  A "step" is one
+pass of the hot path over one batch; 1.024 G descriptor pairs per step per GPU.  The tracking
+(configs[1]), frame-to-frame (configs[0]) and local-mapping (configs[2]) shapes are reported as
+extra keys of the same line ("frames").
+
+  value      pairs/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        same metric through the public host API (numpy in -> numpy out, pinned host input
+             buffers, H2D + D2H inside the timed region)
+  roofline   scan kernel vs the measured POPC issue peak (integer pipe; 8 POPC per pair is the
+             algorithmic count) - plus the HBM view for context
+  cpu_baseline  cv2.BFMatcher.knnMatch(k=2) + Python ratio test on the host cores (N = 1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_PAIRS, N_DESC, RATIO = 256, 2000, 0.8
+N_SETS = 6  # rotating input sets: 6 x 32.8 MB = 197 MB > 126 MB L2
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (pynvml; nvidia-smi fallback)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _reason_names(self, mask):
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        return [k for k, v in names.items() if mask & v]
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.reasons.update(self._reason_names(mask))
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(2)
+        if self._nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+def cv2_step(matcher, q, t, tab, ratio):
+    """One reference pass over a batch: what a boslam-style call site would run per pair."""
+    n = 0
+    for p in range(tab.shape[0]):
+        qb, qc, tb, tc = int(tab[p, 0]), int(tab[p, 1]), int(tab[p, 2]), int(tab[p, 3])
+        rows = matcher.knnMatch(q[qb:qb + qc], t[tb:tb + tc], 2)
+        good = [r[0] for r in rows if len(r) == 2 and r[0].distance < ratio * r[1].distance]
+        n += len(good)
+    return n
+
+
+def reference_arm(args):
+    """--impl reference: cv2.BFMatcher on the host cores, same config / metric / unit."""
+    rank = _env_int("RANK", 0)
+    if rank != 0:
+        return
+    import boslam_b200.synth as synth
+    from boslam_b200.engine import make_problems
+    from oracle import cv2_reference as ref
+    sample_pairs = 32  # bounded sample of the 256-pair batch per step (~0.2-0.4 s of CPU work)
+    q, t = synth.keyframe_pair_batch(sample_pairs, N_DESC, seed=1)
+    tab = make_problems([N_DESC] * sample_pairs, [N_DESC] * sample_pairs)
+    pairs = sample_pairs * N_DESC * N_DESC
+    if ref.HAVE_CV2:
+        m = ref.matcher(False)
+        kind, cores = "reference", ref.threads()
+        step = lambda: cv2_step(m, q, t, tab, RATIO)
+    else:  # plain-C port of the same algorithm, single thread
+        from oracle import c_oracle
+        kind, cores = "port", 1
+        step = lambda: sum(len(c_oracle.knn(q[p * N_DESC:(p + 1) * N_DESC], t[p * N_DESC:(p + 1) * N_DESC], 2)[0])
+                           for p in range(sample_pairs))
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = pairs * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "hamming_pairs_per_s", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "loop_closing", "pairs": N_PAIRS, "desc_per_keyframe": N_DESC, "k": 2, "ratio": RATIO,
+                   "sample": f"{sample_pairs} of {N_PAIRS} pairs per step"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample_pairs} pairs x ({N_DESC}x{N_DESC}) per step, cv2 {ref.version()} knnMatch(k=2) + "
+                                   f"Python ratio test, os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def time_device_loop(torch, fn, steps, barrier):
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def extras(eng, torch, steps):
+    """Tracking / frame-to-frame / local-mapping shapes: device-resident and end-to-end frames/s."""
+    import boslam_b200.synth as synth
+    from boslam_b200.engine import make_problems
+    out = {}
+
+    def run(name, host_fn, dev_fn, frames_per_call, pairs_per_call, reps):
+        for _ in range(3):
+            host_fn()
+            dev_fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            host_fn()
+        e2e = (time.perf_counter() - t0) / reps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dev_fn()
+        e1.record()
+        torch.cuda.synchronize()
+        dev = e0.elapsed_time(e1) / reps * 1e-3
+        out[name] = {"frames_per_s_e2e": frames_per_call / e2e, "frames_per_s_device": frames_per_call / dev,
+                     "pairs_per_s_e2e": pairs_per_call / e2e, "pairs_per_s_device": pairs_per_call / dev,
+                     "ms_e2e": e2e * 1e3, "ms_device": dev * 1e3}
+
+    reps = max(steps, 10)
+    # configs[0]: two frames, 1000 descriptors each, crossCheck + gate < 30 (slam/tracking.py:56-57)
+    q, t, _ = synth.correlated(1000, 1000, 11)
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    tab1 = make_problems([1000], [1000])
+    run("frame_to_frame_1000x1000_crosscheck",
+        lambda: eng.match(q, t, cross_check=True, max_distance=30, strict=True),
+        lambda: eng.match_batched_device(qd, td, tab1, cross_check=True, max_distance=30, strict=True),
+        1, 1000 * 1000, reps)
+    # configs[1]: tracking, 2000 frame descriptors vs 20k local-map points, window + ratio 0.8
+    q, t, qxy, txy, _ = synth.window_scene(2000, 20000, 12)
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    qxyd, txyd = torch.from_numpy(qxy).cuda(), torch.from_numpy(txy).cuda()
+    tab2 = make_problems([2000], [20000])
+    run("tracking_2000x20000_window_ratio",
+        lambda: eng.match(q, t, k=2, ratio=RATIO, window=(qxy, txy, 15.0)),
+        lambda: eng.match_batched_device(qd, td, tab2, k=2, ratio=RATIO, window=(qxyd, txyd, 15.0)),
+        1, 2000 * 20000, reps)
+    run("tracking_2000x20000_crosscheck_gate30",  # the reference-faithful variant (slam/tracking.py:121)
+        lambda: eng.match(q, t, cross_check=True, max_distance=30),
+        lambda: eng.match_batched_device(qd, td, tab2, cross_check=True, max_distance=30),
+        1, 2000 * 20000, reps)
+    # configs[2]: local mapping, new keyframe vs 20 covisible keyframes, 2000 descriptors each
+    qb, tb = synth.keyframe_pair_batch(20, 2000, 13)
+    tab3 = make_problems([2000] * 20, [2000] * 20)
+    qbd, tbd = torch.from_numpy(qb).cuda(), torch.from_numpy(tb).cuda()
+    run("local_mapping_20x2000x2000_k2_ratio",
+        lambda: eng.match_batched(qb, tb, tab3, k=2, ratio=RATIO),
+        lambda: eng.match_batched_device(qbd, tbd, tab3, k=2, ratio=RATIO),
+        1, 20 * 2000 * 2000, reps)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import boslam_b200 as bb
+    import boslam_b200.synth as synth
+    from boslam_b200 import _ffi
+    from boslam_b200.engine import PinnedBuffer, make_problems
+
+    world = _env_int("WORLD_SIZE", 1)
+    rank = _env_int("RANK", 0)
+    local_rank = _env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    barrier = (lambda: dist.barrier()) if dist else (lambda: None)
+
+    eng = bb.Engine(local_rank)
+    dev = torch.device("cuda", local_rank)
+    tab = make_problems([N_DESC] * N_PAIRS, [N_DESC] * N_PAIRS)
+    n_out = N_PAIRS * N_DESC
+    pairs_per_step = N_PAIRS * N_DESC * N_DESC
+
+    # -- inputs: N_SETS distinct synthetic batches per rank, pinned on the host + resident in HBM --
+    pinned, dev_sets = [], []
+    for s in range(N_SETS):
+        q, t = synth.keyframe_pair_batch(N_PAIRS, N_DESC, seed=1000 * rank + s)
+        pq, pt = PinnedBuffer(q.shape), PinnedBuffer(t.shape)
+        pq.array[...] = q
+        pt.array[...] = t
+        pinned.append((pq, pt))
+        dev_sets.append((torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)))
+    out = {"m": torch.empty((3, n_out), dtype=torch.int32, device=dev),
+           "count": torch.zeros(N_PAIRS, dtype=torch.int32, device=dev)}
+    gathered_m = torch.empty((world * 3, n_out), dtype=torch.int32, device=dev) if dist else None
+    gathered_c = torch.empty(world * N_PAIRS, dtype=torch.int32, device=dev) if dist else None
+
+    def device_step(i):
+        q, t = dev_sets[i % N_SETS]
+        eng.match_batched_device(q, t, tab, k=2, ratio=RATIO, out=out)
+        if dist:  # the path's one exchange: gather every rank's match tables
+            dist.all_gather_into_tensor(gathered_m, out["m"])
+            dist.all_gather_into_tensor(gathered_c, out["count"])
+
+    # measured POPC issue peak: the roofline denominator (not in MEASURED_PEAKS.json)
+    popc = _ffi.microbench(local_rank, 2000)["popc"]
+
+    sampler = ClockSampler(local_rank)
+    for i in range(args.warmup):
+        device_step(i)
+    launches0 = eng.kernel_launch_count()
+    sampler.start()
+    ms = time_device_loop(torch, device_step, args.steps, barrier)
+    clocks = sampler.stop()
+    launches = eng.kernel_launch_count() - launches0
+    info = eng.launch_info()
+    if dist:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = pairs_per_step * world * args.steps / (ms * 1e-3)
+
+    # -- roofline pass: per-launch scan-kernel time from CUDA events on the launching stream --
+    eng.set_tuning(timing=1)
+    scan_ms = []
+    for i in range(args.steps):
+        q, t = dev_sets[i % N_SETS]
+        eng.match_batched_device(q, t, tab, k=2, ratio=RATIO, out=out)
+        scan_ms.append(eng.launch_info()["scan_ms"])
+    eng.set_tuning(timing=0)
+    scan_avg = float(np.mean(scan_ms))
+    achieved_popc = pairs_per_step * 8 / (scan_avg * 1e-3)
+    hbm_bytes = 32 * 2 * N_PAIRS * N_DESC + 8 * n_out  # descriptors in + packed row state out
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("loop_closing_scan_bytes")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "int_popc", "kernel": "bfm_scan_kernel", "achieved": achieved_popc / 1e9, "peak": popc["ops_per_s"] / 1e9,
+        "unit": "GPOPC/s", "frac": achieved_popc / popc["ops_per_s"], "traffic": traffic,
+        "algorithmic": "8 POPC per descriptor pair x 1.024e9 pairs per launch",
+        "popc_issued_per_pair": info["popc_mode"], "scan_ms": scan_avg, "scan_share_of_step": scan_avg / (ms / args.steps),
+        "peak_source": "measured in this run: bfm_microbench POPC probe (16 POPC/clk/SM x 148 SMs x SM clock)",
+        "popc_per_clk_per_sm": popc["ops_per_clk_per_sm"],
+        "hbm": {"achieved": hbm_bytes / (scan_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_bytes / (scan_avg * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+    }
+
+    # -- e2e: numpy in -> numpy out through the public API, pinned host inputs ---------------------
+    def host_step(i):
+        pq, pt = pinned[i % N_SETS]
+        return eng.match_batched(pq.array, pt.array, tab, k=2, ratio=RATIO)
+
+    for i in range(args.warmup):
+        res = host_step(i)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = host_step(i)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if dist:
+        tms = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_s = float(tms.item())
+    e2e = {"value": pairs_per_step * world * args.steps / e2e_s, "unit": "pairs/s",
+           "h2d_bytes_per_step": int(2 * n_out * 32 + tab.nbytes), "d2h_bytes_per_step": int(3 * n_out * 4 + N_PAIRS * 4),
+           "ms_per_step": e2e_s / args.steps * 1e3, "matches_last_step": int(res.counts.sum())}
+
+    line = {
+        "metric": "hamming_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "loop_closing", "pairs_per_gpu": N_PAIRS, "desc_per_keyframe": N_DESC, "k": 2,
+                   "ratio": RATIO, "pairs_per_step_per_gpu": pairs_per_step,
+                   "l2": f"{N_SETS} rotating input sets, {N_SETS * 2 * n_out * 32 / 1e6:.0f} MB > 126 MB L2",
+                   "parallelism": f"pair-sharded x{world}, all_gather of match tables" if world > 1 else "single GPU"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "launch": {k: info[k] for k in ("scan_grid", "scan_block", "queries_per_thread", "popc_mode",
+                                        "train_rows_per_segment")},
+        "frames_per_s": N_PAIRS * world * args.steps / (ms * 1e-3),
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cv2_reference as ref
+        q, t = pinned[0][0].array, pinned[0][1].array
+        if ref.HAVE_CV2:
+            m = ref.matcher(False)
+            cv2_step(m, q, t, tab[:8], RATIO)
+            reps, t0 = 0, time.perf_counter()
+            while reps < 3 or time.perf_counter() - t0 < 10.0:
+                n_good = cv2_step(m, q, t, tab, RATIO)
+                reps += 1
+                if reps >= 8:
+                    break
+            dt = (time.perf_counter() - t0) / reps
+            line["cpu_baseline"] = {"value": pairs_per_step / dt, "unit": "pairs/s", "cores": ref.threads(), "kind": "reference",
+                                    "sample": f"the full {N_PAIRS}-pair batch x {reps} reps, cv2 {ref.version()} knnMatch(k=2) + Python "
+                                              f"ratio test incl. DMatch construction, os.cpu_count()={os.cpu_count()}",
+                                    "ms_per_step": dt * 1e3, "matches": int(n_good)}
+            assert n_good == int(eng.match_batched(q, t, tab, k=2, ratio=RATIO).counts.sum()), "cv2 and engine disagree"
+        else:
+            from oracle import c_oracle
+            t0 = time.perf_counter()
+            for p in range(8):
+                c_oracle.knn(q[p * N_DESC:(p + 1) * N_DESC], t[p * N_DESC:(p + 1) * N_DESC], 2)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 8 * N_DESC * N_DESC / dt, "unit": "pairs/s", "cores": 1, "kind": "port",
+                                    "sample": "8 of 256 pairs, plain-C oracle, 1 thread"}
+    if rank == 0 and world == 1 and not args.no_extras:
+        line["frames"] = extras(eng, torch, args.steps)
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

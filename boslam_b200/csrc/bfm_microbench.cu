@@ -18,13 +18,23 @@ constexpr int MB_THREADS = 1024;
 constexpr int CHAINS = 8;
 constexpr int UNROLL = 16;
 
+// per-CTA record: [smid, start clock, end clock]; the host takes (max end - min start) per SM,
+// because the two co-resident CTAs of an SM do not get equal issue priority.
+__device__ __forceinline__ void record(long long *cycles, long long t0, long long t1) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    cycles[3 * blockIdx.x + 0] = (long long)smid;
+    cycles[3 * blockIdx.x + 1] = t0;
+    cycles[3 * blockIdx.x + 2] = t1;
+}
+
 template <int TEST>
 __device__ __forceinline__ void step(uint32_t (&x)[CHAINS], uint32_t a, uint32_t b) {
 #pragma unroll
     for (int c = 0; c < CHAINS; ++c) {
         if (TEST == 0) asm volatile("popc.b32 %0, %0;" : "+r"(x[c]));
-        if (TEST == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
-        if (TEST == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(a));
+        if (TEST == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0xE8;" : "+r"(x[c]) : "r"(x[(c + 1) % CHAINS]), "r"(b));
+        if (TEST == 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[c]) : "r"(x[(c + 1) % CHAINS]));
         if (TEST == 3) {
             asm volatile("popc.b32 %0, %0;" : "+r"(x[c]));
             asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[c]) : "r"(a), "r"(b));
@@ -67,7 +77,7 @@ __global__ void __launch_bounds__(MB_THREADS) probe_kernel(int iters, uint32_t a
     for (int c = 0; c < CHAINS; ++c) acc ^= x[c];
     if (acc == 0x12345678u) sink[0] = acc;  // keeps the chains alive
     __syncthreads();
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) record(cycles, t0, t1);
 }
 
 // The plain per-pair instruction mix of the matcher: 8 XOR + 8 POPC + adds + key + min, against
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(MB_THREADS) probe_pair_kernel(int iters, uint3
     const long long t1 = clock64();
     if (best == 0x12345678u) sink[0] = best;
     __syncthreads();
-    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) record(cycles, t0, t1);
 }
 
 typedef void (*ProbeFn)(int, uint32_t, uint32_t, uint32_t *, long long *);
@@ -128,7 +138,7 @@ extern "C" int bfm_microbench(int device, int test, int iters, double *ops_per_c
     uint32_t *sink = nullptr;
     long long *cyc = nullptr;
     cudaEvent_t e0, e1;
-    if (cudaMalloc(&sink, 64) != cudaSuccess || cudaMalloc(&cyc, sizeof(long long) * ctas) != cudaSuccess) return BFM_ERR_NOMEM;
+    if (cudaMalloc(&sink, 64) != cudaSuccess || cudaMalloc(&cyc, sizeof(long long) * 3 * ctas) != cudaSuccess) return BFM_ERR_NOMEM;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     fn<<<ctas, MB_THREADS>>>(std::max(iters / 8, 1), 3u, 5u, sink, cyc);  // warm-up
@@ -142,11 +152,22 @@ extern "C" int bfm_microbench(int device, int test, int iters, double *ops_per_c
     } else {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        std::vector<long long> h(ctas);
-        cudaMemcpy(h.data(), cyc, sizeof(long long) * ctas, cudaMemcpyDeviceToHost);
-        double mean_cyc = 0;
-        for (long long c : h) mean_cyc += (double)c;
-        mean_cyc /= ctas;
+        std::vector<long long> h(3 * (size_t)ctas);
+        cudaMemcpy(h.data(), cyc, sizeof(long long) * 3 * ctas, cudaMemcpyDeviceToHost);
+        // per SM: busy span = max(end) - min(start) over its CTAs, work = CTAs it ran
+        std::vector<long long> lo(1024, -1), hi(1024, -1);
+        std::vector<int> cnt(1024, 0);
+        for (int i = 0; i < ctas; ++i) {
+            const int sm = (int)(h[3 * i] & 1023);
+            lo[sm] = lo[sm] < 0 ? h[3 * i + 1] : std::min(lo[sm], h[3 * i + 1]);
+            hi[sm] = std::max(hi[sm], h[3 * i + 2]);
+            ++cnt[sm];
+        }
+        double rate_sum = 0;  // mean over SMs of CTAs-per-cycle
+        int sms = 0;
+        for (int sm = 0; sm < 1024; ++sm)
+            if (cnt[sm]) { rate_sum += (double)cnt[sm] / (double)(hi[sm] - lo[sm]); ++sms; }
+        const double mean_cyc = 2.0 * sms / rate_sum;  // cycles an SM needs for 2 CTAs' work
         // per-thread ops: test 9 counts the 8 POPCs of a pair as the unit (POPC/clk/SM of the mix)
         const double per_thread = test == 9 ? (double)iters * UNROLL * 8.0
                                             : (double)iters * UNROLL * CHAINS * ops_per_step(test);

@@ -1,0 +1,136 @@
+"""Keyframe-pair batches sharded over the GPUs of one box.
+
+Every (query keyframe, train keyframe) problem is independent, so rank r takes a contiguous
+block of the pair list, runs its own engine on its own GPU and the only exchange is one
+all-gather of the fixed-shape result tables (NCCL over NVLink).  The reductions are integer mins
+over packed keys, so the gathered result is byte-identical for any world size.
+
+The compute callable is injected so the host logic (partition, gather layout) can be exercised
+on CPU with the gloo backend in tests; the product binding is :class:`ShardedMatcher`, which
+always runs the CUDA engine.
+"""
+from __future__ import annotations
+
+from typing import Sequence, Tuple
+
+import numpy as np
+
+
+def partition_pairs(costs: Sequence[int], world_size: int):
+    """Contiguous block partition of the pair list into ``world_size`` shards of near-equal total
+    cost (cost = Q*T of a pair).  Returns [(begin, end)] per rank; equal-cost pairs split evenly."""
+    n = len(costs)
+    c = np.asarray(costs, dtype=np.float64)
+    if n == 0:
+        return [(0, 0)] * world_size
+    if np.all(c == c[0]):
+        base, rem = divmod(n, world_size)
+        out, b = [], 0
+        for r in range(world_size):
+            e = b + base + (1 if r < rem else 0)
+            out.append((b, e))
+            b = e
+        return out
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    total = cum[-1]
+    out, b = [], 0
+    for r in range(world_size):
+        if r == world_size - 1:
+            e = n
+        else:
+            # the cut whose cumulative cost is closest to this rank's share of the total
+            e = max(int(np.argmin(np.abs(cum - total * (r + 1) / world_size))), b)
+        out.append((b, e))
+        b = e
+    return out
+
+
+def gather_fixed(local, group=None):
+    """All-gather a rank-local torch tensor whose shape is the same on every rank; returns the
+    concatenation along dim 0 (rank order).  One ``all_gather_into_tensor`` call."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    out = torch.empty((ws * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+def gather_ragged(local, group=None):
+    """All-gather along dim 0 of tensors whose dim-0 length differs per rank (ragged pair blocks):
+    lengths are exchanged first, shards are padded to the maximum, gathered once and trimmed."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    lens = torch.empty(ws, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(lens, n, group=group)
+    lens = lens.cpu().tolist()
+    m = max(lens) if lens else 0
+    pad = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = gather_fixed(pad, group)
+    parts = [out[r * m:r * m + lens[r]] for r in range(ws)]
+    return torch.cat(parts, dim=0) if parts else out, lens
+
+
+class ShardedMatcher:
+    """Batched k-NN over a global list of keyframe pairs, sharded across the process group.
+
+    ``knn_pairs(queries, trains, k)``: every rank passes the same global pair list (host arrays);
+    each rank uploads and matches only its block, then the dense ``[rows, k]`` index / distance
+    tables are all-gathered so every rank holds the full result.
+    """
+
+    def __init__(self, engine=None, device=None, group=None, compute=None):
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._compute = compute
+        if compute is None:
+            from .engine import Engine
+            import torch
+            self.device = torch.cuda.current_device() if device is None else device
+            self.engine = engine if engine is not None else Engine(self.device)
+            self._compute = self._engine_compute
+            self._tdev = torch.device("cuda", self.device)
+        else:
+            import torch
+            self._tdev = torch.device("cpu")
+
+    def _engine_compute(self, qs, ts, k):
+        """Local block through the CUDA engine -> (idx, dist) int32 [rows, k] torch tensors on the GPU."""
+        import torch
+        from .engine import make_problems
+        if not qs:
+            z = torch.zeros((0, k), dtype=torch.int32, device=self._tdev)
+            return z, z.clone()
+        qp = torch.from_numpy(np.concatenate(qs)).to(self._tdev)
+        tp = torch.from_numpy(np.concatenate(ts)).to(self._tdev)
+        tab = make_problems([len(a) for a in qs], [len(a) for a in ts])
+        out = self.engine.match_batched_device(qp, tp, tab, k=k, want_knn=True)
+        n = int(tab[:, 1].sum())
+        return out["knn_idx"][:n], out["knn_dist"][:n]
+
+    def knn_pairs(self, queries, trains, k: int = 2) -> Tuple[list, list]:
+        import torch
+        costs = [len(q) * len(t) for q, t in zip(queries, trains)]
+        blocks = partition_pairs(costs, self.world)
+        b, e = blocks[self.rank]
+        idx, dist_ = self._compute(list(queries[b:e]), list(trains[b:e]), k)
+        idx = torch.as_tensor(idx, device=self._tdev)
+        dist_ = torch.as_tensor(dist_, device=self._tdev)
+        both = torch.stack([idx, dist_], dim=1)  # [rows, 2, k]
+        rows = [sum(len(q) for q in queries[bb:ee]) for bb, ee in blocks]
+        if len(set(rows)) == 1:
+            full = gather_fixed(both, self.group)
+        else:
+            full, _ = gather_ragged(both, self.group)
+        full = full.cpu().numpy()
+        out_i, out_d, o = [], [], 0
+        for q in queries:
+            out_i.append(full[o:o + len(q), 0])
+            out_d.append(full[o:o + len(q), 1])
+            o += len(q)
+        return out_i, out_d

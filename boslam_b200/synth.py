@@ -83,3 +83,25 @@ def keyframe_pairs(n_pairs: int, n_desc: int, seed: int = 0, shared_query: bool 
         qs.append(q)
         ts.append(t)
     return qs, ts
+
+
+def keyframe_pair_batch(n_pairs: int, n_desc: int, seed: int = 0, p_flip: float = 0.04, frac_true: float = 0.7):
+    """Vectorised :func:`keyframe_pairs`: packed (query uint8[P*n,32], train uint8[P*n,32]) with
+    problem p in rows [p*n, (p+1)*n) of both arrays.  Same statistics as :func:`correlated`
+    (70 % of queries are a noisy copy of a train row of the same pair)."""
+    rng = np.random.default_rng(seed)
+    total = n_pairs * n_desc
+    train = rng.integers(0, 256, (total, DESC_BYTES), dtype=np.uint8)
+    query = rng.integers(0, 256, (total, DESC_BYTES), dtype=np.uint8)
+    if total == 0:
+        return query, train
+    is_true = rng.random(total) < frac_true
+    src = rng.integers(0, n_desc, total) + np.repeat(np.arange(n_pairs) * n_desc, n_desc)
+    # sparse bit flips: ~p_flip*256 flipped bits per true row, drawn as positions
+    rows = np.nonzero(is_true)[0]
+    query[rows] = train[src[rows]]
+    n_flips = rng.binomial(DESC_BYTES * 8, p_flip, len(rows))
+    r_idx = np.repeat(rows, n_flips)
+    bit = rng.integers(0, DESC_BYTES * 8, len(r_idx))
+    np.bitwise_xor.at(query, (r_idx, bit >> 3), (1 << (bit & 7)).astype(np.uint8))
+    return query, train
