@@ -291,7 +291,7 @@ def main():
             dist.all_gather_into_tensor(gathered_c, out["count"])
 
     # measured POPC issue peak: the roofline denominator (not in MEASURED_PEAKS.json)
-    popc = _ffi.microbench(local_rank, 2000)["popc"]
+    popc = _ffi.microbench(local_rank, 4000, tests=("popc",))["popc"]
 
     sampler = ClockSampler(local_rank)
     for i in range(args.warmup):

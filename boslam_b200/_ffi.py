@@ -109,11 +109,13 @@ MICROBENCH_TESTS = {
 }
 
 
-def microbench(device: int = 0, iters: int = 2000):
+def microbench(device: int = 0, iters: int = 2000, tests=None):
     """Integer-pipe issue rates (thread ops / clk / SM, ops / s, implied SM MHz) per probe."""
     L = lib()
     out = {}
     for name, t in MICROBENCH_TESTS.items():
+        if tests is not None and name not in tests:
+            continue
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
         rc = L.bfm_microbench(device, t, iters, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
         if rc != BFM_OK:

@@ -43,6 +43,8 @@ ScanFn pick_pm(int pm) {
         case 4: return scan_fn<R, MODE, MASK, 4>();
         case 5: return scan_fn<R, MODE, MASK, 5>();
         case 6: return scan_fn<R, MODE, MASK, 6>();
+        case 40: return scan_fn<R, MODE, MASK, 40>();
+        case 50: return scan_fn<R, MODE, MASK, 50>();
         default: return scan_fn<R, MODE, MASK, 8>();
     }
 }
@@ -103,7 +105,7 @@ struct bfm_handle_s {
     int64_t launches = 0;
     std::vector<Segment> segs_host;
     std::vector<Problem> probs_host;
-    int occ_cache[3][3][3][4];  // [R idx][mode][mask][pm idx] -> CTAs per SM (0 = unknown)
+    int occ_cache[3][3][3][6];  // [R idx][mode][mask][pm idx] -> CTAs per SM (0 = unknown)
 };
 
 namespace {
@@ -137,7 +139,7 @@ int ensure(bfm_handle_t h, DevBuf &b, size_t bytes) {
     return BFM_OK;
 }
 
-int pm_index(int pm) { return pm == 4 ? 0 : pm == 5 ? 1 : pm == 6 ? 2 : 3; }
+int pm_index(int pm) { return pm == 4 ? 0 : pm == 5 ? 1 : pm == 6 ? 2 : pm == 40 ? 4 : pm == 50 ? 5 : 3; }
 int r_index(int r) { return r == 1 ? 0 : r == 2 ? 1 : 2; }
 
 int occupancy(bfm_handle_t h, int r, int mode, int mask, int pm, int *out) {
@@ -246,7 +248,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     // -- choose the kernel variant ----------------------------------------------------------------
     const int mode = o->cross_check ? 1 : ((o->k >= 2 || o->ratio >= 0) ? 2 : 0);
     const int mask = o->mask_kind;
-    const int pm = h->popc_mode ? h->popc_mode : 8;
+    const int pm = h->popc_mode ? h->popc_mode : 40;  // measured best for every mode: profiles/sweep_r01.md
     int r = h->qpt;
     int slots = 0, seg_rows = 0;
     if (r != 1 && r != 2 && r != 4) {
@@ -547,7 +549,7 @@ int bfm_match_batched(bfm_handle_t h, int mem, const uint8_t *q, int32_t n_query
     CU_TRY(h, cudaSetDevice(h->device));
     if (mem == BFM_MEM_DEVICE)
         return run_device(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, knn_idx,
-                          knn_dist, m_query, m_train, m_dist, m_count, stream ? static_cast<cudaStream_t>(stream) : h->stream);
+                          knn_dist, m_query, m_train, m_dist, m_count, stream == BFM_STREAM_OWN ? h->stream : static_cast<cudaStream_t>(stream));
     if (mem == BFM_MEM_HOST)
         return run_host(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, knn_idx,
                         knn_dist, m_query, m_train, m_dist, m_count);
@@ -579,7 +581,8 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     if (!h || !knob) return BFM_ERR_INVALID;
     const std::string k(knob);
     if (k == "popc_mode") {
-        if (value != 0 && value != 4 && value != 5 && value != 6 && value != 8) return fail(h, BFM_ERR_INVALID, "popc_mode must be 0,4,5,6,8");
+        if (value != 0 && value != 4 && value != 5 && value != 6 && value != 8 && value != 40 && value != 50)
+            return fail(h, BFM_ERR_INVALID, "popc_mode must be 0,4,5,6,8,40,50");
         h->popc_mode = value;
     } else if (k == "queries_per_thread") {
         if (value != 0 && value != 1 && value != 2 && value != 4) return fail(h, BFM_ERR_INVALID, "queries_per_thread must be 0,1,2,4");

@@ -94,29 +94,71 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
-// PM = POPC instructions issued per pair.  PM == 8 is the plain XOR+POPC form; the others run a
-// carry-save adder (Harley-Seal) tree on LOP3 first, trading quarter-rate POPCs for full-rate
-// logic ops.  All variants return the exact popcount of the 256-bit XOR.
+// PM selects how the 256-bit popcount is evaluated (all variants are exact):
+//   8        plain: 8 XOR + 8 POPC
+//   6, 5, 4  carry-save adder (Harley-Seal) tree on LOP3 over the 8 XOR words, 6/5/4 POPCs
+//   50, 40   the same trees over a TRANSFORMED descriptor.  Both sides are stored as
+//              (w0, w1, w3, w4, w7, w0^w1^w2, w3^w4^w5, w0^...^w6)
+//            which is linear over XOR, so the sum word of every first/second level adder is ONE
+//            XOR of precomputed words, and the carry is a LOP3 of (x_a, x_b, sum) because the
+//            third input is recoverable: maj(a, b, a^b^s) = LUT 0xD4.  11 (PM 50) or 13 (PM 40)
+//            LOP3 per pair instead of 14 / 16, and w2, w5, w6 are never formed.
+// POPC issues at 16 lanes/clk/SM and LOP3 at 64 (measured, profiles/popc_peak_r01.json), so the
+// trade is worth it until the ALU pipe becomes the limiter.
+__device__ __forceinline__ uint32_t carry_from_sum(uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t r;  // maj(a, b, a ^ b ^ s)
+    asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+}
+
+__host__ __device__ constexpr bool pm_transformed(int pm) { return pm >= 40; }
+
+// in: the 8 words of a descriptor; out: the transformed descriptor (see above)
+__device__ __forceinline__ void transform_desc(uint32_t (&w)[8]) {
+    const uint32_t s0 = xor3(w[0], w[1], w[2]);
+    const uint32_t s1 = xor3(w[3], w[4], w[5]);
+    const uint32_t s2 = xor3(s0, s1, w[6]);
+    const uint32_t w3 = w[3], w4 = w[4], w7 = w[7];
+    w[2] = w3; w[3] = w4; w[4] = w7; w[5] = s0; w[6] = s1; w[7] = s2;
+}
+
 template <int PM>
 __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint32_t (&t)[8]) {
-    uint32_t x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = q[i] ^ t[i];
-    if constexpr (PM == 8) {
-        return (__popc(x[0]) + __popc(x[1]) + __popc(x[2])) + (__popc(x[3]) + __popc(x[4]) + __popc(x[5])) +
-               (__popc(x[6]) + __popc(x[7]));
+    if constexpr (pm_transformed(PM)) {
+        // layout: [0]=w0 [1]=w1 [2]=w3 [3]=w4 [4]=w7 [5]=S012 [6]=S345 [7]=S0..6
+        const uint32_t x0 = q[0] ^ t[0], x1 = q[1] ^ t[1], s0 = q[5] ^ t[5];
+        const uint32_t c0 = carry_from_sum(x0, x1, s0);
+        const uint32_t x3 = q[2] ^ t[2], x4 = q[3] ^ t[3], s1 = q[6] ^ t[6];
+        const uint32_t c1 = carry_from_sum(x3, x4, s1);
+        const uint32_t s2 = q[7] ^ t[7];
+        const uint32_t c2 = carry_from_sum(s0, s1, s2);   // maj(s0, s1, x6)
+        const uint32_t x7 = q[4] ^ t[4];
+        if constexpr (PM == 50) {
+            return (__popc(s2) + __popc(x7)) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
+        } else {  // PM == 40
+            const uint32_t s3 = xor3(c0, c1, c2), c3 = maj3(c0, c1, c2);
+            return (__popc(s2) + __popc(x7)) + 2u * __popc(s3) + 4u * __popc(c3);
+        }
     } else {
-        const uint32_t s0 = xor3(x[0], x[1], x[2]), c0 = maj3(x[0], x[1], x[2]);
-        const uint32_t s1 = xor3(x[3], x[4], x[5]), c1 = maj3(x[3], x[4], x[5]);
-        if constexpr (PM == 6) {
-            return (__popc(s0) + __popc(s1) + __popc(x[6])) + __popc(x[7]) + 2u * (__popc(c0) + __popc(c1));
+        uint32_t x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = q[i] ^ t[i];
+        if constexpr (PM == 8) {
+            return (__popc(x[0]) + __popc(x[1]) + __popc(x[2])) + (__popc(x[3]) + __popc(x[4]) + __popc(x[5])) +
+                   (__popc(x[6]) + __popc(x[7]));
         } else {
-            const uint32_t s2 = xor3(s0, s1, x[6]), c2 = maj3(s0, s1, x[6]);
-            if constexpr (PM == 5) {
-                return (__popc(s2) + __popc(x[7])) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
-            } else {  // PM == 4
-                const uint32_t s3 = xor3(c0, c1, c2), c3 = maj3(c0, c1, c2);
-                return (__popc(s2) + __popc(x[7])) + 2u * __popc(s3) + 4u * __popc(c3);
+            const uint32_t s0 = xor3(x[0], x[1], x[2]), c0 = maj3(x[0], x[1], x[2]);
+            const uint32_t s1 = xor3(x[3], x[4], x[5]), c1 = maj3(x[3], x[4], x[5]);
+            if constexpr (PM == 6) {
+                return (__popc(s0) + __popc(s1) + __popc(x[6])) + __popc(x[7]) + 2u * (__popc(c0) + __popc(c1));
+            } else {
+                const uint32_t s2 = xor3(s0, s1, x[6]), c2 = maj3(s0, s1, x[6]);
+                if constexpr (PM == 5) {
+                    return (__popc(s2) + __popc(x[7])) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
+                } else {  // PM == 4
+                    const uint32_t s3 = xor3(c0, c1, c2), c3 = maj3(c0, c1, c2);
+                    return (__popc(s2) + __popc(x[7])) + 2u * __popc(s3) + 4u * __popc(c3);
+                }
             }
         }
     }
@@ -127,15 +169,21 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
 // K     1 or 2 neighbours tracked per query
 // CROSS also reduce the per-train column key (cross-check); K must be 1
 // MASK  0 none, 1 dense uint8 mask, 2 projection window
-// PM    POPCs per pair (8 / 6 / 5 / 4)
-// NT    threads per CTA
+// PM    popcount evaluation (see hamming256)
+// NT    threads per CTA (== TT: one thread transforms one staged train row)
+//
+// Pipeline per CTA: chunk c+2 is fetched by TMA while chunk c is scanned; one __syncthreads per
+// chunk.  Shared memory: 2 x 4 KB train rows, 2 x 1 KB pixel coords (window), 2 x 2 KB column
+// keys (cross-check).
 template <int R, int K, bool CROSS, int MASK, int PM, int NT>
 __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
     constexpr int NW = NT / 32;
+    constexpr bool XF = pm_transformed(PM);
+    static_assert(NT == TT, "one thread per staged train row");
     __shared__ __align__(128) uint4 s_t[2][TT * 2];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ float2 s_xy[MASK == 2 ? 2 : 1][MASK == 2 ? TT : 1];
-    __shared__ uint32_t s_col[CROSS ? NW : 1][CROSS ? TT : 1];
+    __shared__ uint32_t s_col[CROSS ? 2 : 1][CROSS ? NW : 1][CROSS ? TT : 1];
 
     const Segment sg = p.segs[blockIdx.x];
     const int tid = threadIdx.x;
@@ -157,6 +205,7 @@ __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
         const uint4 b = __ldg(p.q + 2 * (size_t)row + 1);
         qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
         qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
+        if (XF) transform_desc(qw[r]);
         ibias[r] = (uint32_t)(sg.q_local0 + lr);
         if (MASK == 0 && !valid[r]) ibias[r] = KEY_DEAD;
         if (MASK == 2) {
@@ -172,39 +221,46 @@ __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
 #pragma unroll
     for (int r = 0; r < R; ++r) { b1[r] = KEY_NONE; b2[r] = KEY_NONE; }
 
-    // -- double-buffered TMA pipeline over the segment's train rows -------------------------------
     const int nchunks = (sg.t_count + TT - 1) / TT;
+    auto chunk_rows = [&](int c) { return min(TT, sg.t_count - c * TT); };
+    auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer c&1
+        const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes
+        mbar_expect_tx(&s_bar[c & 1], bytes);
+        bulk_g2s(&s_t[c & 1][0], p.t + 2 * (size_t)(sg.t_row0 + c * TT), bytes, &s_bar[c & 1]);
+    };
+    auto stage_xy = [&](int c) {
+        if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldg(p.t_xy + sg.t_row0 + c * TT + tid);
+    };
+    auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
+        mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
+        if (XF && tid < chunk_rows(c)) {
+            const uint4 a = s_t[c & 1][2 * tid], b = s_t[c & 1][2 * tid + 1];
+            uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            transform_desc(w);
+            s_t[c & 1][2 * tid] = make_uint4(w[0], w[1], w[2], w[3]);
+            s_t[c & 1][2 * tid + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    };
+
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
     }
-    if (MASK == 2) {
-        for (int j = tid; j < min(TT, sg.t_count); j += NT) s_xy[0][j] = __ldg(p.t_xy + sg.t_row0 + j);
-    }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t bytes = (uint32_t)min(TT, sg.t_count) * 32u;
-        mbar_expect_tx(&s_bar[0], bytes);
-        bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)sg.t_row0, bytes, &s_bar[0]);
+        fetch(0);
+        if (nchunks > 1) fetch(1);
     }
+    stage_xy(0);
+    if (nchunks > 1) stage_xy(1);
+    land(0);
+    __syncthreads();
 
     for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1;
-        const int n = min(TT, sg.t_count - c * TT);
-        if (c + 1 < nchunks) {
-            // buffer b^1 was released by the __syncthreads that closed iteration c-1
-            const int n1 = min(TT, sg.t_count - (c + 1) * TT);
-            if (tid == 0) {
-                mbar_expect_tx(&s_bar[b ^ 1], (uint32_t)n1 * 32u);
-                bulk_g2s(&s_t[b ^ 1][0], p.t + 2 * (size_t)(sg.t_row0 + (c + 1) * TT), (uint32_t)n1 * 32u, &s_bar[b ^ 1]);
-            }
-            if (MASK == 2) {
-                for (int j = tid; j < n1; j += NT) s_xy[b ^ 1][j] = __ldg(p.t_xy + sg.t_row0 + (c + 1) * TT + j);
-            }
-        }
-        mbar_wait(&s_bar[b], (uint32_t)((c >> 1) & 1));
-
+        const int n = chunk_rows(c);
         const uint32_t jbase = (uint32_t)(sg.t_local0 + c * TT);
 #pragma unroll 2
         for (int j = 0; j < n; ++j) {
@@ -233,19 +289,24 @@ __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
             }
             if (CROSS) {
                 ck = __reduce_min_sync(0xffffffffu, ck);
-                if (lane == 0) s_col[warp][j] = ck;
+                if (lane == 0) s_col[b][warp][j] = ck;
             }
         }
+        if (c + 1 < nchunks) land(c + 1);
+        __syncthreads();   // chunk c fully consumed: s_t[b] / s_xy[b] free, s_col[b] complete, chunk c+1 ready
+        if (c + 2 < nchunks) {
+            if (tid == 0) fetch(c + 2);
+            stage_xy(c + 2);
+        }
         if (CROSS) {
-            __syncthreads();
+            // s_col[b] is next written in iteration c+2, i.e. after the barrier of iteration c+1
             for (int j = tid; j < n; j += NT) {
-                uint32_t m = s_col[0][j];
+                uint32_t m = s_col[b][0][j];
 #pragma unroll
-                for (int w = 1; w < NW; ++w) m = min(m, s_col[w][j]);
+                for (int w = 1; w < NW; ++w) m = min(m, s_col[b][w][j]);
                 if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)sg.col0 + sg.t_local0 + c * TT + j, m);
             }
         }
-        __syncthreads();
     }
 
     // -- commit: associative min-merge into the global row state ---------------------------------

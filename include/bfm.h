@@ -18,8 +18,9 @@
  *     of a handle: bfm_last_error(handle) (bfm_last_error(NULL) for a failed bfm_create).
  *   - `mem` says where the caller's buffers live:
  *       BFM_MEM_DEVICE  all data pointers are device pointers on the handle's GPU, the call is
- *                       asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
- *                       handle's own stream) and outputs are valid once the stream has drained.
+ *                       asynchronous on `stream` (a cudaStream_t passed as void*; NULL is CUDA's
+ *                       legacy default stream, exactly as in the runtime API; BFM_STREAM_OWN =
+ *                       the handle's own stream) and outputs are valid once it has drained.
  *       BFM_MEM_HOST    all data pointers are host pointers; the call stages through pinned
  *                       memory, runs on the handle's stream and returns after the results are
  *                       back in the caller's buffers (this is the e2e path bench.py times).
@@ -49,6 +50,7 @@ extern "C" {
 #define BFM_MAX_TRAIN_ROWS (1 << 22)
 #define BFM_MAX_QUERY_ROWS (1 << 22)
 #define BFM_MAX_K 16
+#define BFM_STREAM_OWN ((void *)(intptr_t)-1) /* `stream` value meaning "the handle's own stream" */
 
 typedef struct bfm_handle_s *bfm_handle_t;
 
@@ -138,7 +140,7 @@ typedef struct bfm_launch_info {
     int32_t scan_grid;          /* CTAs of the distance-scan kernel */
     int32_t scan_block;         /* threads per CTA */
     int32_t queries_per_thread; /* register tile R */
-    int32_t popc_mode;          /* POPCs issued per pair (8 plain, 5/4 carry-save variants) */
+    int32_t popc_mode;          /* popcount evaluation: 8 plain, 6/5/4 carry-save, 50/40 transformed carry-save */
     int32_t segments;           /* (query block, train range) work items */
     int32_t train_rows_per_segment;
     int32_t reserved;
@@ -147,7 +149,7 @@ typedef struct bfm_launch_info {
 } bfm_launch_info_t;
 
 int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
-/* knob: "popc_mode" {0=auto,8,6,5,4}, "queries_per_thread" {0=auto,1,2,4}, "timing" {0,1},
+/* knob: "popc_mode" {0=auto,8,6,5,4,50,40}, "queries_per_thread" {0=auto,1,2,4}, "timing" {0,1},
  *       "segment_rows" {0=auto, n}, "waves" {0=auto, n} */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */

@@ -42,7 +42,7 @@ def test_golden_vectors(eng, golden):
         _eq((rq, rt, rd), (golden[f"{name}/ratio_q"], golden[f"{name}/ratio_t"], golden[f"{name}/ratio_d"]), name)
 
 
-@pytest.mark.parametrize("pm", [8, 6, 5, 4])
+@pytest.mark.parametrize("pm", [8, 6, 5, 4, 50, 40])
 @pytest.mark.parametrize("r", [1, 2, 4])
 def test_kernel_variants_bit_exact(eng, pm, r):
     """Every POPC / register-tile variant must return identical results."""

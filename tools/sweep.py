@@ -39,7 +39,7 @@ def main():
         pairs = P * nq * nt
         for mode, kw in (("k2", dict(k=2)), ("k1", dict(k=1)), ("cross", dict(k=1, cross_check=True))):
             for r in (4, 2, 1):
-                for pm in (8, 6, 5, 4):
+                for pm in (8, 5, 4, 50, 40):
                     for waves in (0,):
                         eng.set_tuning(queries_per_thread=r, popc_mode=pm, waves=waves)
                         obuf = {}
