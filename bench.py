@@ -343,9 +343,11 @@ def main():
     }
 
     # -- e2e: numpy in -> numpy out through the public API, pinned host inputs ---------------------
+    host_out = bb.HostBatchBuffers(n_out, N_PAIRS, k=2)  # pinned result arrays, reused every step
+
     def host_step(i):
         pq, pt = pinned[i % N_SETS]
-        return eng.match_batched(pq.array, pt.array, tab, k=2, ratio=RATIO)
+        return eng.match_batched(pq.array, pt.array, tab, k=2, ratio=RATIO, out=host_out)
 
     for i in range(args.warmup):
         res = host_step(i)

@@ -10,7 +10,9 @@
 #include "../../include/bfm.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -98,13 +100,22 @@ struct bfm_handle_s {
     size_t h_out_cap = 0;
 
     // tuning knobs
-    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0;
+    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
     bfm_launch_info_t info{};
     int64_t launches = 0;
     std::vector<Segment> segs_host;
+    std::vector<int> seg_begin;  // first segment of every problem (+ end sentinel)
     std::vector<Problem> probs_host;
+    // plan cache + workspace hygiene
+    bool plan_valid = false, state_clean = false;
+    int plan_sig[6] = {0, 0, 0, 0, 0, 0};
+    int plan_seg_rows = 0;
+    std::vector<bfm_problem_t> plan_problems;
+    // pipelined host path: copy-in / copy-out streams and per-chunk events
+    cudaStream_t in_stream = nullptr, out_stream = nullptr;
+    cudaEvent_t chunk_ev[2 * 16] = {};
     int occ_cache[3][3][3][6];  // [R idx][mode][mask][pm idx] -> CTAs per SM (0 = unknown)
 };
 
@@ -155,8 +166,8 @@ int occupancy(bfm_handle_t h, int r, int mode, int mask, int pm, int *out) {
 
 // Cut every problem into (query block, train range) segments of near-equal cost so that the grid
 // is a few balanced waves over all SMs, whatever the batch shape.
-void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems, int r, int slots,
-                   std::vector<Segment> &segs, int *seg_rows_out) {
+void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems, int r, int slots, int groups,
+                   std::vector<Segment> &segs, std::vector<int> &seg_begin, int *seg_rows_out) {
     const int bq = NT * r;
     long long steps = 0;  // sum over query blocks of their train rows
     for (int p = 0; p < n_problems; ++p) {
@@ -165,12 +176,16 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
         steps += (long long)((pr.q_count + bq - 1) / bq) * pr.t_count;
     }
     const int waves = h->waves > 0 ? h->waves : 6;
-    long long target = (long long)slots * waves;
+    // `groups` launches share this plan (pipelined host path): each of them should still be a few waves
+    long long target = (long long)slots * waves * std::max(groups, 1);
     int L = h->segment_rows > 0 ? h->segment_rows : (int)std::max<long long>(MIN_SEG_ROWS, (steps + target - 1) / target);
     *seg_rows_out = L;
     segs.clear();
+    seg_begin.assign((size_t)n_problems + 1, 0);
     for (int p = 0; p < n_problems; ++p) {
         const bfm_problem_t &pr = problems[p];
+        seg_begin[p] = (int)segs.size();
+        seg_begin[p + 1] = (int)segs.size();
         if (pr.q_count <= 0 || pr.t_count <= 0) continue;
         const int nsp = (pr.t_count + L - 1) / L;
         const int base = pr.t_count / nsp, rem = pr.t_count % nsp;
@@ -191,8 +206,20 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
                 t0 += cnt;
             }
         }
+        seg_begin[p + 1] = (int)segs.size();
     }
 }
+
+// Optional launch grouping (pipelined host path): the batch is planned and its tables uploaded once,
+// then problems [bounds[g], bounds[g+1]) are scanned + finalized as launch group g, with the hooks
+// called around each group to tie it to the copy streams.
+struct GroupHooks {
+    int n_groups;
+    const int *bounds;
+    void *ctx;
+    int (*before)(void *ctx, int g);
+    int (*after)(void *ctx, int g);
+};
 
 int check_opts(bfm_handle_t h, const bfm_options_t *o, int n_problems) {
     if (!o) return fail(h, BFM_ERR_INVALID, "options is NULL");
@@ -214,9 +241,13 @@ int check_opts(bfm_handle_t h, const bfm_options_t *o, int n_problems) {
 int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t, int32_t nt_rows,
                const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
                const bfm_options_t *o, int32_t *knn_idx, int32_t *knn_dist, int32_t *m_query,
-               int32_t *m_train, int32_t *m_dist, int32_t *m_count, cudaStream_t st) {
+               int32_t *m_train, int32_t *m_dist, int32_t *m_count, cudaStream_t st,
+               const GroupHooks *hooks = nullptr) {
     h->info = bfm_launch_info_t{};
     if (n_problems <= 0 || n_out_rows <= 0) return BFM_OK;
+    const int one_group[2] = {0, n_problems};
+    const int n_groups = hooks ? hooks->n_groups : 1;
+    const int *gbounds = hooks ? hooks->bounds : one_group;
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(t)) & 15)
         return fail(h, BFM_ERR_INVALID, "descriptor arrays must be 16-byte aligned");
     const bool want_matches = m_count != nullptr;
@@ -272,7 +303,15 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         if (rc) return rc;
         slots = occ * h->sm_count;
     }
-    plan_segments(h, problems, n_problems, r, slots, h->segs_host, &seg_rows);
+    // -- plan cache: same problems + same variant as the previous call -> the device tables are
+    //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
+    const int plan_sig[6] = {n_problems, r, mode * 64 + n_groups, h->segment_rows, h->waves, slots};
+    const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
+                          h->plan_problems.size() == (size_t)n_problems &&
+                          std::memcmp(h->plan_problems.data(), problems, sizeof(bfm_problem_t) * (size_t)n_problems) == 0;
+    if (!plan_hit) {
+    plan_segments(h, problems, n_problems, r, slots, n_groups, h->segs_host, h->seg_begin, &seg_rows);
+    h->plan_seg_rows = seg_rows;
         if (o->cross_check) {
         // segment order follows problem order: recover each segment's problem by walking
         size_t si = 0;
@@ -284,20 +323,28 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             for (int i = 0; i < nsp * nqb; ++i, ++si) h->segs_host[si].col0 = h->probs_host[p].col0;
         }
     }
+    }  // !plan_hit
+    seg_rows = h->plan_seg_rows;
     const size_t n_segs = h->segs_host.size();
 
-    // -- workspace ------------------------------------------------------------------------------------
+    // -- workspace: self-cleaning (the finalize kernel restores every slot it read to all-ones), so
+    //    a memset is only queued after (re)allocation or after a call that failed half-way -----------
     const size_t state_bytes = (size_t)n_out_rows * 8;
     const size_t col_bytes = (size_t)col_rows * 4;
+    const void *state_before = h->state.p;
     int rc = ensure(h, h->state, state_bytes + col_bytes);
     if (rc) return rc;
+    if (h->state.p != state_before) h->state_clean = false;
     unsigned long long *rowstate = static_cast<unsigned long long *>(h->state.p);
     uint32_t *colkeys = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes);
 
     const size_t prob_bytes = ((size_t)n_problems * sizeof(Problem) + 15) & ~(size_t)15;
     const size_t table_bytes = prob_bytes + n_segs * sizeof(Segment);
+    const void *tables_before = h->tables.p;
     rc = ensure(h, h->tables, table_bytes);
     if (rc) return rc;
+    if (!plan_hit || h->tables.p != tables_before) {
+    h->plan_valid = false;
     const int slot = h->table_slot;
     h->table_slot = (slot + 1) % N_TABLE_SLOTS;
     if (h->h_tables_cap[slot] < table_bytes) {
@@ -318,52 +365,69 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     // upload of call n+1 behind the kernels of call n when both use the same stream (the contract).
     CU_TRY(h, cudaMemcpyAsync(h->tables.p, h->h_tables[slot], table_bytes, cudaMemcpyHostToDevice, st));
     CU_TRY(h, cudaEventRecord(h->table_ev[slot], st));
+    std::memcpy(h->plan_sig, plan_sig, sizeof(plan_sig));
+    h->plan_problems.assign(problems, problems + n_problems);
+    h->plan_valid = true;
+    }
     const Problem *d_probs = static_cast<const Problem *>(h->tables.p);
     const Segment *d_segs = reinterpret_cast<const Segment *>(static_cast<char *>(h->tables.p) + prob_bytes);
 
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], st));
-    CU_TRY(h, cudaMemsetAsync(h->state.p, 0xFF, state_bytes + col_bytes, st));
+    if (!h->state_clean) CU_TRY(h, cudaMemsetAsync(h->state.p, 0xFF, h->state.cap, st));
+    h->state_clean = false;  // set again once the finalize kernel (which restores the state) is queued
 
     int kernels = 0;
-    if (n_segs) {
-        ScanParams sp;
-        sp.q = reinterpret_cast<const uint4 *>(q);
-        sp.t = reinterpret_cast<const uint4 *>(t);
-        sp.segs = d_segs;
-        sp.rowstate = rowstate;
-        sp.colkeys = colkeys;
-        sp.mask = o->mask;
-        sp.mask_stride = o->mask_row_stride;
-        sp.q_xy = reinterpret_cast<const float2 *>(o->q_xy);
-        sp.t_xy = reinterpret_cast<const float2 *>(o->t_xy);
-        sp.radius = o->window_radius;
-        ScanFn fn = pick_scan(r, mode, mask, pm);
-        if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
-        fn<<<(unsigned)n_segs, NT, 0, st>>>(sp);
+    ScanParams sp;
+    sp.q = reinterpret_cast<const uint4 *>(q);
+    sp.t = reinterpret_cast<const uint4 *>(t);
+    sp.rowstate = rowstate;
+    sp.colkeys = colkeys;
+    sp.mask = o->mask;
+    sp.mask_stride = o->mask_row_stride;
+    sp.q_xy = reinterpret_cast<const float2 *>(o->q_xy);
+    sp.t_xy = reinterpret_cast<const float2 *>(o->t_xy);
+    sp.radius = o->window_radius;
+    bfm::FinalizeParams fp;
+    fp.rowstate = rowstate;
+    fp.colkeys = colkeys;
+    fp.k = o->k;
+    fp.cross_check = o->cross_check;
+    fp.max_distance = o->max_distance;
+    fp.use_ratio = o->ratio >= 0;
+    fp.ratio = o->ratio;
+    fp.knn_idx = knn_idx;
+    fp.knn_dist = knn_dist;
+    fp.m_query = m_query;
+    fp.m_train = m_train;
+    fp.m_dist = m_dist;
+    const ScanFn fn = pick_scan(r, mode, mask, pm);
+    for (int g = 0; g < n_groups; ++g) {
+        const int p0 = gbounds[g], p1 = gbounds[g + 1];
+        if (p1 <= p0) continue;
+        if (hooks && hooks->before) {
+            rc = hooks->before(hooks->ctx, g);
+            if (rc) return rc;
+        }
+        const int s0 = h->seg_begin[p0], s1 = h->seg_begin[p1];
+        if (s1 > s0) {
+            sp.segs = d_segs + s0;
+            if (h->timing && g == 0) CU_TRY(h, cudaEventRecord(h->ev[1], st));
+            fn<<<(unsigned)(s1 - s0), NT, 0, st>>>(sp);
+            CU_TRY(h, cudaGetLastError());
+            if (h->timing && g == n_groups - 1) CU_TRY(h, cudaEventRecord(h->ev[2], st));
+            ++kernels;
+        }
+        fp.problems = d_probs + p0;
+        fp.m_count = m_count ? m_count + p0 : nullptr;
+        bfm::bfm_finalize_kernel<FIN_NT><<<(unsigned)(p1 - p0), FIN_NT, 0, st>>>(fp);
         CU_TRY(h, cudaGetLastError());
-        if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[2], st));
         ++kernels;
+        if (hooks && hooks->after) {
+            rc = hooks->after(hooks->ctx, g);
+            if (rc) return rc;
+        }
     }
-    {
-        bfm::FinalizeParams fp;
-        fp.rowstate = rowstate;
-        fp.colkeys = colkeys;
-        fp.problems = d_probs;
-        fp.k = o->k;
-        fp.cross_check = o->cross_check;
-        fp.max_distance = o->max_distance;
-        fp.use_ratio = o->ratio >= 0;
-        fp.ratio = o->ratio;
-        fp.knn_idx = knn_idx;
-        fp.knn_dist = knn_dist;
-        fp.m_query = m_query;
-        fp.m_train = m_train;
-        fp.m_dist = m_dist;
-        fp.m_count = m_count;
-        bfm::bfm_finalize_kernel<FIN_NT><<<(unsigned)n_problems, FIN_NT, 0, st>>>(fp);
-        CU_TRY(h, cudaGetLastError());
-        ++kernels;
-    }
+    h->state_clean = true;  // every slot touched above is restored by its group's finalize kernel
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[3], st));
 
     h->launches += kernels;
@@ -461,6 +525,8 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
     return BFM_OK;
 }
 
+#include "bfm_pipeline.cuh"
+
 }  // namespace
 
 extern "C" {
@@ -499,7 +565,10 @@ int bfm_create(int device, bfm_handle_t *out) {
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     std::memset(h->occ_cache, 0, sizeof(h->occ_cache));
-    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 32; ++i) ok = cudaEventCreate(&h->chunk_ev[i]) == cudaSuccess;
     for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     for (int i = 0; ok && i < N_TABLE_SLOTS; ++i) {
         ok = cudaEventCreateWithFlags(&h->table_ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -527,6 +596,10 @@ int bfm_destroy(bfm_handle_t h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 32; ++i)
+        if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
+    if (h->in_stream) cudaStreamDestroy(h->in_stream);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return BFM_OK;
@@ -550,6 +623,9 @@ int bfm_match_batched(bfm_handle_t h, int mem, const uint8_t *q, int32_t n_query
     if (mem == BFM_MEM_DEVICE)
         return run_device(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, knn_idx,
                           knn_dist, m_query, m_train, m_dist, m_count, stream == BFM_STREAM_OWN ? h->stream : static_cast<cudaStream_t>(stream));
+    if (mem == BFM_MEM_HOST && pipeline_eligible(h, n_query_rows, n_train_rows, problems, n_problems, opts))
+        return run_host_pipelined(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, knn_idx,
+                                  knn_dist, m_query, m_train, m_dist, m_count);
     if (mem == BFM_MEM_HOST)
         return run_host(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, knn_idx,
                         knn_dist, m_query, m_train, m_dist, m_count);
@@ -592,6 +668,9 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "segment_rows") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "segment_rows must be >= 0");
         h->segment_rows = value;
+    } else if (k == "pipeline_chunks") {
+        if (value < 0 || value > 16) return fail(h, BFM_ERR_INVALID, "pipeline_chunks must be 0 (auto), 1 (off) .. 16");
+        h->pipeline_chunks = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");
         h->waves = value;

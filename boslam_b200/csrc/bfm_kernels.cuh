@@ -339,8 +339,8 @@ struct Problem {   // mirrors bfm_problem_t; `col0` (reserved there) = first col
 };
 
 struct FinalizeParams {
-    const unsigned long long *rowstate;
-    const uint32_t *colkeys;
+    unsigned long long *rowstate;   // read, then reset to all-ones: the workspace is self-cleaning,
+    uint32_t *colkeys;              // so a steady-state call needs no memset launch
     const Problem *problems;
     int32_t k;             // columns of the knn table (1 or 2 on this path)
     int32_t cross_check;
@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(NT) bfm_finalize_kernel(const FinalizeParams p
         uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
         if (in) {
             const unsigned long long st = p.rowstate[(size_t)pr.out_begin + i];
+            p.rowstate[(size_t)pr.out_begin + i] = ~0ull;
             k1 = (uint32_t)(st >> 32);
             k2 = (uint32_t)st;
         }
@@ -405,6 +406,10 @@ __global__ void __launch_bounds__(NT) bfm_finalize_kernel(const FinalizeParams p
         }
     }
     if (p.m_count && tid == 0) p.m_count[blockIdx.x] = s_running;
+    if (p.cross_check) {
+        __syncthreads();   // every column-key read of this problem happened in this CTA, above
+        for (int j = tid; j < pr.t_count; j += NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
+    }
 }
 
 }  // namespace bfm

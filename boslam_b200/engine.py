@@ -68,7 +68,9 @@ class PinnedBuffer:
 
 class BatchResult:
     """Matches of a batch of problems, packed.  ``counts[p]`` matches of problem p start at
-    ``offsets[p]`` in ``query_idx`` / ``train_idx`` / ``distance`` (problem-local indices)."""
+    ``offsets[p]`` in ``query_idx`` / ``train_idx`` / ``distance`` (problem-local indices; only the
+    first ``counts[p]`` entries of a problem's slice are meaningful).  ``distance`` is kept as the
+    integer Hamming distance; ``result[p]`` yields cv2-style float32 distances."""
 
     __slots__ = ("query_idx", "train_idx", "distance", "counts", "offsets")
 
@@ -81,11 +83,27 @@ class BatchResult:
 
     def __getitem__(self, p):
         b, n = int(self.offsets[p]), int(self.counts[p])
-        return self.query_idx[b:b + n], self.train_idx[b:b + n], self.distance[b:b + n]
+        return self.query_idx[b:b + n], self.train_idx[b:b + n], self.distance[b:b + n].astype(np.float32)
 
     def __iter__(self):
         for p in range(len(self)):
             yield self[p]
+
+
+class HostBatchBuffers:
+    """Reusable pinned output arrays for :meth:`Engine.match_batched` (``out=``): results are DMA-ed
+    straight into them, so a steady-state batched call allocates nothing."""
+
+    def __init__(self, n_out: int, n_problems: int, k: int = 1, want_knn: bool = False):
+        self.n_out, self.n_problems, self.k = int(n_out), int(n_problems), int(k)
+        self._m = PinnedBuffer((3, max(self.n_out, 1)), np.int32)
+        self._c = PinnedBuffer((max(self.n_problems, 1),), np.int32)
+        self.m, self.count = self._m.array, self._c.array
+        self.knn_idx = self.knn_dist = None
+        if want_knn:
+            self._ki = PinnedBuffer((max(self.n_out, 1), self.k), np.int32)
+            self._kd = PinnedBuffer((max(self.n_out, 1), self.k), np.int32)
+            self.knn_idx, self.knn_dist = self._ki.array, self._kd.array
 
 
 def make_problems(q_counts: Sequence[int], t_counts: Sequence[int], shared_query: bool = False) -> np.ndarray:
@@ -256,7 +274,7 @@ class Engine:
     # -- batched (keyframe pairs) -----------------------------------------------------------------------
     def match_batched(self, q_packed, t_packed, problems: np.ndarray, k: int = 1, ratio=None,
                       cross_check: bool = False, max_distance=None, strict: bool = False, window=None,
-                      want_knn: bool = False):
+                      want_knn: bool = False, out: "HostBatchBuffers | None" = None):
         """Batched form over packed descriptor arrays + a problem table (see :func:`make_problems`).
 
         Returns a :class:`BatchResult` (and the dense (idx, dist) tables first if ``want_knn``).
@@ -281,19 +299,25 @@ class Engine:
         keep = []
         if window is not None:
             self._mask_args_np(opts, None, window, q.shape[0], t.shape[0], keep)
-        mq = np.empty(n_out, np.int32)
-        mt = np.empty(n_out, np.int32)
-        md = np.empty(n_out, np.int32)
-        mc = np.zeros(P, np.int32)
-        idx = np.full((n_out, k), -1, np.int32) if want_knn else None
-        dist = np.full((n_out, k), -1, np.int32) if want_knn else None
+        if out is not None:
+            if out.n_out < n_out or out.n_problems < P or (want_knn and (out.knn_idx is None or out.k != k)):
+                raise ValueError("out= buffers are too small for this batch")
+            mq, mt, md, mc = out.m[0], out.m[1], out.m[2], out.count[:P]
+            idx, dist = (out.knn_idx, out.knn_dist) if want_knn else (None, None)
+        else:
+            mq = np.empty(n_out, np.int32)
+            mt = np.empty(n_out, np.int32)
+            md = np.empty(n_out, np.int32)
+            mc = np.zeros(P, np.int32)
+            idx = np.full((n_out, k), -1, np.int32) if want_knn else None
+            dist = np.full((n_out, k), -1, np.int32) if want_knn else None
         if P and n_out:
             self._call(_ffi.MEM_HOST, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0], probs, n_out, opts,
                        (idx.ctypes.data, dist.ctypes.data) if want_knn else None,
                        (mq.ctypes.data, mt.ctypes.data, md.ctypes.data, mc.ctypes.data))
         if none_pass:
             mc[:] = 0
-        res = BatchResult(mq, mt, md.astype(np.float32), mc, probs[:, 4].copy())
+        res = BatchResult(mq, mt, md, mc, probs[:, 4].copy())
         return (idx, dist, res) if want_knn else res
 
     def match_pairs(self, queries: Sequence, trains: Sequence, **kw):
@@ -303,8 +327,7 @@ class Engine:
             raise ValueError("queries and trains must have the same length")
         P = len(trains)
         if P == 0:
-            return BatchResult(*(np.zeros(0, np.int32),) * 2, np.zeros(0, np.float32), np.zeros(0, np.int32),
-                               np.zeros(0, np.int32))
+            return BatchResult(*(np.zeros(0, np.int32),) * 5)
         qs = [_check_desc_np(a, "query") for a in queries]
         ts = [_check_desc_np(a, "train") for a in trains]
         tab = np.zeros((P, 6), np.int32)
@@ -442,7 +465,7 @@ class Engine:
         probs = np.ascontiguousarray(problems, np.int32)
         m = out["m"].cpu().numpy()
         cnt = out["count"].cpu().numpy()[:probs.shape[0]]
-        res = BatchResult(m[0], m[1], m[2].astype(np.float32), cnt, probs[:, 4].copy())
+        res = BatchResult(m[0], m[1], m[2], cnt, probs[:, 4].copy())
         if want_knn:
             return out["knn_idx"], out["knn_dist"], res
         return res

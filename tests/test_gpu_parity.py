@@ -268,3 +268,54 @@ def test_threads_own_handles():
     [x.start() for x in th]
     [x.join() for x in th]
     assert not errs, errs
+
+
+def test_pipelined_host_path_and_reused_buffers(eng):
+    """Large batches take the chunked copy/compute-overlap path; results must not depend on it."""
+    qp, tp = synth.keyframe_pair_batch(24, 1500, seed=77)
+    tab = bb.make_problems([1500] * 24, [1500] * 24)
+    out = bb.HostBatchBuffers(24 * 1500, 24, k=2, want_knn=True)
+    ref_res = None
+    for chunks in (1, 0, 3, 16):                                     # 1 = pipeline off
+        eng.set_tuning(pipeline_chunks=chunks)
+        idx, dist, res = eng.match_batched(qp, tp, tab, k=2, ratio=0.8, want_knn=True, out=out)
+        snap = (idx.copy(), dist.copy(), res.counts.copy(), [tuple(a.copy() for a in res[p]) for p in range(24)])
+        if ref_res is None:
+            ref_res = snap
+            for p in (0, 7, 23):
+                oi, od = c_oracle.knn(qp[p * 1500:(p + 1) * 1500], tp[p * 1500:(p + 1) * 1500], 2)
+                assert np.array_equal(idx[p * 1500:(p + 1) * 1500], oi) and np.array_equal(dist[p * 1500:(p + 1) * 1500], od)
+                _eq(res[p], orc.match(qp[p * 1500:(p + 1) * 1500], tp[p * 1500:(p + 1) * 1500], k=2, ratio=0.8), p)
+        else:
+            assert np.array_equal(snap[0], ref_res[0]) and np.array_equal(snap[1], ref_res[1])
+            assert np.array_equal(snap[2], ref_res[2])
+            for a, b in zip(snap[3], ref_res[3]):
+                _eq(a, b)
+    eng.set_tuning(pipeline_chunks=0)
+    # shared query keyframe + cross-check through the pipelined path (pageable outputs)
+    q0 = qp[:1500]
+    tab2 = bb.make_problems([1500] * 24, [1500] * 24, shared_query=True)
+    eng.set_tuning(pipeline_chunks=4)
+    res = eng.match_batched(q0, tp, tab2, cross_check=True)
+    eng.set_tuning(pipeline_chunks=0)
+    for p in (0, 11, 23):
+        _eq(res[p], c_oracle.cross_check(q0, tp[p * 1500:(p + 1) * 1500]), p)
+
+
+def test_self_cleaning_workspace_and_plan_cache(eng):
+    """Back-to-back calls of different modes / shapes reuse one workspace without a memset, and a
+    repeated shape reuses the cached plan: results must stay exact."""
+    shapes = [(300, 700), (300, 700), (1200, 400), (50, 5000), (300, 700), (1200, 400)]
+    for rep, (nq, nt) in enumerate(shapes * 2):
+        q, t, _ = synth.correlated(nq, nt, 500 + rep)
+        mode = rep % 3
+        if mode == 0:
+            _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t), rep)
+        elif mode == 1:
+            _eq(eng.knn(q, t, 2), c_oracle.knn(q, t, 2), rep)
+        else:
+            _eq(eng.knn(q, t, 1), c_oracle.knn(q, t, 1), rep)
+    q, t, _ = synth.correlated(640, 480, 3)
+    want = c_oracle.cross_check(q, t)
+    for _ in range(5):                                               # identical call: plan-cache hits
+        _eq(eng.match(q, t, cross_check=True), want)
