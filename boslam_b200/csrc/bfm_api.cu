@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -77,6 +78,7 @@ ScanFn pick_scan(int r, int mode, int mask, int pm) {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    unsigned generation = 0;  // bumped on every (re)allocation; the address alone may be reused by cudaMalloc
 };
 
 }  // namespace
@@ -147,6 +149,7 @@ int ensure(bfm_handle_t h, DevBuf &b, size_t bytes) {
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) return fail(h, BFM_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     b.cap = want;
+    ++b.generation;
     return BFM_OK;
 }
 
@@ -175,10 +178,42 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
         if (pr.q_count <= 0 || pr.t_count <= 0) continue;
         steps += (long long)((pr.q_count + bq - 1) / bq) * pr.t_count;
     }
-    const int waves = h->waves > 0 ? h->waves : 6;
     // `groups` launches share this plan (pipelined host path): each of them should still be a few waves
-    long long target = (long long)slots * waves * std::max(groups, 1);
-    int L = h->segment_rows > 0 ? h->segment_rows : (int)std::max<long long>(MIN_SEG_ROWS, (steps + target - 1) / target);
+    const int ng = std::max(groups, 1);
+    int L;
+    if (h->segment_rows > 0) {
+        L = h->segment_rows;
+    } else if (h->waves > 0) {
+        const long long target = (long long)slots * h->waves * ng;
+        L = (int)std::max<long long>(MIN_SEG_ROWS, (steps + target - 1) / target);
+    } else {
+        // All CTAs of a launch cost about the same, so a grid of n CTAs over `slots` resident ones runs
+        // about ceil(n / slots) waves; avoid a nearly empty last wave.  (Measured effect on the 256-pair
+        // batch is small - 7168 CTAs = 6.05 waves: 1.042 ms, 8192 = 6.92 waves: 1.039 ms - because CTA
+        // start times drift apart, but it costs nothing.)  Search the segment length between ~3 and ~12
+        // waves per launch for the best wave efficiency, discounted by the per-CTA fixed cost (~4 rows).
+        const long long lo = std::max<long long>(MIN_SEG_ROWS, steps / ((long long)slots * 12 * ng));
+        const long long hi = std::max<long long>(lo, steps / ((long long)slots * 3 * ng) + 1);
+        double best = -1.0;
+        L = (int)lo;
+        const long long stride = std::max<long long>(1, (hi - lo) / 256);
+        for (long long cand = hi; cand >= lo; cand -= stride) {
+            long long n = 0;
+            for (int p = 0; p < n_problems; ++p) {
+                const bfm_problem_t &pr = problems[p];
+                if (pr.q_count <= 0 || pr.t_count <= 0) continue;
+                n += (long long)((pr.q_count + bq - 1) / bq) * ((pr.t_count + cand - 1) / cand);
+            }
+            const double per_launch = (double)n / ng;
+            const double waves = per_launch / slots;
+            const double eff = waves / std::ceil(waves - 1e-9);
+            const double score = eff * (double)cand / ((double)cand + 4.0);
+            if (score > best + 1e-9) {
+                best = score;
+                L = (int)cand;
+            }
+        }
+    }
     *seg_rows_out = L;
     segs.clear();
     seg_begin.assign((size_t)n_problems + 1, 0);
@@ -331,19 +366,19 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     //    a memset is only queued after (re)allocation or after a call that failed half-way -----------
     const size_t state_bytes = (size_t)n_out_rows * 8;
     const size_t col_bytes = (size_t)col_rows * 4;
-    const void *state_before = h->state.p;
+    const unsigned state_gen = h->state.generation;
     int rc = ensure(h, h->state, state_bytes + col_bytes);
     if (rc) return rc;
-    if (h->state.p != state_before) h->state_clean = false;
+    if (h->state.generation != state_gen) h->state_clean = false;
     unsigned long long *rowstate = static_cast<unsigned long long *>(h->state.p);
     uint32_t *colkeys = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes);
 
     const size_t prob_bytes = ((size_t)n_problems * sizeof(Problem) + 15) & ~(size_t)15;
     const size_t table_bytes = prob_bytes + n_segs * sizeof(Segment);
-    const void *tables_before = h->tables.p;
+    const unsigned tables_gen = h->tables.generation;
     rc = ensure(h, h->tables, table_bytes);
     if (rc) return rc;
-    if (!plan_hit || h->tables.p != tables_before) {
+    if (!plan_hit || h->tables.generation != tables_gen) {
     h->plan_valid = false;
     const int slot = h->table_slot;
     h->table_slot = (slot + 1) % N_TABLE_SLOTS;
@@ -387,6 +422,12 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     sp.q_xy = reinterpret_cast<const float2 *>(o->q_xy);
     sp.t_xy = reinterpret_cast<const float2 *>(o->t_xy);
     sp.radius = o->window_radius;
+    sp.mul_d32 = 1u << bfm::DIST_SHIFT;
+    sp.mul_lo16 = 1u << 7;
+    sp.mul_hi16 = 1u << 23;
+    sp.mul_one = 1u;
+    sp.mul_two = 2u;
+    sp.mul_four = 4u;
     bfm::FinalizeParams fp;
     fp.rowstate = rowstate;
     fp.colkeys = colkeys;
@@ -442,6 +483,17 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         CU_TRY(h, cudaEventSynchronize(h->ev[3]));
         if (n_segs) CU_TRY(h, cudaEventElapsedTime(&h->info.scan_ms, h->ev[1], h->ev[2]));
         CU_TRY(h, cudaEventElapsedTime(&h->info.total_ms, h->ev[0], h->ev[3]));
+    }
+    if (std::getenv("BFM_CHECK_CLEAN")) {  // debugging aid: the workspace must be all-ones after every call
+        CU_TRY(h, cudaDeviceSynchronize());
+        std::vector<unsigned char> host(h->state.cap);
+        CU_TRY(h, cudaMemcpy(host.data(), h->state.p, h->state.cap, cudaMemcpyDeviceToHost));
+        size_t bad = 0, first = 0;
+        for (size_t i = 0; i < host.size(); ++i)
+            if (host[i] != 0xFF) { if (!bad) first = i; ++bad; }
+        if (bad)
+            std::fprintf(stderr, "[bfm check] workspace dirty after call: %zu bytes, first at %zu (rows=%d col_rows=%lld state_bytes=%zu cap=%zu mode=%d P=%d groups=%d)\n",
+                         bad, first, n_out_rows, col_rows, state_bytes, h->state.cap, mode, n_problems, n_groups);
     }
     return BFM_OK;
 }

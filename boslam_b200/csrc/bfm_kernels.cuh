@@ -24,8 +24,9 @@ namespace bfm {
 constexpr int DIST_SHIFT = 22;
 constexpr uint32_t IDX_MASK = (1u << DIST_SHIFT) - 1u;
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;      // empty slot
-constexpr uint32_t KEY_DEAD = 0x80000000u;      // any key >= this is "no candidate" (distance field >= 512)
-constexpr uint32_t DIST_MASKED = 512u;          // OR-ed into a masked pair's distance
+constexpr uint32_t DIST_MASKED = 511u;          // distance given to a masked pair (real distances are 0..256)
+constexpr uint32_t KEY_DEAD = DIST_MASKED << DIST_SHIFT;  // any key >= this is "no candidate"
+constexpr uint32_t KEY16_DEAD = DIST_MASKED << 7;          // same, for the chunk-local 16-bit keys (d << 7 | j)
 constexpr int TT = 128;                         // train rows per shared-memory chunk (4 KB)
 
 // One work item: a block of BQ = NT*R query rows against a contiguous range of train rows of
@@ -52,6 +53,12 @@ struct ScanParams {
     const float2 *q_xy;              // window: pixel coordinates per query / train row
     const float2 *t_xy;
     float radius;
+    // multipliers for key formation, passed as data so that ptxas keeps them IMADs (FMA pipe)
+    // instead of strength-reducing to LEA/SHF on the ALU pipe, which is the binding one
+    uint32_t mul_d32;   // 1 << 22
+    uint32_t mul_lo16;  // 1 << 7
+    uint32_t mul_hi16;  // 1 << 23
+    uint32_t mul_one, mul_two, mul_four;  // weights of the carry-save popcount sum, same reason
 };
 
 // ---- PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------------------
@@ -94,6 +101,17 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     return r;
 }
 
+__device__ __forceinline__ uint32_t min_u16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
 // PM selects how the 256-bit popcount is evaluated (all variants are exact):
 //   8        plain: 8 XOR + 8 POPC
 //   6, 5, 4  carry-save adder (Harley-Seal) tree on LOP3 over the 8 XOR words, 6/5/4 POPCs
@@ -123,7 +141,7 @@ __device__ __forceinline__ void transform_desc(uint32_t (&w)[8]) {
 }
 
 template <int PM>
-__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint32_t (&t)[8]) {
+__device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uint32_t (&t)[8], const ScanParams &p) {
     if constexpr (pm_transformed(PM)) {
         // layout: [0]=w0 [1]=w1 [2]=w3 [3]=w4 [4]=w7 [5]=S012 [6]=S345 [7]=S0..6
         const uint32_t x0 = q[0] ^ t[0], x1 = q[1] ^ t[1], s0 = q[5] ^ t[5];
@@ -135,9 +153,9 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
         const uint32_t x7 = q[4] ^ t[4];
         if constexpr (PM == 50) {
             return (__popc(s2) + __popc(x7)) + 2u * (__popc(c0) + __popc(c1) + __popc(c2));
-        } else {  // PM == 40
+        } else {  // PM == 40: the weighted sum as three IMADs (FMA pipe; the ALU pipe is the binding one)
             const uint32_t s3 = xor3(c0, c1, c2), c3 = maj3(c0, c1, c2);
-            return (__popc(s2) + __popc(x7)) + 2u * __popc(s3) + 4u * __popc(c3);
+            return __popc(c3) * p.mul_four + (__popc(s3) * p.mul_two + (__popc(s2) * p.mul_one + __popc(x7)));
         }
     } else {
         uint32_t x[8];
@@ -262,34 +280,92 @@ __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
         const int b = c & 1;
         const int n = chunk_rows(c);
         const uint32_t jbase = (uint32_t)(sg.t_local0 + c * TT);
-#pragma unroll 2
-        for (int j = 0; j < n; ++j) {
-            const uint4 ta = s_t[b][2 * j];
-            const uint4 tb = s_t[b][2 * j + 1];
-            const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-            float2 txy;
-            if (MASK == 2) txy = s_xy[b][j];
-            const uint32_t jj = jbase + (uint32_t)j;
-            uint32_t ck = KEY_NONE;
+        if constexpr (R >= 2) {
+            // ---- packed path: two queries share one register of chunk-local 16-bit keys ----------
+            // key16 = d << 7 | j (j < 128), so one VIMNMX.U16x2 updates two queries at once; the
+            // chunk's winners are folded into the 32-bit global keys once per 128 train rows.
+            uint32_t p1[R / 2], p2[R / 2];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                uint32_t d = hamming256<PM>(qw[r], tw);
-                if (MASK == 1) {
-                    const bool ok = valid[r] && (__ldg(mrow[r] + jj) != 0);
-                    d = ok ? d : (d | DIST_MASKED);
+            for (int h = 0; h < R / 2; ++h) { p1[h] = 0xFFFFFFFFu; p2[h] = 0xFFFFFFFFu; }
+#pragma unroll 2
+            for (int j = 0; j < n; ++j) {
+                const uint4 ta = s_t[b][2 * j];
+                const uint4 tb = s_t[b][2 * j + 1];
+                const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+                float2 txy;
+                if (MASK == 2) txy = s_xy[b][j];
+                const uint32_t jpack = (uint32_t)j * 0x10001u;
+                uint32_t ck = KEY_NONE;
+#pragma unroll
+                for (int h = 0; h < R / 2; ++h) {
+                    uint32_t d[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = 2 * h + e;
+                        d[e] = hamming256<PM>(qw[r], tw, p);
+                        if (MASK == 1) {
+                            const bool ok = valid[r] && (__ldg(mrow[r] + jbase + j) != 0);
+                            d[e] = ok ? d[e] : DIST_MASKED;
+                        }
+                        if (MASK == 2) {
+                            const bool ok = (fabsf(qx[r] - txy.x) < p.radius) && (fabsf(qy[r] - txy.y) < p.radius);
+                            d[e] = ok ? d[e] : DIST_MASKED;
+                        }
+                        if (CROSS) ck = min(ck, d[e] * p.mul_d32 + ibias[r]);
+                    }
+                    const uint32_t packed = d[1] * p.mul_hi16 + (d[0] * p.mul_lo16 + jpack);
+                    if (K == 2) p2[h] = min_u16x2(p2[h], max_u16x2(p1[h], packed));
+                    p1[h] = min_u16x2(p1[h], packed);
                 }
-                if (MASK == 2) {
-                    const bool ok = (fabsf(qx[r] - txy.x) < p.radius) && (fabsf(qy[r] - txy.y) < p.radius);
-                    d = ok ? d : (d | DIST_MASKED);
+                if (CROSS) {
+                    ck = __reduce_min_sync(0xffffffffu, ck);
+                    if (lane == 0) s_col[b][warp][j] = ck;
                 }
-                const uint32_t key = (d << DIST_SHIFT) + jj;
-                if (K == 2) b2[r] = min(b2[r], max(b1[r], key));
-                b1[r] = min(b1[r], key);
-                if (CROSS) ck = min(ck, (d << DIST_SHIFT) + ibias[r]);
             }
-            if (CROSS) {
-                ck = __reduce_min_sync(0xffffffffu, ck);
-                if (lane == 0) s_col[b][warp][j] = ck;
+            // fold the chunk winners into the global 32-bit keys (sorted-pair merge)
+#pragma unroll
+            for (int h = 0; h < R / 2; ++h) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = 2 * h + e;
+                    const uint32_t k1 = e ? (p1[h] >> 16) : (p1[h] & 0xFFFFu);
+                    const uint32_t k2 = e ? (p2[h] >> 16) : (p2[h] & 0xFFFFu);
+                    const uint32_t c1 = k1 >= KEY16_DEAD ? KEY_NONE : ((k1 >> 7) << DIST_SHIFT) + jbase + (k1 & 127u);
+                    const uint32_t c2 = (K == 1 || k2 >= KEY16_DEAD) ? KEY_NONE : ((k2 >> 7) << DIST_SHIFT) + jbase + (k2 & 127u);
+                    if (K == 2) b2[r] = min(max(b1[r], c1), min(b2[r], c2));
+                    b1[r] = min(b1[r], c1);
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int j = 0; j < n; ++j) {
+                const uint4 ta = s_t[b][2 * j];
+                const uint4 tb = s_t[b][2 * j + 1];
+                const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+                float2 txy;
+                if (MASK == 2) txy = s_xy[b][j];
+                const uint32_t jj = jbase + (uint32_t)j;
+                uint32_t ck = KEY_NONE;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    uint32_t d = hamming256<PM>(qw[r], tw, p);
+                    if (MASK == 1) {
+                        const bool ok = valid[r] && (__ldg(mrow[r] + jj) != 0);
+                        d = ok ? d : DIST_MASKED;
+                    }
+                    if (MASK == 2) {
+                        const bool ok = (fabsf(qx[r] - txy.x) < p.radius) && (fabsf(qy[r] - txy.y) < p.radius);
+                        d = ok ? d : DIST_MASKED;
+                    }
+                    const uint32_t key = d * p.mul_d32 + jj;
+                    if (K == 2) b2[r] = min(b2[r], max(b1[r], key));
+                    b1[r] = min(b1[r], key);
+                    if (CROSS) ck = min(ck, d * p.mul_d32 + ibias[r]);
+                }
+                if (CROSS) {
+                    ck = __reduce_min_sync(0xffffffffu, ck);
+                    if (lane == 0) s_col[b][warp][j] = ck;
+                }
             }
         }
         if (c + 1 < nchunks) land(c + 1);
