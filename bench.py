@@ -282,11 +282,27 @@ def main():
            "count": torch.zeros(N_PAIRS, dtype=torch.int32, device=dev)}
     gathered_m = torch.empty((world * 3, n_out), dtype=torch.int32, device=dev) if dist else None
     gathered_c = torch.empty(world * N_PAIRS, dtype=torch.int32, device=dev) if dist else None
+    # the path's one exchange: every rank ends up with every rank's match tables.
+    # Default: fused into the matching kernel's epilogue (stores to NVLink peer memory + one barrier);
+    # BFM_GATHER=nccl selects the plain NCCL all_gather for comparison.
+    fused = None
+    gather_mode = os.environ.get("BFM_GATHER", "fused") if dist else "none"
+    if dist and gather_mode == "fused":
+        try:
+            from boslam_b200.distributed import FusedGather
+            fused = FusedGather(n_out, N_PAIRS, k=2)
+        except Exception as e:  # symmetric memory unavailable on this box: say so and use NCCL
+            print(f"[bench] fused gather unavailable ({type(e).__name__}: {e}); using NCCL all_gather", file=sys.stderr)
+            gather_mode = "nccl"
 
     def device_step(i):
         q, t = dev_sets[i % N_SETS]
+        if fused is not None:
+            fused.run(eng, q, t, tab, k=2, ratio=RATIO)
+            fused.barrier()
+            return
         eng.match_batched_device(q, t, tab, k=2, ratio=RATIO, out=out)
-        if dist:  # the path's one exchange: gather every rank's match tables
+        if dist:
             dist.all_gather_into_tensor(gathered_m, out["m"])
             dist.all_gather_into_tensor(gathered_c, out["count"])
 
@@ -373,7 +389,9 @@ def main():
         "config": {"workload": "loop_closing", "pairs_per_gpu": N_PAIRS, "desc_per_keyframe": N_DESC, "k": 2,
                    "ratio": RATIO, "pairs_per_step_per_gpu": pairs_per_step,
                    "l2": f"{N_SETS} rotating input sets, {N_SETS * 2 * n_out * 32 / 1e6:.0f} MB > 126 MB L2",
-                   "parallelism": f"pair-sharded x{world}, all_gather of match tables" if world > 1 else "single GPU"},
+                   "parallelism": (f"pair-sharded x{world}, match tables gathered by the kernel epilogue over NVLink peer memory + barrier"
+                                   if fused is not None else f"pair-sharded x{world}, NCCL all_gather of match tables")
+                   if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "launch": {k: info[k] for k in ("scan_grid", "scan_block", "queries_per_thread", "popc_mode",
                                         "train_rows_per_segment")},

@@ -18,12 +18,12 @@ MASK_NONE, MASK_DENSE, MASK_WINDOW = 0, 1, 2
 MAX_TRAIN_ROWS = 1 << 22
 MAX_QUERY_ROWS = 1 << 22
 MAX_K = 16
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/bfm.h declares; tests/test_abi.py checks the library exports all of them
 EXPORTED_SYMBOLS = (
     "bfm_abi_version", "bfm_create", "bfm_destroy", "bfm_last_error", "bfm_match_batched", "bfm_knn",
-    "bfm_match", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
+    "bfm_match", "bfm_match_batched_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
     "bfm_device_info", "bfm_host_alloc", "bfm_host_free",
 )
 
@@ -46,10 +46,15 @@ class Options(ctypes.Structure):
                 ("q_xy", ctypes.c_void_p), ("t_xy", ctypes.c_void_p)]
 
 
+class Outputs(ctypes.Structure):
+    _fields_ = [("knn_idx", ctypes.c_void_p), ("knn_dist", ctypes.c_void_p), ("m_query", ctypes.c_void_p),
+                ("m_train", ctypes.c_void_p), ("m_dist", ctypes.c_void_p), ("m_count", ctypes.c_void_p)]
+
+
 class LaunchInfo(ctypes.Structure):
     _fields_ = [("kernels_launched", ctypes.c_int32), ("scan_grid", ctypes.c_int32), ("scan_block", ctypes.c_int32),
                 ("queries_per_thread", ctypes.c_int32), ("popc_mode", ctypes.c_int32), ("segments", ctypes.c_int32),
-                ("train_rows_per_segment", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("train_rows_per_segment", ctypes.c_int32), ("copy_chunks", ctypes.c_int32),
                 ("scan_ms", ctypes.c_float), ("total_ms", ctypes.c_float)]
 
 
@@ -78,6 +83,8 @@ def lib():
         L.bfm_last_error.restype = ctypes.c_char_p
         L.bfm_match_batched.argtypes = [vp, ctypes.c_int, vp, i32, vp, i32, ctypes.POINTER(Problem), i32, i32,
                                         ctypes.POINTER(Options), vp, vp, vp, vp, vp, vp, vp]
+        L.bfm_match_batched_multi.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(Problem), i32, i32,
+                                              ctypes.POINTER(Options), ctypes.POINTER(Outputs), i32, vp]
         L.bfm_knn.argtypes = [vp, ctypes.c_int, vp, i32, vp, i32, ctypes.POINTER(Options), vp, vp, vp]
         L.bfm_match.argtypes = [vp, ctypes.c_int, vp, i32, vp, i32, ctypes.POINTER(Options), vp, vp, vp, vp, vp]
         L.bfm_get_launch_info.argtypes = [vp, ctypes.POINTER(LaunchInfo)]

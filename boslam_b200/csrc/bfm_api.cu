@@ -26,9 +26,9 @@ using bfm::ScanParams;
 using bfm::Segment;
 
 constexpr int NT = 128;          // threads per scan CTA
-constexpr int FIN_NT = 256;      // threads per finalize CTA
 constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
 constexpr int N_TABLE_SLOTS = 4;
+constexpr int MAX_COPY_CHUNKS = 64;  // input chunks of the pipelined host path
 
 std::string g_create_error;
 std::mutex g_create_mutex;
@@ -96,28 +96,33 @@ struct bfm_handle_s {
     cudaEvent_t table_ev[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
     int table_slot = 0;
 
-    // host-mode staging (BFM_MEM_HOST)
-    DevBuf d_in, d_out;
+    // host-mode staging (BFM_MEM_HOST): device copy of the inputs; pinned staging for results when
+    // the caller's output arrays are pageable (the kernel writes results straight into pinned host memory)
+    DevBuf d_in;
     void *h_out = nullptr;
     size_t h_out_cap = 0;
+    // input gate of the pipelined host path
+    unsigned long long *d_ready = nullptr;   // device: two watermarks
+    unsigned long long *h_marks = nullptr;   // pinned: per-chunk watermark values (copy sources)
+    uint32_t *h_status = nullptr;            // pinned: gate time-out flag written by the kernel
+    unsigned long long seq = 0;              // call sequence number (watermark epoch)
 
     // tuning knobs
     int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
 
     bfm_launch_info_t info{};
     int64_t launches = 0;
     std::vector<Segment> segs_host;
     std::vector<int> seg_begin;  // first segment of every problem (+ end sentinel)
-    std::vector<Problem> probs_host;
+    std::vector<Problem> probs_host, plan_probs;
     // plan cache + workspace hygiene
     bool plan_valid = false, state_clean = false;
     int plan_sig[6] = {0, 0, 0, 0, 0, 0};
     int plan_seg_rows = 0;
     std::vector<bfm_problem_t> plan_problems;
-    // pipelined host path: copy-in / copy-out streams and per-chunk events
-    cudaStream_t in_stream = nullptr, out_stream = nullptr;
-    cudaEvent_t chunk_ev[2 * 16] = {};
+    // pipelined host path: the copy-in stream
+    cudaStream_t in_stream = nullptr;
     int occ_cache[3][3][3][6];  // [R idx][mode][mask][pm idx] -> CTAs per SM (0 = unknown)
 };
 
@@ -169,7 +174,7 @@ int occupancy(bfm_handle_t h, int r, int mode, int mask, int pm, int *out) {
 
 // Cut every problem into (query block, train range) segments of near-equal cost so that the grid
 // is a few balanced waves over all SMs, whatever the batch shape.
-void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems, int r, int slots, int groups,
+void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems, int r, int slots,
                    std::vector<Segment> &segs, std::vector<int> &seg_begin, int *seg_rows_out) {
     const int bq = NT * r;
     long long steps = 0;  // sum over query blocks of their train rows
@@ -178,22 +183,20 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
         if (pr.q_count <= 0 || pr.t_count <= 0) continue;
         steps += (long long)((pr.q_count + bq - 1) / bq) * pr.t_count;
     }
-    // `groups` launches share this plan (pipelined host path): each of them should still be a few waves
-    const int ng = std::max(groups, 1);
     int L;
     if (h->segment_rows > 0) {
         L = h->segment_rows;
     } else if (h->waves > 0) {
-        const long long target = (long long)slots * h->waves * ng;
+        const long long target = (long long)slots * h->waves;
         L = (int)std::max<long long>(MIN_SEG_ROWS, (steps + target - 1) / target);
     } else {
         // All CTAs of a launch cost about the same, so a grid of n CTAs over `slots` resident ones runs
         // about ceil(n / slots) waves; avoid a nearly empty last wave.  (Measured effect on the 256-pair
         // batch is small - 7168 CTAs = 6.05 waves: 1.042 ms, 8192 = 6.92 waves: 1.039 ms - because CTA
         // start times drift apart, but it costs nothing.)  Search the segment length between ~3 and ~12
-        // waves per launch for the best wave efficiency, discounted by the per-CTA fixed cost (~4 rows).
-        const long long lo = std::max<long long>(MIN_SEG_ROWS, steps / ((long long)slots * 12 * ng));
-        const long long hi = std::max<long long>(lo, steps / ((long long)slots * 3 * ng) + 1);
+        // waves for the best wave efficiency, discounted by the per-CTA fixed cost (~4 rows).
+        const long long lo = std::max<long long>(MIN_SEG_ROWS, steps / ((long long)slots * 12));
+        const long long hi = std::max<long long>(lo, steps / ((long long)slots * 3) + 1);
         double best = -1.0;
         L = (int)lo;
         const long long stride = std::max<long long>(1, (hi - lo) / 256);
@@ -204,8 +207,7 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
                 if (pr.q_count <= 0 || pr.t_count <= 0) continue;
                 n += (long long)((pr.q_count + bq - 1) / bq) * ((pr.t_count + cand - 1) / cand);
             }
-            const double per_launch = (double)n / ng;
-            const double waves = per_launch / slots;
+            const double waves = (double)n / slots;
             const double eff = waves / std::ceil(waves - 1e-9);
             const double score = eff * (double)cand / ((double)cand + 4.0);
             if (score > best + 1e-9) {
@@ -220,8 +222,16 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
     for (int p = 0; p < n_problems; ++p) {
         const bfm_problem_t &pr = problems[p];
         seg_begin[p] = (int)segs.size();
-        seg_begin[p + 1] = (int)segs.size();
-        if (pr.q_count <= 0 || pr.t_count <= 0) continue;
+        if (pr.q_count <= 0 || pr.t_count <= 0) {
+            // an empty problem still needs one work item: the CTA that completes a problem finalizes it
+            // (writes its match count and the "no neighbour" rows of its knn table)
+            Segment sg;
+            sg.q_row0 = 0; sg.q_valid = 0; sg.q_local0 = 0; sg.out_row0 = pr.out_begin;
+            sg.t_row0 = 0; sg.t_count = 0; sg.t_local0 = 0; sg.problem = p;
+            segs.push_back(sg);
+            seg_begin[p + 1] = (int)segs.size();
+            continue;
+        }
         const int nsp = (pr.t_count + L - 1) / L;
         const int base = pr.t_count / nsp, rem = pr.t_count % nsp;
         for (int qb = 0; qb * bq < pr.q_count; ++qb) {
@@ -236,7 +246,7 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
                 sg.t_row0 = pr.t_begin + t0;
                 sg.t_count = cnt;
                 sg.t_local0 = t0;
-                sg.col0 = 0;  // filled with the problem's column-key base by the caller
+                sg.problem = p;
                 segs.push_back(sg);
                 t0 += cnt;
             }
@@ -244,17 +254,6 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
         seg_begin[p + 1] = (int)segs.size();
     }
 }
-
-// Optional launch grouping (pipelined host path): the batch is planned and its tables uploaded once,
-// then problems [bounds[g], bounds[g+1]) are scanned + finalized as launch group g, with the hooks
-// called around each group to tie it to the copy streams.
-struct GroupHooks {
-    int n_groups;
-    const int *bounds;
-    void *ctx;
-    int (*before)(void *ctx, int g);
-    int (*after)(void *ctx, int g);
-};
 
 int check_opts(bfm_handle_t h, const bfm_options_t *o, int n_problems) {
     if (!o) return fail(h, BFM_ERR_INVALID, "options is NULL");
@@ -272,24 +271,33 @@ int check_opts(bfm_handle_t h, const bfm_options_t *o, int n_problems) {
     return BFM_OK;
 }
 
-// The device path: every data pointer is a device pointer, work is queued on `st`.
+// Input gate of the pipelined host path (see run_host): the kernel's CTAs wait on these watermarks.
+struct Gate {
+    const unsigned long long *ready = nullptr;  // device: [0] query rows landed, [1] train rows landed (+ base)
+    unsigned long long base = 0;
+    uint32_t *status = nullptr;                 // pinned host word, device-visible
+};
+
+// The device path: every data pointer is device-visible, work is queued on `st`.  ONE kernel launch.
 int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t, int32_t nt_rows,
                const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
-               const bfm_options_t *o, int32_t *knn_idx, int32_t *knn_dist, int32_t *m_query,
-               int32_t *m_train, int32_t *m_dist, int32_t *m_count, cudaStream_t st,
-               const GroupHooks *hooks = nullptr) {
+               const bfm_options_t *o, const bfm_outputs_t *dests, int n_dests, cudaStream_t st,
+               const Gate *gate = nullptr) {
     h->info = bfm_launch_info_t{};
     if (n_problems <= 0 || n_out_rows <= 0) return BFM_OK;
-    const int one_group[2] = {0, n_problems};
-    const int n_groups = hooks ? hooks->n_groups : 1;
-    const int *gbounds = hooks ? hooks->bounds : one_group;
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(t)) & 15)
         return fail(h, BFM_ERR_INVALID, "descriptor arrays must be 16-byte aligned");
-    const bool want_matches = m_count != nullptr;
-    if (want_matches && (!m_query || !m_train || !m_dist))
-        return fail(h, BFM_ERR_INVALID, "m_query/m_train/m_dist/m_count must be given together");
-    if ((knn_idx == nullptr) != (knn_dist == nullptr))
-        return fail(h, BFM_ERR_INVALID, "knn_idx and knn_dist must be given together");
+    if (n_dests < 1 || n_dests > bfm::MAX_DEST || !dests)
+        return fail(h, BFM_ERR_INVALID, "between 1 and 8 result destinations are supported");
+    for (int d = 0; d < n_dests; ++d) {
+        const bfm_outputs_t &od = dests[d];
+        if (od.m_count && (!od.m_query || !od.m_train || !od.m_dist))
+            return fail(h, BFM_ERR_INVALID, "m_query/m_train/m_dist/m_count must be given together");
+        if ((od.knn_idx == nullptr) != (od.knn_dist == nullptr))
+            return fail(h, BFM_ERR_INVALID, "knn_idx and knn_dist must be given together");
+        if (od.knn_idx && o->k > 1 && ((reinterpret_cast<uintptr_t>(od.knn_idx) | reinterpret_cast<uintptr_t>(od.knn_dist)) & 7))
+            return fail(h, BFM_ERR_INVALID, "knn_idx / knn_dist must be 8-byte aligned");
+    }
 
     // -- validate problems, lay out column keys ------------------------------------------------
     h->probs_host.resize(n_problems);
@@ -306,6 +314,8 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         d.q_begin = pr.q_begin; d.q_count = pr.q_count; d.t_begin = pr.t_begin; d.t_count = pr.t_count;
         d.out_begin = pr.out_begin;
         d.col0 = (int32_t)col_rows;  // column-key base of this problem
+        d.n_segs = 0;                // filled from the plan below
+        d.pad = 0;
         h->probs_host[p] = d;
         if (o->cross_check) col_rows += pr.t_count;
     }
@@ -314,7 +324,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     // -- choose the kernel variant ----------------------------------------------------------------
     const int mode = o->cross_check ? 1 : ((o->k >= 2 || o->ratio >= 0) ? 2 : 0);
     const int mask = o->mask_kind;
-    const int pm = h->popc_mode ? h->popc_mode : 40;  // measured best for every mode: profiles/sweep_r01.md
+    const int pm = h->popc_mode ? h->popc_mode : 40;  // measured best for every mode: profiles/sweep_r01.json
     int r = h->qpt;
     int slots = 0, seg_rows = 0;
     if (r != 1 && r != 2 && r != 4) {
@@ -340,83 +350,84 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
-    const int plan_sig[6] = {n_problems, r, mode * 64 + n_groups, h->segment_rows, h->waves, slots};
+    const int plan_sig[6] = {n_problems, r, mode, h->segment_rows, h->waves, slots};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
                           h->plan_problems.size() == (size_t)n_problems &&
                           std::memcmp(h->plan_problems.data(), problems, sizeof(bfm_problem_t) * (size_t)n_problems) == 0;
     if (!plan_hit) {
-    plan_segments(h, problems, n_problems, r, slots, n_groups, h->segs_host, h->seg_begin, &seg_rows);
-    h->plan_seg_rows = seg_rows;
-        if (o->cross_check) {
-        // segment order follows problem order: recover each segment's problem by walking
-        size_t si = 0;
-        for (int p = 0; p < n_problems; ++p) {
-            const bfm_problem_t &pr = problems[p];
-            if (pr.q_count <= 0 || pr.t_count <= 0) continue;
-            const int nsp = (pr.t_count + seg_rows - 1) / seg_rows;
-            const int nqb = (pr.q_count + NT * r - 1) / (NT * r);
-            for (int i = 0; i < nsp * nqb; ++i, ++si) h->segs_host[si].col0 = h->probs_host[p].col0;
-        }
+        plan_segments(h, problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows);
+        h->plan_seg_rows = seg_rows;
+        h->plan_probs = h->probs_host;
+        for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = h->seg_begin[p + 1] - h->seg_begin[p];
     }
-    }  // !plan_hit
     seg_rows = h->plan_seg_rows;
     const size_t n_segs = h->segs_host.size();
 
-    // -- workspace: self-cleaning (the finalize kernel restores every slot it read to all-ones), so
-    //    a memset is only queued after (re)allocation or after a call that failed half-way -----------
+    // -- workspace: [row state u64 | column keys u32 | done counters u32], all-ones when idle.  It is
+    //    self-cleaning (the finalizing CTA restores every slot it read), so a memset is only queued
+    //    after (re)allocation or after a call that failed half-way --------------------------------------
     const size_t state_bytes = (size_t)n_out_rows * 8;
     const size_t col_bytes = (size_t)col_rows * 4;
+    const size_t done_bytes = (size_t)n_problems * 4;
     const unsigned state_gen = h->state.generation;
-    int rc = ensure(h, h->state, state_bytes + col_bytes);
+    int rc = ensure(h, h->state, state_bytes + col_bytes + done_bytes);
     if (rc) return rc;
     if (h->state.generation != state_gen) h->state_clean = false;
     unsigned long long *rowstate = static_cast<unsigned long long *>(h->state.p);
     uint32_t *colkeys = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes);
+    uint32_t *done = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes + col_bytes);
 
-    const size_t prob_bytes = ((size_t)n_problems * sizeof(Problem) + 15) & ~(size_t)15;
+    const size_t prob_bytes = (size_t)n_problems * sizeof(Problem);
     const size_t table_bytes = prob_bytes + n_segs * sizeof(Segment);
     const unsigned tables_gen = h->tables.generation;
     rc = ensure(h, h->tables, table_bytes);
     if (rc) return rc;
     if (!plan_hit || h->tables.generation != tables_gen) {
-    h->plan_valid = false;
-    const int slot = h->table_slot;
-    h->table_slot = (slot + 1) % N_TABLE_SLOTS;
-    if (h->h_tables_cap[slot] < table_bytes) {
-        if (h->h_tables[slot]) {
-            CU_TRY(h, cudaEventSynchronize(h->table_ev[slot]));
-            CU_TRY(h, cudaFreeHost(h->h_tables[slot]));
-            h->h_tables[slot] = nullptr;
+        h->plan_valid = false;
+        const int slot = h->table_slot;
+        h->table_slot = (slot + 1) % N_TABLE_SLOTS;
+        if (h->h_tables_cap[slot] < table_bytes) {
+            if (h->h_tables[slot]) {
+                CU_TRY(h, cudaEventSynchronize(h->table_ev[slot]));
+                CU_TRY(h, cudaFreeHost(h->h_tables[slot]));
+                h->h_tables[slot] = nullptr;
+            }
+            const size_t want = table_bytes + table_bytes / 2 + 4096;
+            CU_TRY(h, cudaMallocHost(&h->h_tables[slot], want));
+            h->h_tables_cap[slot] = want;
+        } else {
+            CU_TRY(h, cudaEventSynchronize(h->table_ev[slot]));  // previous upload from this slot is done
         }
-        const size_t want = table_bytes + table_bytes / 2 + 4096;
-        CU_TRY(h, cudaMallocHost(&h->h_tables[slot], want));
-        h->h_tables_cap[slot] = want;
-    } else {
-        CU_TRY(h, cudaEventSynchronize(h->table_ev[slot]));  // previous upload from this slot is done
-    }
-    std::memcpy(h->h_tables[slot], h->probs_host.data(), (size_t)n_problems * sizeof(Problem));
-    if (n_segs) std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes, h->segs_host.data(), n_segs * sizeof(Segment));
-    // NOTE: the device table is shared by consecutive calls on one handle; stream order keeps the
-    // upload of call n+1 behind the kernels of call n when both use the same stream (the contract).
-    CU_TRY(h, cudaMemcpyAsync(h->tables.p, h->h_tables[slot], table_bytes, cudaMemcpyHostToDevice, st));
-    CU_TRY(h, cudaEventRecord(h->table_ev[slot], st));
-    std::memcpy(h->plan_sig, plan_sig, sizeof(plan_sig));
-    h->plan_problems.assign(problems, problems + n_problems);
-    h->plan_valid = true;
+        std::memcpy(h->h_tables[slot], h->plan_probs.data(), prob_bytes);
+        std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes, h->segs_host.data(), n_segs * sizeof(Segment));
+        // NOTE: the device table is shared by consecutive calls on one handle; stream order keeps the
+        // upload of call n+1 behind the kernel of call n when both use the same stream (the contract).
+        CU_TRY(h, cudaMemcpyAsync(h->tables.p, h->h_tables[slot], table_bytes, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaEventRecord(h->table_ev[slot], st));
+        std::memcpy(h->plan_sig, plan_sig, sizeof(plan_sig));
+        h->plan_problems.assign(problems, problems + n_problems);
+        h->plan_valid = true;
     }
     const Problem *d_probs = static_cast<const Problem *>(h->tables.p);
     const Segment *d_segs = reinterpret_cast<const Segment *>(static_cast<char *>(h->tables.p) + prob_bytes);
 
-    if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], st));
     if (!h->state_clean) CU_TRY(h, cudaMemsetAsync(h->state.p, 0xFF, h->state.cap, st));
-    h->state_clean = false;  // set again once the finalize kernel (which restores the state) is queued
+    h->state_clean = false;  // set again once the kernel (which restores the state) is queued
 
-    int kernels = 0;
     ScanParams sp;
+    std::memset(&sp, 0, sizeof(sp));
     sp.q = reinterpret_cast<const uint4 *>(q);
     sp.t = reinterpret_cast<const uint4 *>(t);
+    sp.segs = d_segs;
+    sp.problems = d_probs;
     sp.rowstate = rowstate;
     sp.colkeys = colkeys;
+    sp.done = done;
+    if (gate) {
+        sp.ready = gate->ready;
+        sp.ready_base = gate->base;
+        sp.status = gate->status;
+    }
     sp.mask = o->mask;
     sp.mask_stride = o->mask_row_stride;
     sp.q_xy = reinterpret_cast<const float2 *>(o->q_xy);
@@ -428,63 +439,41 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     sp.mul_one = 1u;
     sp.mul_two = 2u;
     sp.mul_four = 4u;
-    bfm::FinalizeParams fp;
-    fp.rowstate = rowstate;
-    fp.colkeys = colkeys;
-    fp.k = o->k;
-    fp.cross_check = o->cross_check;
-    fp.max_distance = o->max_distance;
-    fp.use_ratio = o->ratio >= 0;
-    fp.ratio = o->ratio;
-    fp.knn_idx = knn_idx;
-    fp.knn_dist = knn_dist;
-    fp.m_query = m_query;
-    fp.m_train = m_train;
-    fp.m_dist = m_dist;
-    const ScanFn fn = pick_scan(r, mode, mask, pm);
-    for (int g = 0; g < n_groups; ++g) {
-        const int p0 = gbounds[g], p1 = gbounds[g + 1];
-        if (p1 <= p0) continue;
-        if (hooks && hooks->before) {
-            rc = hooks->before(hooks->ctx, g);
-            if (rc) return rc;
-        }
-        const int s0 = h->seg_begin[p0], s1 = h->seg_begin[p1];
-        if (s1 > s0) {
-            sp.segs = d_segs + s0;
-            if (h->timing && g == 0) CU_TRY(h, cudaEventRecord(h->ev[1], st));
-            fn<<<(unsigned)(s1 - s0), NT, 0, st>>>(sp);
-            CU_TRY(h, cudaGetLastError());
-            if (h->timing && g == n_groups - 1) CU_TRY(h, cudaEventRecord(h->ev[2], st));
-            ++kernels;
-        }
-        fp.problems = d_probs + p0;
-        fp.m_count = m_count ? m_count + p0 : nullptr;
-        bfm::bfm_finalize_kernel<FIN_NT><<<(unsigned)(p1 - p0), FIN_NT, 0, st>>>(fp);
-        CU_TRY(h, cudaGetLastError());
-        ++kernels;
-        if (hooks && hooks->after) {
-            rc = hooks->after(hooks->ctx, g);
-            if (rc) return rc;
-        }
+    sp.k = o->k;
+    sp.cross_check = o->cross_check;
+    sp.max_distance = o->max_distance;
+    sp.use_ratio = o->ratio >= 0;
+    sp.ratio = o->ratio;
+    sp.n_dest = n_dests;
+    for (int d = 0; d < n_dests; ++d) {
+        sp.dest[d].knn_idx = dests[d].knn_idx;
+        sp.dest[d].knn_dist = dests[d].knn_dist;
+        sp.dest[d].m_query = dests[d].m_query;
+        sp.dest[d].m_train = dests[d].m_train;
+        sp.dest[d].m_dist = dests[d].m_dist;
+        sp.dest[d].m_count = dests[d].m_count;
     }
-    h->state_clean = true;  // every slot touched above is restored by its group's finalize kernel
-    if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[3], st));
+    const ScanFn fn = pick_scan(r, mode, mask, pm);
+    if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], st));
+    fn<<<(unsigned)n_segs, NT, 0, st>>>(sp);
+    CU_TRY(h, cudaGetLastError());
+    if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
+    h->state_clean = true;  // every slot touched is restored by the CTA that finalizes its problem
 
-    h->launches += kernels;
-    h->info.kernels_launched = kernels;
+    h->launches += 1;
+    h->info.kernels_launched = 1;
     h->info.scan_grid = (int32_t)n_segs;
     h->info.scan_block = NT;
     h->info.queries_per_thread = r;
     h->info.popc_mode = pm;
     h->info.segments = (int32_t)n_segs;
     h->info.train_rows_per_segment = seg_rows;
-    if (h->timing) {
-        CU_TRY(h, cudaEventSynchronize(h->ev[3]));
-        if (n_segs) CU_TRY(h, cudaEventElapsedTime(&h->info.scan_ms, h->ev[1], h->ev[2]));
-        CU_TRY(h, cudaEventElapsedTime(&h->info.total_ms, h->ev[0], h->ev[3]));
+    if (h->timing && !gate) {
+        CU_TRY(h, cudaEventSynchronize(h->ev[1]));
+        CU_TRY(h, cudaEventElapsedTime(&h->info.scan_ms, h->ev[0], h->ev[1]));
+        h->info.total_ms = h->info.scan_ms;
     }
-    if (std::getenv("BFM_CHECK_CLEAN")) {  // debugging aid: the workspace must be all-ones after every call
+    if (std::getenv("BFM_CHECK_CLEAN") && !gate) {  // debugging aid: the workspace must be all-ones after every call
         CU_TRY(h, cudaDeviceSynchronize());
         std::vector<unsigned char> host(h->state.cap);
         CU_TRY(h, cudaMemcpy(host.data(), h->state.p, h->state.cap, cudaMemcpyDeviceToHost));
@@ -492,90 +481,13 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         for (size_t i = 0; i < host.size(); ++i)
             if (host[i] != 0xFF) { if (!bad) first = i; ++bad; }
         if (bad)
-            std::fprintf(stderr, "[bfm check] workspace dirty after call: %zu bytes, first at %zu (rows=%d col_rows=%lld state_bytes=%zu cap=%zu mode=%d P=%d groups=%d)\n",
-                         bad, first, n_out_rows, col_rows, state_bytes, h->state.cap, mode, n_problems, n_groups);
+            std::fprintf(stderr, "[bfm check] workspace dirty after call: %zu bytes, first at %zu (rows=%d col_rows=%lld state_bytes=%zu cap=%zu mode=%d P=%d)\n",
+                         bad, first, n_out_rows, col_rows, state_bytes, h->state.cap, mode, n_problems);
     }
     return BFM_OK;
 }
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
-// The host path: stage in, run the device path on the handle's stream, stage out, wait.
-int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t, int32_t nt_rows,
-             const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
-             const bfm_options_t *o, int32_t *knn_idx, int32_t *knn_dist, int32_t *m_query,
-             int32_t *m_train, int32_t *m_dist, int32_t *m_count) {
-    if (n_problems <= 0 || n_out_rows <= 0) return BFM_OK;
-    cudaStream_t st = h->stream;
-    const size_t qb = (size_t)nq_rows * 32, tb = (size_t)nt_rows * 32;
-    size_t mask_b = 0, qxy_b = 0, txy_b = 0;
-    if (o->mask_kind == BFM_MASK_DENSE && o->mask) mask_b = problems[0].q_count > 0 ? (size_t)(problems[0].q_count - 1) * (size_t)o->mask_row_stride + (size_t)problems[0].t_count : 0;
-    if (o->mask_kind == BFM_MASK_WINDOW) { qxy_b = (size_t)nq_rows * 8; txy_b = (size_t)nt_rows * 8; }
-    const size_t o_q = 0, o_t = align256(o_q + qb), o_m = align256(o_t + tb), o_qxy = align256(o_m + mask_b),
-                 o_txy = align256(o_qxy + qxy_b), in_total = align256(o_txy + txy_b);
-    int rc = ensure(h, h->d_in, in_total);
-    if (rc) return rc;
-    char *din = static_cast<char *>(h->d_in.p);
-    if (qb) CU_TRY(h, cudaMemcpyAsync(din + o_q, q, qb, cudaMemcpyHostToDevice, st));
-    if (tb) CU_TRY(h, cudaMemcpyAsync(din + o_t, t, tb, cudaMemcpyHostToDevice, st));
-    bfm_options_t od = *o;
-    if (mask_b) {
-        CU_TRY(h, cudaMemcpyAsync(din + o_m, o->mask, mask_b, cudaMemcpyHostToDevice, st));
-        od.mask = reinterpret_cast<const uint8_t *>(din + o_m);
-    }
-    if (qxy_b) {
-        CU_TRY(h, cudaMemcpyAsync(din + o_qxy, o->q_xy, qxy_b, cudaMemcpyHostToDevice, st));
-        CU_TRY(h, cudaMemcpyAsync(din + o_txy, o->t_xy, txy_b, cudaMemcpyHostToDevice, st));
-        od.q_xy = reinterpret_cast<const float *>(din + o_qxy);
-        od.t_xy = reinterpret_cast<const float *>(din + o_txy);
-    }
-    // outputs: [knn_idx | knn_dist | m_query | m_train | m_dist | m_count] in one block
-    const size_t knn_b = knn_idx ? (size_t)n_out_rows * o->k * 4 : 0;
-    const size_t m_b = m_count ? (size_t)n_out_rows * 4 : 0;
-    const size_t cnt_b = m_count ? (size_t)n_problems * 4 : 0;
-    const size_t out_total = 2 * knn_b + 3 * m_b + cnt_b;
-    rc = ensure(h, h->d_out, std::max<size_t>(out_total, 16));
-    if (rc) return rc;
-    if (h->h_out_cap < out_total) {
-        if (h->h_out) CU_TRY(h, cudaFreeHost(h->h_out));
-        h->h_out = nullptr;
-        const size_t want = out_total + out_total / 4 + 4096;
-        CU_TRY(h, cudaMallocHost(&h->h_out, want));
-        h->h_out_cap = want;
-    }
-    char *dout = static_cast<char *>(h->d_out.p);
-    int32_t *d_ki = knn_idx ? reinterpret_cast<int32_t *>(dout) : nullptr;
-    int32_t *d_kd = knn_idx ? reinterpret_cast<int32_t *>(dout + knn_b) : nullptr;
-    int32_t *d_mq = m_count ? reinterpret_cast<int32_t *>(dout + 2 * knn_b) : nullptr;
-    int32_t *d_mt = m_count ? reinterpret_cast<int32_t *>(dout + 2 * knn_b + m_b) : nullptr;
-    int32_t *d_md = m_count ? reinterpret_cast<int32_t *>(dout + 2 * knn_b + 2 * m_b) : nullptr;
-    int32_t *d_mc = m_count ? reinterpret_cast<int32_t *>(dout + 2 * knn_b + 3 * m_b) : nullptr;
-    rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows,
-                    reinterpret_cast<const uint8_t *>(din + o_t), nt_rows, problems, n_problems, n_out_rows,
-                    &od, d_ki, d_kd, d_mq, d_mt, d_md, d_mc, st);
-    if (rc) return rc;
-    if (out_total) CU_TRY(h, cudaMemcpyAsync(h->h_out, dout, out_total, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaStreamSynchronize(st));
-    const char *ho = static_cast<const char *>(h->h_out);
-    if (knn_idx) {
-        std::memcpy(knn_idx, ho, knn_b);
-        std::memcpy(knn_dist, ho + knn_b, knn_b);
-    }
-    if (m_count) {
-        std::memcpy(m_count, ho + 2 * knn_b + 3 * m_b, cnt_b);
-        // only the filled prefix of every problem's slice is meaningful; copy exactly that
-        const int32_t *hq = reinterpret_cast<const int32_t *>(ho + 2 * knn_b);
-        const int32_t *ht = reinterpret_cast<const int32_t *>(ho + 2 * knn_b + m_b);
-        const int32_t *hd = reinterpret_cast<const int32_t *>(ho + 2 * knn_b + 2 * m_b);
-        for (int p = 0; p < n_problems; ++p) {
-            const size_t b = (size_t)problems[p].out_begin, n = (size_t)m_count[p];
-            std::memcpy(m_query + b, hq + b, n * 4);
-            std::memcpy(m_train + b, ht + b, n * 4);
-            std::memcpy(m_dist + b, hd + b, n * 4);
-        }
-    }
-    return BFM_OK;
-}
 
 #include "bfm_pipeline.cuh"
 
@@ -618,17 +530,19 @@ int bfm_create(int device, bfm_handle_t *out) {
     h->sm_count = prop.multiProcessorCount;
     std::memset(h->occ_cache, 0, sizeof(h->occ_cache));
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < 32; ++i) ok = cudaEventCreate(&h->chunk_ev[i]) == cudaSuccess;
-    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+              cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_ready, 256) == cudaSuccess && cudaMemset(h->d_ready, 0, 256) == cudaSuccess &&
+         cudaMallocHost(&h->h_marks, sizeof(unsigned long long) * 2 * MAX_COPY_CHUNKS) == cudaSuccess &&
+         cudaMallocHost(&h->h_status, 64) == cudaSuccess;
+    if (ok) *h->h_status = 0;
     for (int i = 0; ok && i < N_TABLE_SLOTS; ++i) {
         ok = cudaEventCreateWithFlags(&h->table_ev[i], cudaEventDisableTiming) == cudaSuccess;
         if (ok) ok = cudaEventRecord(h->table_ev[i], h->stream) == cudaSuccess;
     }
     if (!ok) {
-        g_create_error = std::string("stream/event creation failed: ") + cudaGetErrorString(cudaGetLastError());
-        delete h;
+        g_create_error = std::string("stream/event/buffer creation failed: ") + cudaGetErrorString(cudaGetLastError());
+        bfm_destroy(h);
         return BFM_ERR_CUDA;
     }
     *out = h;
@@ -639,19 +553,19 @@ int bfm_destroy(bfm_handle_t h) {
     if (!h) return BFM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->d_out})
+    for (DevBuf *b : {&h->state, &h->tables, &h->d_in})
         if (b->p) cudaFree(b->p);
+    if (h->d_ready) cudaFree(h->d_ready);
+    if (h->h_marks) cudaFreeHost(h->h_marks);
+    if (h->h_status) cudaFreeHost(h->h_status);
     for (int i = 0; i < N_TABLE_SLOTS; ++i) {
         if (h->h_tables[i]) cudaFreeHost(h->h_tables[i]);
         if (h->table_ev[i]) cudaEventDestroy(h->table_ev[i]);
     }
     if (h->h_out) cudaFreeHost(h->h_out);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-    for (int i = 0; i < 32; ++i)
-        if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
     if (h->in_stream) cudaStreamDestroy(h->in_stream);
-    if (h->out_stream) cudaStreamDestroy(h->out_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return BFM_OK;
@@ -659,12 +573,8 @@ int bfm_destroy(bfm_handle_t h) {
 
 const char *bfm_last_error(bfm_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int bfm_match_batched(bfm_handle_t h, int mem, const uint8_t *q, int32_t n_query_rows, const uint8_t *t,
-                      int32_t n_train_rows, const bfm_problem_t *problems, int32_t n_problems,
-                      int32_t n_out_rows, const bfm_options_t *opts, int32_t *knn_idx, int32_t *knn_dist,
-                      int32_t *m_query, int32_t *m_train, int32_t *m_dist, int32_t *m_count, void *stream) {
-    if (!h) return BFM_ERR_INVALID;
-    h->err.clear();
+static int check_call(bfm_handle_t h, const uint8_t *q, int32_t n_query_rows, const uint8_t *t, int32_t n_train_rows,
+                      const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows, const bfm_options_t *opts) {
     if (n_problems < 0 || n_query_rows < 0 || n_train_rows < 0 || n_out_rows < 0)
         return fail(h, BFM_ERR_INVALID, "negative size");
     if (n_problems > 0 && !problems) return fail(h, BFM_ERR_INVALID, "problems is NULL");
@@ -672,16 +582,36 @@ int bfm_match_batched(bfm_handle_t h, int mem, const uint8_t *q, int32_t n_query
     if (rc) return rc;
     if ((n_query_rows > 0 && !q) || (n_train_rows > 0 && !t)) return fail(h, BFM_ERR_INVALID, "descriptor pointer is NULL");
     CU_TRY(h, cudaSetDevice(h->device));
+    return BFM_OK;
+}
+
+int bfm_match_batched(bfm_handle_t h, int mem, const uint8_t *q, int32_t n_query_rows, const uint8_t *t,
+                      int32_t n_train_rows, const bfm_problem_t *problems, int32_t n_problems,
+                      int32_t n_out_rows, const bfm_options_t *opts, int32_t *knn_idx, int32_t *knn_dist,
+                      int32_t *m_query, int32_t *m_train, int32_t *m_dist, int32_t *m_count, void *stream) {
+    if (!h) return BFM_ERR_INVALID;
+    h->err.clear();
+    int rc = check_call(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts);
+    if (rc) return rc;
+    const bfm_outputs_t out = {knn_idx, knn_dist, m_query, m_train, m_dist, m_count};
     if (mem == BFM_MEM_DEVICE)
-        return run_device(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, knn_idx,
-                          knn_dist, m_query, m_train, m_dist, m_count, stream == BFM_STREAM_OWN ? h->stream : static_cast<cudaStream_t>(stream));
-    if (mem == BFM_MEM_HOST && pipeline_eligible(h, n_query_rows, n_train_rows, problems, n_problems, opts))
-        return run_host_pipelined(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, knn_idx,
-                                  knn_dist, m_query, m_train, m_dist, m_count);
+        return run_device(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, &out, 1,
+                          stream == BFM_STREAM_OWN ? h->stream : static_cast<cudaStream_t>(stream));
     if (mem == BFM_MEM_HOST)
-        return run_host(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, knn_idx,
-                        knn_dist, m_query, m_train, m_dist, m_count);
+        return run_host(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, out);
     return fail(h, BFM_ERR_INVALID, "mem must be BFM_MEM_HOST or BFM_MEM_DEVICE");
+}
+
+int bfm_match_batched_multi(bfm_handle_t h, const uint8_t *q, int32_t n_query_rows, const uint8_t *t,
+                            int32_t n_train_rows, const bfm_problem_t *problems, int32_t n_problems,
+                            int32_t n_out_rows, const bfm_options_t *opts, const bfm_outputs_t *dests,
+                            int32_t n_dests, void *stream) {
+    if (!h) return BFM_ERR_INVALID;
+    h->err.clear();
+    int rc = check_call(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts);
+    if (rc) return rc;
+    return run_device(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, dests, n_dests,
+                      stream == BFM_STREAM_OWN ? h->stream : static_cast<cudaStream_t>(stream));
 }
 
 int bfm_knn(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8_t *t, int32_t nt,
@@ -721,7 +651,7 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "segment_rows must be >= 0");
         h->segment_rows = value;
     } else if (k == "pipeline_chunks") {
-        if (value < 0 || value > 16) return fail(h, BFM_ERR_INVALID, "pipeline_chunks must be 0 (auto), 1 (off) .. 16");
+        if (value < 0 || value > MAX_COPY_CHUNKS) return fail(h, BFM_ERR_INVALID, "pipeline_chunks must be 0 (auto), 1 (off) .. 64");
         h->pipeline_chunks = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");

@@ -30,24 +30,43 @@ constexpr uint32_t KEY16_DEAD = DIST_MASKED << 7;          // same, for the chun
 constexpr int TT = 128;                         // train rows per shared-memory chunk (4 KB)
 
 // One work item: a block of BQ = NT*R query rows against a contiguous range of train rows of
-// the same problem.  Built on the host by the planner (bfm_api.cu: plan_segments).
+// the same problem.  Built on the host by the planner (bfm_api.cu: plan_segments).  Every problem
+// has at least one segment (an empty problem gets one with t_count == 0) because the CTA that
+// completes a problem's last segment also finalizes it.
 struct __align__(16) Segment {
     int32_t q_row0;    // first query row (global row in the query array)
-    int32_t q_valid;   // rows of this block that exist (1..BQ)
+    int32_t q_valid;   // rows of this block that exist (0..BQ)
     int32_t q_local0;  // index of q_row0 inside its problem (cv2 queryIdx of the first row)
     int32_t out_row0;  // output row of the first query of the block
     int32_t t_row0;    // first train row (global row in the train array)
-    int32_t t_count;   // train rows in this segment (>= 1)
+    int32_t t_count;   // train rows in this segment (0 only for an empty problem)
     int32_t t_local0;  // index of t_row0 inside its problem (cv2 trainIdx)
-    int32_t col0;      // first column-key slot of this segment's problem (cross-check)
+    int32_t problem;   // index into the problem table
 };
 
+struct __align__(16) Problem {   // device view of bfm_problem_t
+    int32_t q_begin, q_count, t_begin, t_count, out_begin;
+    int32_t col0;      // first column-key slot of this problem (cross-check)
+    int32_t n_segs;    // segments of this problem (>= 1)
+    int32_t pad;
+};
+
+constexpr int MAX_DEST = 8;  // result replicas (this GPU + NVLink peers)
+
+// Everything one launch needs.  The kernel is scan + finalize in one: there is no second launch.
 struct ScanParams {
     const uint4 *q;                  // [rows][2] 16-byte halves of the 32-byte descriptors
     const uint4 *t;
     const Segment *segs;
+    const Problem *problems;
     unsigned long long *rowstate;    // [out rows] (best key << 32) | second key
-    uint32_t *colkeys;               // [sum of problem train rows] (cross-check), problem base = Segment::col0
+    uint32_t *colkeys;               // [sum of problem train rows] (cross-check), problem base = Problem::col0
+    uint32_t *done;                  // [problems] completed-segment counters, all-ones when idle
+    // input gating (pipelined host path): a CTA starts once the copy engine has landed the rows it
+    // reads; ready[0] / ready[1] = ready_base + query / train rows uploaded so far.  NULL = resident.
+    const unsigned long long *ready;
+    unsigned long long ready_base;
+    uint32_t *status;                // set non-zero if the gate timed out (host reports the error)
     const uint8_t *mask;             // dense mask (single problem): [q_local][mask_stride]
     long long mask_stride;
     const float2 *q_xy;              // window: pixel coordinates per query / train row
@@ -59,6 +78,21 @@ struct ScanParams {
     uint32_t mul_lo16;  // 1 << 7
     uint32_t mul_hi16;  // 1 << 23
     uint32_t mul_one, mul_two, mul_four;  // weights of the carry-save popcount sum, same reason
+    // ---- finalize (run by the CTA that completes a problem's last segment) ----------------------
+    int32_t k;             // columns of the knn table (1 or 2 on this path)
+    int32_t cross_check;
+    int32_t max_distance;  // < 0 off
+    int32_t use_ratio;
+    double ratio;
+    // Result destinations.  dest[0] is the caller's buffers (device memory, or pinned host memory
+    // written over PCIe on the host path); dest[1..] are the same buffers of NVLink peers
+    // (multi-GPU gather fused into the epilogue).  Each pointer may be NULL.
+    int32_t n_dest;
+    struct Dest {
+        int32_t *knn_idx, *knn_dist;                 // [out rows][k]
+        int32_t *m_query, *m_train, *m_dist;         // [out rows]
+        int32_t *m_count;                            // [problems]
+    } dest[MAX_DEST];
 };
 
 // ---- PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------------------
@@ -87,6 +121,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 
 // ---- 256-bit Hamming distance ------------------------------------------------------------------
@@ -182,6 +227,116 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
     }
 }
 
+// ---- finalize: decode keys, cross-check / ratio / distance gate, ordered compaction -----------------
+// Run by ONE CTA per problem: the one whose segment completed the problem (last-arriver pattern,
+// see the kernel tail).  Decodes the packed keys into the dense cv2 knnMatch table, applies
+// cross-check (colkey[trainIdx] == (d, queryIdx)), the ratio test in fp64 exactly as Python
+// evaluates `m.distance < ratio * n.distance`, the distance gate, and compacts the surviving
+// matches in ascending queryIdx order.  Every workspace slot it reads is reset to all-ones, so the
+// workspace is self-cleaning and a steady-state call needs no memset.  Results go to every
+// destination in p.dest (plain stores: device memory, pinned host memory or NVLink peer memory).
+constexpr int FIN_RPT = 4;  // rows per thread and tile
+
+template <int NT>
+__device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi, int (*s_cnt)[NT / 32]) {
+    constexpr int NW = NT / 32;
+    const Problem pr = p.problems[pi];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int k = p.k;
+    int running = 0;
+    for (int base = 0; base < pr.q_count; base += NT * FIN_RPT) {
+        int idx1[FIN_RPT], d1[FIN_RPT];
+        bool keep[FIN_RPT];
+        uint32_t bal[FIN_RPT];
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            const int i = base + j * NT + tid;
+            const bool in = i < pr.q_count;
+            uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
+            if (in) {
+                unsigned long long *slot = p.rowstate + (size_t)pr.out_begin + i;
+                const unsigned long long st = __ldcg(slot);
+                *slot = ~0ull;
+                k1 = (uint32_t)(st >> 32);
+                k2 = (uint32_t)st;
+            }
+            const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
+            idx1[j] = has1 ? (int)(k1 & IDX_MASK) : -1;
+            d1[j] = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
+            const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
+            if (in) {
+                const size_t o = ((size_t)pr.out_begin + i) * (size_t)k;
+                for (int d = 0; d < p.n_dest; ++d) {
+                    int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
+                    if (!ki) continue;
+                    if (k > 1) {   // 8-byte aligned: o is even
+                        *reinterpret_cast<int2 *>(ki + o) = make_int2(idx1[j], idx2);
+                        *reinterpret_cast<int2 *>(kd + o) = make_int2(d1[j], d2);
+                    } else {
+                        ki[o] = idx1[j];
+                        kd[o] = d1[j];
+                    }
+                }
+            }
+            bool kp = in && has1;
+            if (kp && p.cross_check)
+                kp = __ldcg(p.colkeys + (size_t)pr.col0 + idx1[j]) == (((uint32_t)d1[j] << DIST_SHIFT) | (uint32_t)i);
+            if (kp && p.use_ratio) kp = has2 && ((double)d1[j] < p.ratio * (double)d2);
+            if (kp && p.max_distance >= 0) kp = d1[j] <= p.max_distance;
+            keep[j] = kp;
+            bal[j] = __ballot_sync(0xffffffffu, kp);
+            if (lane == 0) s_cnt[j][warp] = __popc(bal[j]);
+        }
+        __syncthreads();
+        // ordered compaction: rows ascend with (j, warp, lane)
+        int before = running, tile_total = 0;
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int c = s_cnt[j][w];
+                tile_total += c;
+                if (j == 0 && w < warp) before += c;
+            }
+        }
+        int pos_j = before;   // rank of this warp's first kept row of slot j = 0
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            if (j > 0) {
+                // rows of slot j come after every row of slot j-1: add the rest of slot j-1 and the
+                // warps before this one in slot j
+                int add = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    if (w >= warp) add += s_cnt[j - 1][w];
+                    if (w < warp) add += s_cnt[j][w];
+                }
+                pos_j += add;
+            }
+            if (keep[j]) {
+                const size_t o = (size_t)pr.out_begin + pos_j + __popc(bal[j] & lt);
+                const int i = base + j * NT + tid;
+                for (int d = 0; d < p.n_dest; ++d) {
+                    if (!p.dest[d].m_count) continue;
+                    p.dest[d].m_query[o] = i;
+                    p.dest[d].m_train[o] = idx1[j];
+                    p.dest[d].m_dist[o] = d1[j];
+                }
+            }
+        }
+        running += tile_total;
+        __syncthreads();   // s_cnt is rewritten by the next tile
+    }
+    if (tid == 0)
+        for (int d = 0; d < p.n_dest; ++d)
+            if (p.dest[d].m_count) p.dest[d].m_count[pi] = running;
+    if (p.cross_check) {
+        // every column-key read of this problem happened above, in this CTA
+        for (int j = tid; j < pr.t_count; j += NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
+    }
+}
+
 // ---- the distance-scan kernel --------------------------------------------------------------------
 // R     queries per thread (register tile)
 // K     1 or 2 neighbours tracked per query
@@ -194,7 +349,7 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
 // chunk.  Shared memory: 2 x 4 KB train rows, 2 x 1 KB pixel coords (window), 2 x 2 KB column
 // keys (cross-check).
 template <int R, int K, bool CROSS, int MASK, int PM, int NT>
-__global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const __grid_constant__ ScanParams p) {
     constexpr int NW = NT / 32;
     constexpr bool XF = pm_transformed(PM);
     static_assert(NT == TT, "one thread per staged train row");
@@ -202,11 +357,41 @@ __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ float2 s_xy[MASK == 2 ? 2 : 1][MASK == 2 ? TT : 1];
     __shared__ uint32_t s_col[CROSS ? 2 : 1][CROSS ? NW : 1][CROSS ? TT : 1];
+    __shared__ int s_cnt[FIN_RPT][NW];
+    __shared__ int s_flag;
 
     const Segment sg = p.segs[blockIdx.x];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    int col0 = 0;
+    if (CROSS) col0 = p.problems[sg.problem].col0;
+
+    // -- input gate (pipelined host path): wait until the copy engine has landed this segment's rows
+    if (p.ready != nullptr) {
+        if (tid == 0) {
+            const unsigned long long need_q = p.ready_base + (unsigned long long)(sg.q_row0 + sg.q_valid);
+            const unsigned long long need_t = p.ready_base + (unsigned long long)(sg.t_row0 + sg.t_count);
+            const unsigned long long t0 = global_timer_ns();
+            int ok = 1;
+            while (ld_relaxed_sys(p.ready) < need_q || ld_relaxed_sys(p.ready + 1) < need_t) {
+                __nanosleep(200);
+                if (global_timer_ns() - t0 > 4000000000ull) {   // 4 s: the copies were never queued
+                    ok = 0;
+                    atomicExch(p.status, 1u);
+                    break;
+                }
+            }
+            // the rows were written by the copy engine before the flag: order our reads (generic and
+            // async proxy) after the flag read
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+            s_flag = ok;
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        __syncthreads();   // s_flag is reused by the kernel tail
+    }
 
     // -- this thread's R query descriptors (two coalesced 16-byte loads each) ---------------------
     uint32_t qw[R][8];
@@ -267,13 +452,15 @@ __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
         mbar_fence_init();
     }
     __syncthreads();
-    if (tid == 0) {
-        fetch(0);
-        if (nchunks > 1) fetch(1);
+    if (nchunks > 0) {
+        if (tid == 0) {
+            fetch(0);
+            if (nchunks > 1) fetch(1);
+        }
+        stage_xy(0);
+        if (nchunks > 1) stage_xy(1);
+        land(0);
     }
-    stage_xy(0);
-    if (nchunks > 1) stage_xy(1);
-    land(0);
     __syncthreads();
 
     for (int c = 0; c < nchunks; ++c) {
@@ -380,7 +567,7 @@ __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
                 uint32_t m = s_col[b][0][j];
 #pragma unroll
                 for (int w = 1; w < NW; ++w) m = min(m, s_col[b][w][j]);
-                if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)sg.col0 + sg.t_local0 + c * TT + j, m);
+                if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)col0 + sg.t_local0 + c * TT + j, m);
             }
         }
     }
@@ -407,84 +594,21 @@ __global__ void __launch_bounds__(NT) bfm_scan_kernel(const ScanParams p) {
             }
         }
     }
-}
 
-// ---- finalize: decode keys, cross-check / ratio / distance gate, ordered compaction -----------------
-struct Problem {   // mirrors bfm_problem_t; `col0` (reserved there) = first column-key slot
-    int32_t q_begin, q_count, t_begin, t_count, out_begin, col0;
-};
-
-struct FinalizeParams {
-    unsigned long long *rowstate;   // read, then reset to all-ones: the workspace is self-cleaning,
-    uint32_t *colkeys;              // so a steady-state call needs no memset launch
-    const Problem *problems;
-    int32_t k;             // columns of the knn table (1 or 2 on this path)
-    int32_t cross_check;
-    int32_t max_distance;  // < 0 off
-    int32_t use_ratio;
-    double ratio;
-    int32_t *knn_idx, *knn_dist;                 // nullable
-    int32_t *m_query, *m_train, *m_dist, *m_count;  // nullable (all or none)
-};
-
-template <int NT>
-__global__ void __launch_bounds__(NT) bfm_finalize_kernel(const FinalizeParams p) {
-    __shared__ int s_warp[NT / 32];
-    __shared__ int s_running;
-    const Problem pr = p.problems[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_running = 0;
+    // -- problem completion: the CTA whose segment is the last of its problem finalizes it -------------
+    // (threadfence + counter: every CTA's state updates are visible before its count is)
+    __threadfence();
     __syncthreads();
-    for (int base = 0; base < pr.q_count; base += NT) {
-        const int i = base + tid;
-        const bool in = i < pr.q_count;
-        uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
-        if (in) {
-            const unsigned long long st = p.rowstate[(size_t)pr.out_begin + i];
-            p.rowstate[(size_t)pr.out_begin + i] = ~0ull;
-            k1 = (uint32_t)(st >> 32);
-            k2 = (uint32_t)st;
-        }
-        const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
-        const int idx1 = has1 ? (int)(k1 & IDX_MASK) : -1, d1 = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
-        const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
-        if (in && p.knn_idx) {
-            const size_t o = ((size_t)pr.out_begin + i) * (size_t)p.k;
-            p.knn_idx[o] = idx1;
-            p.knn_dist[o] = d1;
-            if (p.k > 1) { p.knn_idx[o + 1] = idx2; p.knn_dist[o + 1] = d2; }
-        }
-        if (p.m_count) {
-            bool keep = in && has1;
-            if (keep && p.cross_check)
-                keep = p.colkeys[(size_t)pr.col0 + idx1] == (((uint32_t)d1 << DIST_SHIFT) | (uint32_t)i);
-            if (keep && p.use_ratio) keep = has2 && ((double)d1 < p.ratio * (double)d2);
-            if (keep && p.max_distance >= 0) keep = d1 <= p.max_distance;
-            // ordered (ascending queryIdx) compaction: ballot inside the warp, scan across warps
-            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_warp[warp] = __popc(bal);
-            __syncthreads();
-            int before = s_running;
-            for (int w = 0; w < warp; ++w) before += s_warp[w];
-            if (keep) {
-                const size_t o = (size_t)pr.out_begin + before + __popc(bal & ((1u << lane) - 1u));
-                p.m_query[o] = i;
-                p.m_train[o] = idx1;
-                p.m_dist[o] = d1;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int tot = 0;
-                for (int w = 0; w < NT / 32; ++w) tot += s_warp[w];
-                s_running += tot;
-            }
-            __syncthreads();
-        }
+    if (tid == 0) {
+        const uint32_t n_segs = (uint32_t)p.problems[sg.problem].n_segs;
+        const uint32_t old = atomicAdd(p.done + sg.problem, 1u);   // idles at 0xFFFFFFFF: first arrival wraps to 0
+        s_flag = (old == n_segs - 2u) ? 1 : 0;
+        if (s_flag) p.done[sg.problem] = 0xFFFFFFFFu;              // self-cleaning, like the rest of the workspace
     }
-    if (p.m_count && tid == 0) p.m_count[blockIdx.x] = s_running;
-    if (p.cross_check) {
-        __syncthreads();   // every column-key read of this problem happened in this CTA, above
-        for (int j = tid; j < pr.t_count; j += NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
+    __syncthreads();
+    if (s_flag) {
+        __threadfence();
+        finalize_problem<NT>(p, sg.problem, s_cnt);
     }
 }
 

@@ -74,6 +74,86 @@ def gather_ragged(local, group=None):
     return torch.cat(parts, dim=0) if parts else out, lens
 
 
+class FusedGather:
+    """Result tables of a sharded batch, gathered by the matching kernel itself.
+
+    Every rank owns a symmetric buffer (``torch.distributed._symmetric_memory``: CUDA IPC / fabric
+    handles exchanged once, peers mapped over NVLink) laid out as ``[slot][rank][table]``.  A step's
+    kernel (:meth:`Engine.match_batched_device` with ``replicas``) writes this rank's match lists
+    into slice ``rank`` of EVERY rank's buffer from its epilogue, so when all kernels have finished
+    each rank holds the full table - there is no separate collective, only :meth:`barrier`.
+    Two slots alternate between steps so a peer may still be reading step n while step n + 1 is
+    being written (one barrier per step is then sufficient).
+
+    Per-rank table (int32): ``m[3][n_out]`` (queryIdx, trainIdx, distance), ``count[P]`` and,
+    with ``want_knn``, ``knn_idx[n_out][k]`` / ``knn_dist[n_out][k]``.
+    """
+
+    SLOTS = 2
+
+    def __init__(self, n_out: int, n_problems: int, k: int = 1, want_knn: bool = False, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 8:
+            raise ValueError("the fused gather writes to at most 8 destinations (one NVLink box)")
+        self.n_out, self.P, self.k, self.want_knn = int(n_out), int(n_problems), int(k), bool(want_knn)
+        a2 = lambda n: (n + 3) & ~3  # keep every sub-table 16-byte aligned
+        self._o_m, self._o_c = 0, a2(3 * self.n_out)
+        self._o_ki = self._o_c + a2(self.P)
+        self._o_kd = self._o_ki + (a2(self.n_out * self.k) if want_knn else 0)
+        self.table = self._o_kd + (a2(self.n_out * self.k) if want_knn else 0)
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.buf = symm.empty(self.SLOTS * self.world * self.table, dtype=torch.int32, device=dev)
+        self.buf.fill_(-1)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self._ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.step = 0
+        torch.cuda.synchronize(dev)
+        self.hdl.barrier()
+
+    def _dest(self, base_ptr: int, slot: int) -> dict:
+        b = base_ptr + 4 * (slot * self.world + self.rank) * self.table
+        d = {"m_query": b + 4 * self._o_m, "m_train": b + 4 * (self._o_m + self.n_out),
+             "m_dist": b + 4 * (self._o_m + 2 * self.n_out), "count": b + 4 * self._o_c}
+        if self.want_knn:
+            d["knn_idx"], d["knn_dist"] = b + 4 * self._o_ki, b + 4 * self._o_kd
+        return d
+
+    def destinations(self):
+        """(own, peers) destination dicts of raw device pointers for the current step's slot."""
+        slot = self.step % self.SLOTS
+        own = self._dest(self._ptrs[self.rank], slot)
+        peers = [self._dest(self._ptrs[r], slot) for r in range(self.world) if r != self.rank]
+        return own, peers
+
+    def run(self, engine, q, t, problems, **kw):
+        """One sharded step: match this rank's block, results land in every rank's table."""
+        own, peers = self.destinations()
+        engine.match_batched_device(q, t, problems, out=own, replicas=peers, want_knn=self.want_knn, **kw)
+
+    def barrier(self):
+        """All ranks' kernels of this step have finished (and their NVLink writes with them): the
+        slot is complete on every rank.  Queued on the current stream; advances to the other slot."""
+        self.hdl.barrier()
+        self.step += 1
+
+    def tables(self, step=None):
+        """Views of the gathered tables of ``step`` (default: the last completed one):
+        m int32[world, 3, n_out], count int32[world, P] (+ knn_idx / knn_dist [world, n_out, k])."""
+        step = self.step - 1 if step is None else step
+        slot = step % self.SLOTS
+        v = self.buf[slot * self.world * self.table:(slot + 1) * self.world * self.table].view(self.world, self.table)
+        out = {"m": v[:, self._o_m:self._o_m + 3 * self.n_out].view(self.world, 3, self.n_out),
+               "count": v[:, self._o_c:self._o_c + self.P]}
+        if self.want_knn:
+            out["knn_idx"] = v[:, self._o_ki:self._o_ki + self.n_out * self.k].view(self.world, self.n_out, self.k)
+            out["knn_dist"] = v[:, self._o_kd:self._o_kd + self.n_out * self.k].view(self.world, self.n_out, self.k)
+        return out
+
+
 class ShardedMatcher:
     """Batched k-NN over a global list of keyframe pairs, sharded across the process group.
 

@@ -425,11 +425,16 @@ class Engine:
         return out[0, :n], out[1, :n], out[2, :n].to(torch.float32)
 
     def match_batched_device(self, q, t, problems: np.ndarray, k=1, ratio=None, cross_check=False,
-                             max_distance=None, strict=False, window=None, want_knn=False, out=None):
+                             max_distance=None, strict=False, window=None, want_knn=False, out=None,
+                             replicas=None):
         """Fully asynchronous device form: returns padded CUDA tensors, no host sync.
 
         out = dict(m=int32[3, n_out], count=int32[P], knn_idx=..., knn_dist=...) may be passed to
         reuse buffers.  Matches of problem p sit at m[:, out_begin[p] : out_begin[p] + count[p]].
+
+        replicas = up to 7 more dicts of the same layout whose tensors (or raw device pointers, as
+        ints) live on NVLink peers: the kernel's epilogue writes every result there as well (the
+        multi-GPU gather fused into the match, see :class:`boslam_b200.distributed.FusedGather`).
         """
         import torch
         q = self._torch_prep(q, "q_packed")
@@ -454,11 +459,37 @@ class Engine:
                 out["knn_idx"] = torch.empty((max(n_out, 1), k), dtype=torch.int32, device=dev)
                 out["knn_dist"] = torch.empty((max(n_out, 1), k), dtype=torch.int32, device=dev)
         if P and n_out:
+            if replicas or "m" not in out:
+                replicas = replicas or []
+                dests = (_ffi.Outputs * (1 + len(replicas)))()
+                for d, o in zip(dests, [out] + list(replicas)):
+                    self._fill_outputs(d, o, want_knn)
+                pp = probs.ctypes.data_as(ctypes.POINTER(_ffi.Problem))
+                with self._lock:
+                    rc = self._lib.bfm_match_batched_multi(self._h, q.data_ptr(), q.shape[0], t.data_ptr(), t.shape[0],
+                                                           pp, P, n_out, ctypes.byref(opts), dests, len(dests),
+                                                           self._stream())
+                    _ffi.check(self._h, rc)
+                return out
             m = out["m"]
             self._call(_ffi.MEM_DEVICE, q.data_ptr(), q.shape[0], t.data_ptr(), t.shape[0], probs, n_out, opts,
                        (out["knn_idx"].data_ptr(), out["knn_dist"].data_ptr()) if want_knn else None,
                        (m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(), out["count"].data_ptr()), self._stream())
         return out
+
+    @staticmethod
+    def _fill_outputs(d, o, want_knn):
+        """One bfm_outputs_t from a dict of tensors (m int32[3, n], count, knn_idx, knn_dist) or of raw
+        device pointers (m_query, m_train, m_dist, count, knn_idx, knn_dist as ints)."""
+        ptr = lambda x: int(x) if isinstance(x, int) else x.data_ptr()
+        if "m" in o:
+            m = o["m"]
+            d.m_query, d.m_train, d.m_dist = m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr()
+        else:
+            d.m_query, d.m_train, d.m_dist = ptr(o["m_query"]), ptr(o["m_train"]), ptr(o["m_dist"])
+        d.m_count = ptr(o["count"])
+        if want_knn:
+            d.knn_idx, d.knn_dist = ptr(o["knn_idx"]), ptr(o["knn_dist"])
 
     def _match_batched_torch(self, q, t, problems, k, ratio, cross_check, max_distance, strict, window, want_knn):
         out = self.match_batched_device(q, t, problems, k, ratio, cross_check, max_distance, strict, window, want_knn)

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define BFM_ABI_VERSION 1
+#define BFM_ABI_VERSION 2
 #define BFM_DESC_BYTES 32
 /* per-problem limits of the packed (distance, index) keys the kernels reduce over;
  * cv2 itself refuses train sets of 2^18 rows or more (matchers.cpp:860, rule R7). */
@@ -127,6 +127,28 @@ int bfm_match_batched(bfm_handle_t h, int mem,
                       int32_t *m_query, int32_t *m_train, int32_t *m_dist, int32_t *m_count,
                       void *stream);
 
+/*
+ * Multi-destination form (device memory only): the same batch, with every result written to
+ * n_dests (1..8) sets of output buffers by the kernel's epilogue.  dests[0] is normally this GPU's
+ * own buffers; dests[1..] are the corresponding buffers of NVLink peers (peer-mapped device
+ * pointers, e.g. from CUDA IPC / torch symmetric memory), already offset to this rank's slice.
+ * This is the multi-GPU gather of SURVEY.md 8(e) fused into the matching kernel: the match lists
+ * of the sharded keyframe-pair batches (the shape slam/loop_closing.py:13-29 would issue) land in
+ * every rank's table without a separate collective; the caller only needs a barrier afterwards.
+ */
+typedef struct bfm_outputs {
+    int32_t *knn_idx, *knn_dist;             /* int32[n_out_rows][k], both or neither */
+    int32_t *m_query, *m_train, *m_dist;     /* int32[n_out_rows] */
+    int32_t *m_count;                        /* int32[n_problems]; NULL skips the match list */
+} bfm_outputs_t;
+
+int bfm_match_batched_multi(bfm_handle_t h,
+                            const uint8_t *q, int32_t n_query_rows,
+                            const uint8_t *t, int32_t n_train_rows,
+                            const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
+                            const bfm_options_t *opts,
+                            const bfm_outputs_t *dests, int32_t n_dests, void *stream);
+
 /* Single-problem conveniences (what slam/tracking.py:56,121 bind to). */
 int bfm_knn(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8_t *t, int32_t nt,
             const bfm_options_t *opts, int32_t *knn_idx, int32_t *knn_dist, void *stream);
@@ -136,21 +158,22 @@ int bfm_match(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8
 
 /* ---- introspection / tuning (used by bench.py and the tests; not needed by a call site) --- */
 typedef struct bfm_launch_info {
-    int32_t kernels_launched;   /* CUDA kernels launched by the last call on this handle */
-    int32_t scan_grid;          /* CTAs of the distance-scan kernel */
+    int32_t kernels_launched;   /* CUDA kernels launched by the last call on this handle (1: scan and
+                                   finalize are one kernel) */
+    int32_t scan_grid;          /* CTAs of the matching kernel */
     int32_t scan_block;         /* threads per CTA */
     int32_t queries_per_thread; /* register tile R */
     int32_t popc_mode;          /* popcount evaluation: 8 plain, 6/5/4 carry-save, 50/40 transformed carry-save */
     int32_t segments;           /* (query block, train range) work items */
     int32_t train_rows_per_segment;
-    int32_t reserved;
-    float scan_ms;              /* device time of the scan kernel of the last call when timing is on */
-    float total_ms;             /* device time of all kernels of the last call when timing is on */
+    int32_t copy_chunks;        /* BFM_MEM_HOST: input chunks the copy engine fed the kernel with (1 = no overlap) */
+    float scan_ms;              /* device time of the kernel of the last call when timing is on */
+    float total_ms;             /* same (kept for ABI stability) */
 } bfm_launch_info_t;
 
 int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
 /* knob: "popc_mode" {0=auto,8,6,5,4,50,40}, "queries_per_thread" {0=auto,1,2,4}, "timing" {0,1},
- *       "segment_rows" {0=auto, n}, "waves" {0=auto, n} */
+ *       "segment_rows" {0=auto, n}, "waves" {0=auto, n}, "pipeline_chunks" {0=auto, 1=off, n <= 64} */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t bfm_kernel_launch_count(bfm_handle_t h);

@@ -319,3 +319,50 @@ def test_self_cleaning_workspace_and_plan_cache(eng):
     want = c_oracle.cross_check(q, t)
     for _ in range(5):                                               # identical call: plan-cache hits
         _eq(eng.match(q, t, cross_check=True), want)
+
+
+def test_empty_problems_inside_a_batch(eng):
+    """Problems with no query or no train rows still get their count / knn rows written (one kernel:
+    the CTA that completes a problem finalizes it, so every problem owns at least one work item)."""
+    q, t, _ = synth.correlated(300, 400, 61)
+    tab = np.array([[0, 100, 0, 0, 0, 0],        # no train rows
+                    [100, 0, 0, 50, 100, 0],     # no query rows
+                    [100, 200, 50, 350, 100, 0],
+                    [0, 100, 0, 0, 300, 0]], np.int32)
+    idx, dist, res = eng.match_batched(q, t, tab, k=2, want_knn=True)
+    assert res.counts.tolist()[:2] == [0, 0] and res.counts[3] == 0
+    assert (idx[:100] == -1).all() and (dist[:100] == -1).all() and (idx[300:400] == -1).all()
+    oi, od = c_oracle.knn(q[100:300], t[50:400], 2)
+    assert np.array_equal(idx[100:300], oi) and np.array_equal(dist[100:300], od)
+    _eq(res[2], orc.match(q[100:300], t[50:400], k=2))
+
+
+def test_multi_destination_epilogue(eng):
+    """bfm_match_batched_multi: the epilogue writes identical results to every destination (the
+    fused multi-GPU gather; here all destinations are buffers on the same GPU)."""
+    torch = pytest.importorskip("torch")
+    qs, ts = synth.keyframe_pairs(5, 700, seed=9)
+    qp, tp = np.concatenate(qs), np.concatenate(ts)
+    tab = bb.make_problems([700] * 5, [700] * 5)
+    qd, td = torch.from_numpy(qp).cuda(), torch.from_numpy(tp).cuda()
+    n = 5 * 700
+
+    def bufs():
+        return {"m": torch.full((3, n), -7, dtype=torch.int32, device="cuda"),
+                "count": torch.full((5,), -7, dtype=torch.int32, device="cuda"),
+                "knn_idx": torch.full((n, 2), -7, dtype=torch.int32, device="cuda"),
+                "knn_dist": torch.full((n, 2), -7, dtype=torch.int32, device="cuda")}
+
+    out, reps = bufs(), [bufs(), bufs(), bufs()]
+    eng.match_batched_device(qd, td, tab, k=2, ratio=0.8, want_knn=True, out=out, replicas=reps)
+    torch.cuda.synchronize()
+    for p in range(5):
+        oi, od = c_oracle.knn(qs[p], ts[p], 2)
+        want = orc.match(qs[p], ts[p], k=2, ratio=0.8)
+        for o in [out] + reps:
+            assert np.array_equal(o["knn_idx"][p * 700:(p + 1) * 700].cpu().numpy(), oi)
+            assert np.array_equal(o["knn_dist"][p * 700:(p + 1) * 700].cpu().numpy(), od)
+            c = int(o["count"][p])
+            assert c == len(want[0])
+            m = o["m"][:, p * 700:p * 700 + c].cpu().numpy()
+            assert np.array_equal(m[0], want[0]) and np.array_equal(m[1], want[1])
