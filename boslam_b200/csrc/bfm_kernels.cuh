@@ -235,7 +235,7 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
 // matches in ascending queryIdx order.  Every workspace slot it reads is reset to all-ones, so the
 // workspace is self-cleaning and a steady-state call needs no memset.  Results go to every
 // destination in p.dest (plain stores: device memory, pinned host memory or NVLink peer memory).
-constexpr int FIN_RPT = 4;  // rows per thread and tile
+constexpr int FIN_RPT = 8;  // rows per thread and tile
 
 template <int NT>
 __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi, int (*s_cnt)[NT / 32]) {
@@ -249,18 +249,32 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
         int idx1[FIN_RPT], d1[FIN_RPT];
         bool keep[FIN_RPT];
         uint32_t bal[FIN_RPT];
+        // phase 1: all row-state loads of the tile in flight together, then the resets
+        unsigned long long st[FIN_RPT];
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            const int i = base + j * NT + tid;
+            st[j] = i < pr.q_count ? __ldcg(p.rowstate + (size_t)pr.out_begin + i) : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            const int i = base + j * NT + tid;
+            if (i < pr.q_count) p.rowstate[(size_t)pr.out_begin + i] = ~0ull;
+        }
+        // phase 2: all column-key loads (cross-check) in flight together
+        uint32_t ck[FIN_RPT];
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            const uint32_t k1 = (uint32_t)(st[j] >> 32);
+            ck[j] = KEY_NONE;
+            if (p.cross_check && k1 < KEY_DEAD) ck[j] = __ldcg(p.colkeys + (size_t)pr.col0 + (k1 & IDX_MASK));
+        }
+        // phase 3: decode, knn table, keep decisions
 #pragma unroll
         for (int j = 0; j < FIN_RPT; ++j) {
             const int i = base + j * NT + tid;
             const bool in = i < pr.q_count;
-            uint32_t k1 = KEY_NONE, k2 = KEY_NONE;
-            if (in) {
-                unsigned long long *slot = p.rowstate + (size_t)pr.out_begin + i;
-                const unsigned long long st = __ldcg(slot);
-                *slot = ~0ull;
-                k1 = (uint32_t)(st >> 32);
-                k2 = (uint32_t)st;
-            }
+            const uint32_t k1 = (uint32_t)(st[j] >> 32), k2 = (uint32_t)st[j];
             const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
             idx1[j] = has1 ? (int)(k1 & IDX_MASK) : -1;
             d1[j] = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
@@ -280,8 +294,7 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
                 }
             }
             bool kp = in && has1;
-            if (kp && p.cross_check)
-                kp = __ldcg(p.colkeys + (size_t)pr.col0 + idx1[j]) == (((uint32_t)d1[j] << DIST_SHIFT) | (uint32_t)i);
+            if (kp && p.cross_check) kp = ck[j] == (((uint32_t)d1[j] << DIST_SHIFT) | (uint32_t)i);
             if (kp && p.use_ratio) kp = has2 && ((double)d1[j] < p.ratio * (double)d2);
             if (kp && p.max_distance >= 0) kp = d1[j] <= p.max_distance;
             keep[j] = kp;
@@ -393,6 +406,22 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         __syncthreads();   // s_flag is reused by the kernel tail
     }
 
+    // -- start the train stream first: the TMA of chunks 0 and 1 flies while the queries are loaded ----
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        const int n0 = min(TT, sg.t_count), n1 = min(TT, sg.t_count - TT);
+        if (n0 > 0) {
+            mbar_expect_tx(&s_bar[0], (uint32_t)n0 * 32u);
+            bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)sg.t_row0, (uint32_t)n0 * 32u, &s_bar[0]);
+        }
+        if (n1 > 0) {
+            mbar_expect_tx(&s_bar[1], (uint32_t)n1 * 32u);
+            bulk_g2s(&s_t[1][0], p.t + 2 * (size_t)(sg.t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[1]);
+        }
+    }
+
     // -- this thread's R query descriptors (two coalesced 16-byte loads each) ---------------------
     uint32_t qw[R][8];
     uint32_t ibias[R];          // CROSS: low bits of the column key (query index), dead bit if row absent
@@ -446,17 +475,8 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         }
     };
 
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
+    __syncthreads();   // barrier init (thread 0, above) visible to every waiter
     if (nchunks > 0) {
-        if (tid == 0) {
-            fetch(0);
-            if (nchunks > 1) fetch(1);
-        }
         stage_xy(0);
         if (nchunks > 1) stage_xy(1);
         land(0);
@@ -576,22 +596,19 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         if (!valid[r] || b1[r] >= KEY_DEAD) continue;
-        unsigned long long *addr = p.rowstate + (size_t)(sg.out_row0 + r * NT + tid);
+        // row state = (best << 32) | second, updated through its two 32-bit halves (little endian):
+        // one atomicMin on `best` returns the displaced key; whatever lost there, or this segment's
+        // own runner-up, competes for `second` with a fire-and-forget atomic.  Every key except the
+        // final best is offered to `second` exactly when it stops being (or fails to become) the
+        // best, so `second` ends as the true runner-up for any arrival order.
+        uint32_t *half = reinterpret_cast<uint32_t *>(p.rowstate + (size_t)(sg.out_row0 + r * NT + tid));
         if (K == 1) {
-            atomicMin(addr, ((unsigned long long)b1[r] << 32) | 0xFFFFFFFFull);
+            atomicMin(half + 1, b1[r]);
         } else {
             const uint32_t n2 = b2[r] >= KEY_DEAD ? KEY_NONE : b2[r];
-            unsigned long long old = *reinterpret_cast<volatile unsigned long long *>(addr);
-            while (true) {
-                const uint32_t o1 = (uint32_t)(old >> 32), o2 = (uint32_t)old;
-                const uint32_t m1 = min(o1, b1[r]);
-                const uint32_t m2 = min(max(o1, b1[r]), min(o2, n2));
-                const unsigned long long want = ((unsigned long long)m1 << 32) | m2;
-                if (want == old) break;
-                const unsigned long long seen = atomicCAS(addr, old, want);
-                if (seen == old) break;
-                old = seen;
-            }
+            const uint32_t displaced = atomicMin(half + 1, b1[r]);
+            const uint32_t cand = min(max(displaced, b1[r]), n2);
+            if (cand != KEY_NONE) atomicMin(half, cand);
         }
     }
 

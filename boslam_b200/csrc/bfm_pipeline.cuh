@@ -106,11 +106,16 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
             CU_TRY(h, cudaMemcpyAsync(din + o_qxy, o->q_xy, qxy_b, cudaMemcpyHostToDevice, st));
             CU_TRY(h, cudaMemcpyAsync(din + o_txy, o->t_xy, txy_b, cudaMemcpyHostToDevice, st));
         }
+        const double t_copies = cpu_ms();
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
                         nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st);
         if (rc) return rc;
+        const double t_launch = cpu_ms();
         CU_TRY(h, cudaStreamSynchronize(st));
         h->info.copy_chunks = 1;
+        if (trace)
+            std::fprintf(stderr, "[bfm trace] 1 chunk: copies queued %.3f ms, kernel queued %.3f ms, synced %.3f ms (direct=%d)\n",
+                         t_copies, t_launch, cpu_ms(), (int)direct);
     } else {
         int bounds[MAX_COPY_CHUNKS + 1];
         {
