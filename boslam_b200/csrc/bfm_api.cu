@@ -67,7 +67,14 @@ ScanFn pick_mode(int mode, int mask, int pm) {
         default: return pick_mask<R, 0>(mask, pm);
     }
 }
-ScanFn pick_scan(int r, int mode, int mask, int pm) {
+ScanFn pick_scan(int r, int mode, int mask, int pm, bool bound = false) {
+    if (bound) {  // k > 2 passes: R = 1, K = 2, transformed carry-save popcount
+        switch (mask) {
+            case 1: return bfm::bfm_scan_kernel<1, 2, false, 1, 40, NT, true>;
+            case 2: return bfm::bfm_scan_kernel<1, 2, false, 2, 40, NT, true>;
+            default: return bfm::bfm_scan_kernel<1, 2, false, 0, 40, NT, true>;
+        }
+    }
     switch (r) {
         case 1: return pick_mode<1>(mode, mask, pm);
         case 2: return pick_mode<2>(mode, mask, pm);
@@ -91,6 +98,7 @@ struct bfm_handle_s {
 
     DevBuf state;    // rowstate (u64 per out row) followed by colkeys (u32 per problem-train row)
     DevBuf tables;   // device copy of [problems | segments]
+    DevBuf lower;    // k > 2: per-row lower bound handed from one pass to the next
     void *h_tables[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring
     size_t h_tables_cap[N_TABLE_SLOTS] = {0, 0, 0, 0};
     cudaEvent_t table_ev[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
@@ -258,7 +266,8 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
 int check_opts(bfm_handle_t h, const bfm_options_t *o, int n_problems) {
     if (!o) return fail(h, BFM_ERR_INVALID, "options is NULL");
     if (o->k < 1) return fail(h, BFM_ERR_INVALID, "k must be >= 1");
-    if (o->k > 2) return fail(h, BFM_ERR_UNSUPPORTED, "k > 2 is not supported by this build");
+    if (o->k > BFM_MAX_K) return fail(h, BFM_ERR_UNSUPPORTED, "k > 16 is not supported by this build");
+    if (o->k > 2 && o->ratio >= 0) return fail(h, BFM_ERR_INVALID, "the ratio test is defined on k == 2");
     if (o->cross_check && o->k != 1) return fail(h, BFM_ERR_INVALID, "cross_check requires k == 1 (cv2 asserts the same)");
     if (o->cross_check && o->ratio >= 0) return fail(h, BFM_ERR_INVALID, "cross_check and ratio are exclusive");
     if (o->mask_kind < 0 || o->mask_kind > 2) return fail(h, BFM_ERR_INVALID, "bad mask_kind");
@@ -324,8 +333,9 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     // -- choose the kernel variant ----------------------------------------------------------------
     const int mode = o->cross_check ? 1 : ((o->k >= 2 || o->ratio >= 0) ? 2 : 0);
     const int mask = o->mask_kind;
-    const int pm = h->popc_mode ? h->popc_mode : 40;  // measured best for every mode: profiles/sweep_r01.json
-    int r = h->qpt;
+    const int passes = (o->k + 1) / 2;  // k > 2: two more neighbours per pass (see ScanParams::lower)
+    const int pm = (h->popc_mode && passes == 1) ? h->popc_mode : 40;  // measured best for every mode: profiles/sweep_r01.json
+    int r = passes > 1 ? 1 : h->qpt;
     int slots = 0, seg_rows = 0;
     if (r != 1 && r != 2 && r != 4) {
         // largest register tile that still leaves >= 2 work items per CTA slot
@@ -376,6 +386,10 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     unsigned long long *rowstate = static_cast<unsigned long long *>(h->state.p);
     uint32_t *colkeys = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes);
     uint32_t *done = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes + col_bytes);
+    if (passes > 1) {
+        rc = ensure(h, h->lower, (size_t)n_out_rows * 4);
+        if (rc) return rc;
+    }
 
     const size_t prob_bytes = (size_t)n_problems * sizeof(Problem);
     const size_t table_bytes = prob_bytes + n_segs * sizeof(Segment);
@@ -453,15 +467,23 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         sp.dest[d].m_dist = dests[d].m_dist;
         sp.dest[d].m_count = dests[d].m_count;
     }
-    const ScanFn fn = pick_scan(r, mode, mask, pm);
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], st));
-    fn<<<(unsigned)n_segs, NT, 0, st>>>(sp);
-    CU_TRY(h, cudaGetLastError());
+    for (int pass = 0; pass < passes; ++pass) {
+        sp.knn_col0 = 2 * pass;
+        sp.knn_cols = std::min(2, o->k - 2 * pass);
+        sp.lower = pass > 0 ? static_cast<const uint32_t *>(h->lower.p) : nullptr;
+        sp.lower_out = pass + 1 < passes ? static_cast<uint32_t *>(h->lower.p) : nullptr;
+        if (pass > 0)  // the match list (gate on the nearest neighbour) was produced by the first pass
+            for (int d = 0; d < n_dests; ++d) sp.dest[d].m_count = nullptr;
+        const ScanFn fn = pick_scan(r, mode, mask, pm, pass > 0);
+        fn<<<(unsigned)n_segs, NT, 0, st>>>(sp);
+        CU_TRY(h, cudaGetLastError());
+    }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
     h->state_clean = true;  // every slot touched is restored by the CTA that finalizes its problem
 
-    h->launches += 1;
-    h->info.kernels_launched = 1;
+    h->launches += passes;
+    h->info.kernels_launched = passes;
     h->info.scan_grid = (int32_t)n_segs;
     h->info.scan_block = NT;
     h->info.queries_per_thread = r;
@@ -553,7 +575,7 @@ int bfm_destroy(bfm_handle_t h) {
     if (!h) return BFM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&h->state, &h->tables, &h->d_in})
+    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower})
         if (b->p) cudaFree(b->p);
     if (h->d_ready) cudaFree(h->d_ready);
     if (h->h_marks) cudaFreeHost(h->h_marks);

@@ -78,8 +78,13 @@ struct ScanParams {
     uint32_t mul_lo16;  // 1 << 7
     uint32_t mul_hi16;  // 1 << 23
     uint32_t mul_one, mul_two, mul_four;  // weights of the carry-save popcount sum, same reason
+    // ---- k > 2: one pass per two neighbours.  Pass n only admits keys strictly greater than the last
+    //      key pass n-1 found for that row (keys are unique per row, so this is exact exclusion).
+    const uint32_t *lower;           // [out rows] or NULL (first pass)
+    uint32_t *lower_out;             // [out rows] or NULL: finalize stores the row's second key of this pass
+    int32_t knn_col0, knn_cols;      // this pass fills columns [knn_col0, knn_col0 + knn_cols) of the knn table
     // ---- finalize (run by the CTA that completes a problem's last segment) ----------------------
-    int32_t k;             // columns of the knn table (1 or 2 on this path)
+    int32_t k;             // columns (row stride) of the knn table
     int32_t cross_check;
     int32_t max_distance;  // < 0 off
     int32_t use_ratio;
@@ -280,18 +285,20 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
             d1[j] = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
             const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
             if (in) {
-                const size_t o = ((size_t)pr.out_begin + i) * (size_t)k;
+                const size_t o = ((size_t)pr.out_begin + i) * (size_t)k + (size_t)p.knn_col0;
                 for (int d = 0; d < p.n_dest; ++d) {
                     int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
                     if (!ki) continue;
-                    if (k > 1) {   // 8-byte aligned: o is even
+                    if (k == 2) {   // 8-byte aligned: o is even
                         *reinterpret_cast<int2 *>(ki + o) = make_int2(idx1[j], idx2);
                         *reinterpret_cast<int2 *>(kd + o) = make_int2(d1[j], d2);
                     } else {
                         ki[o] = idx1[j];
                         kd[o] = d1[j];
+                        if (p.knn_cols > 1) { ki[o + 1] = idx2; kd[o + 1] = d2; }
                     }
                 }
+                if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
             }
             bool kp = in && has1;
             if (kp && p.cross_check) kp = ck[j] == (((uint32_t)d1[j] << DIST_SHIFT) | (uint32_t)i);
@@ -361,8 +368,9 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
 // Pipeline per CTA: chunk c+2 is fetched by TMA while chunk c is scanned; one __syncthreads per
 // chunk.  Shared memory: 2 x 4 KB train rows, 2 x 1 KB pixel coords (window), 2 x 2 KB column
 // keys (cross-check).
-template <int R, int K, bool CROSS, int MASK, int PM, int NT>
+template <int R, int K, bool CROSS, int MASK, int PM, int NT, bool BOUND = false>
 __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const __grid_constant__ ScanParams p) {
+    static_assert(!BOUND || R == 1, "the lower-bound variant (k > 2 passes) uses the plain 32-bit key path");
     constexpr int NW = NT / 32;
     constexpr bool XF = pm_transformed(PM);
     static_assert(NT == TT, "one thread per staged train row");
@@ -452,6 +460,9 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     uint32_t b1[R], b2[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { b1[r] = KEY_NONE; b2[r] = KEY_NONE; }
+    uint32_t lb[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) lb[r] = (BOUND && valid[r]) ? __ldg(p.lower + sg.out_row0 + r * NT + tid) : 0u;
 
     const int nchunks = (sg.t_count + TT - 1) / TT;
     auto chunk_rows = [&](int c) { return min(TT, sg.t_count - c * TT); };
@@ -564,7 +575,8 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
                         const bool ok = (fabsf(qx[r] - txy.x) < p.radius) && (fabsf(qy[r] - txy.y) < p.radius);
                         d = ok ? d : DIST_MASKED;
                     }
-                    const uint32_t key = d * p.mul_d32 + jj;
+                    uint32_t key = d * p.mul_d32 + jj;
+                    if (BOUND) key = key > lb[r] ? key : KEY_NONE;
                     if (K == 2) b2[r] = min(b2[r], max(b1[r], key));
                     b1[r] = min(b1[r], key);
                     if (CROSS) ck = min(ck, d * p.mul_d32 + ibias[r]);

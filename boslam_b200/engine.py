@@ -169,6 +169,8 @@ class Engine:
             raise ValueError("cross_check requires k == 1 (cv2 asserts the same, batch_distance.cpp:303)")
         if cross_check and ratio is not None:
             raise ValueError("cross_check and ratio are exclusive")
+        if ratio is not None and k > 2:
+            raise ValueError("the ratio test is defined on the two nearest neighbours: use k <= 2")
         o = _ffi.Options()
         o.k = int(k)
         o.cross_check = 1 if cross_check else 0
@@ -268,8 +270,8 @@ class Engine:
     def _check_limits(nq, nt, k):
         if nt >= _ffi.MAX_TRAIN_ROWS or nq >= _ffi.MAX_QUERY_ROWS:
             raise ValueError("at most 2^22 - 1 rows per problem (cv2 itself stops at 2^18 - 1 train rows)")
-        if k > 2:
-            raise NotImplementedError("k > 2 is not supported by this build")
+        if k > _ffi.MAX_K:
+            raise NotImplementedError(f"k > {_ffi.MAX_K} is not supported by this build")
 
     # -- batched (keyframe pairs) -----------------------------------------------------------------------
     def match_batched(self, q_packed, t_packed, problems: np.ndarray, k: int = 1, ratio=None,
@@ -293,8 +295,8 @@ class Engine:
         n_out = int((probs[:, 4] + probs[:, 1]).max()) if P else 0
         if P and (int(probs[:, 3].max()) >= _ffi.MAX_TRAIN_ROWS or int(probs[:, 1].max()) >= _ffi.MAX_QUERY_ROWS):
             raise ValueError("at most 2^22 - 1 rows per problem")
-        if k > 2:
-            raise NotImplementedError("k > 2 is not supported by this build")
+        if k > _ffi.MAX_K:
+            raise NotImplementedError(f"k > {_ffi.MAX_K} is not supported by this build")
         opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
         keep = []
         if window is not None:
@@ -442,8 +444,8 @@ class Engine:
         probs = np.ascontiguousarray(problems, np.int32)
         P = probs.shape[0]
         n_out = int((probs[:, 4] + probs[:, 1]).max()) if P else 0
-        if k > 2:
-            raise NotImplementedError("k > 2 is not supported by this build")
+        if k > _ffi.MAX_K:
+            raise NotImplementedError(f"k > {_ffi.MAX_K} is not supported by this build")
         opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
         if none_pass:
             opts.max_distance = 0

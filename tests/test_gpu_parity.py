@@ -366,3 +366,39 @@ def test_multi_destination_epilogue(eng):
             assert c == len(want[0])
             m = o["m"][:, p * 700:p * 700 + c].cpu().numpy()
             assert np.array_equal(m[0], want[0]) and np.array_equal(m[1], want[1])
+
+
+@pytest.mark.parametrize("k", [3, 4, 5, 8, 16])
+def test_knn_k_above_two(eng, golden, k):
+    """cv2 knnMatch with k > 2 (rules R2, R3): rows ascend by (distance, trainIdx); short rows when
+    fewer than k candidates exist.  One kernel pass per two neighbours."""
+    q, t, _ = synth.correlated(600, 900, 70 + k)
+    oi, od = c_oracle.knn(q, t, k)
+    idx, dist = eng.knn(q, t, k)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    qt, tt = synth.tie_stress(300, k), synth.duplicate_rows(40, k)      # ties and duplicate rows
+    oi, od = c_oracle.knn(qt, tt, k)
+    idx, dist = eng.knn(qt, tt, k)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    idx, dist = eng.knn(q[:50], t[:k - 1], k)                            # fewer than k candidates
+    assert (idx[:, k - 1] == -1).all() and (idx[:, :k - 1] >= 0).all()
+    q2, t2, qxy, txy, _ = synth.window_scene(400, 1200, k)               # masked
+    dense = orc.window_mask(qxy, txy, 25.0)
+    oi, od = c_oracle.knn(q2, t2, k, dense)
+    for got in (eng.knn(q2, t2, k, window=(qxy, txy, 25.0)), eng.knn(q2, t2, k, mask=dense)):
+        assert np.array_equal(got[0], oi) and np.array_equal(got[1], od)
+    if k == 3:
+        for name in _names(golden):
+            gq, gt = golden[f"{name}/q"], golden[f"{name}/t"]
+            idx, dist = eng.knn(gq, gt, 3)
+            assert np.array_equal(idx, golden[f"{name}/knn3_idx"]) and np.array_equal(dist, golden[f"{name}/knn3_dist"]), name
+    # batched + the drop-in object
+    qs, ts = synth.keyframe_pairs(3, 300, seed=k)
+    tab = bb.make_problems([300] * 3, [300] * 3)
+    bi, bd, _ = eng.match_batched(np.concatenate(qs), np.concatenate(ts), tab, k=k, want_knn=True)
+    for p in range(3):
+        oi, od = c_oracle.knn(qs[p], ts[p], k)
+        assert np.array_equal(bi[p * 300:(p + 1) * 300], oi) and np.array_equal(bd[p * 300:(p + 1) * 300], od)
+    rows = bb.BFMatcher_create(bb.NORM_HAMMING).knnMatch(q[:20], t, k=k)
+    oi, od = c_oracle.knn(q[:20], t, k)
+    assert [[m.trainIdx for m in r] for r in rows] == oi.tolist()
