@@ -18,13 +18,14 @@ MASK_NONE, MASK_DENSE, MASK_WINDOW = 0, 1, 2
 MAX_TRAIN_ROWS = 1 << 22
 MAX_QUERY_ROWS = 1 << 22
 MAX_K = 16
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/bfm.h declares; tests/test_abi.py checks the library exports all of them
 EXPORTED_SYMBOLS = (
     "bfm_abi_version", "bfm_create", "bfm_destroy", "bfm_last_error", "bfm_match_batched", "bfm_knn",
     "bfm_match", "bfm_match_batched_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
-    "bfm_device_info", "bfm_host_alloc", "bfm_host_free",
+    "bfm_device_info", "bfm_host_alloc", "bfm_host_free", "bfm_map_create", "bfm_map_destroy", "bfm_map_update",
+    "bfm_track_local_map",
 )
 
 
@@ -49,6 +50,12 @@ class Options(ctypes.Structure):
 class Outputs(ctypes.Structure):
     _fields_ = [("knn_idx", ctypes.c_void_p), ("knn_dist", ctypes.c_void_p), ("m_query", ctypes.c_void_p),
                 ("m_train", ctypes.c_void_p), ("m_dist", ctypes.c_void_p), ("m_count", ctypes.c_void_p)]
+
+
+class TrackParams(ctypes.Structure):
+    _fields_ = [("q", ctypes.c_double * 4), ("t", ctypes.c_double * 3), ("see_vector", ctypes.c_double * 3),
+                ("fx", ctypes.c_double), ("fy", ctypes.c_double), ("cx", ctypes.c_double), ("cy", ctypes.c_double),
+                ("cos_max", ctypes.c_double), ("width", ctypes.c_int32), ("height", ctypes.c_int32)]
 
 
 class LaunchInfo(ctypes.Structure):
@@ -85,6 +92,11 @@ def lib():
                                         ctypes.POINTER(Options), vp, vp, vp, vp, vp, vp, vp]
         L.bfm_match_batched_multi.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(Problem), i32, i32,
                                               ctypes.POINTER(Options), ctypes.POINTER(Outputs), i32, vp]
+        L.bfm_map_create.argtypes = [vp, i32, ctypes.POINTER(vp)]
+        L.bfm_map_destroy.argtypes = [vp]
+        L.bfm_map_update.argtypes = [vp, i32, vp, vp, vp, vp]
+        L.bfm_track_local_map.argtypes = [vp, ctypes.POINTER(TrackParams), vp, i32, vp, vp, i32, ctypes.POINTER(Options),
+                                          vp, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.bfm_knn.argtypes = [vp, ctypes.c_int, vp, i32, vp, i32, ctypes.POINTER(Options), vp, vp, vp]
         L.bfm_match.argtypes = [vp, ctypes.c_int, vp, i32, vp, i32, ctypes.POINTER(Options), vp, vp, vp, vp, vp]
         L.bfm_get_launch_info.argtypes = [vp, ctypes.POINTER(LaunchInfo)]

@@ -291,7 +291,7 @@ struct Gate {
 int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t, int32_t nt_rows,
                const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
                const bfm_options_t *o, const bfm_outputs_t *dests, int n_dests, cudaStream_t st,
-               const Gate *gate = nullptr) {
+               const Gate *gate = nullptr, const int32_t *t_limit = nullptr) {
     h->info = bfm_launch_info_t{};
     if (n_problems <= 0 || n_out_rows <= 0) return BFM_OK;
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(t)) & 15)
@@ -437,6 +437,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     sp.rowstate = rowstate;
     sp.colkeys = colkeys;
     sp.done = done;
+    sp.t_limit = t_limit;
     if (gate) {
         sp.ready = gate->ready;
         sp.ready_base = gate->base;
@@ -512,8 +513,11 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 #include "bfm_pipeline.cuh"
+#include "bfm_localmap.cuh"
 
 }  // namespace
+
+#include "bfm_localmap_host.cuh"
 
 extern "C" {
 

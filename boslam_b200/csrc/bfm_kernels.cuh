@@ -67,6 +67,7 @@ struct ScanParams {
     const unsigned long long *ready;
     unsigned long long ready_base;
     uint32_t *status;                // set non-zero if the gate timed out (host reports the error)
+    const int32_t *t_limit;          // optional device scalar: train rows that exist (single problem), else NULL
     const uint8_t *mask;             // dense mask (single problem): [q_local][mask_stride]
     long long mask_stride;
     const float2 *q_xy;              // window: pixel coordinates per query / train row
@@ -414,12 +415,17 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         __syncthreads();   // s_flag is reused by the kernel tail
     }
 
+    // train rows of this segment; with a device-side limit (a train set whose size was decided by an
+    // earlier kernel on the same stream, e.g. the visible local-map points) the range is clamped here
+    int t_count = sg.t_count;
+    if (p.t_limit != nullptr) t_count = max(0, min(t_count, __ldg(p.t_limit) - sg.t_local0));
+
     // -- start the train stream first: the TMA of chunks 0 and 1 flies while the queries are loaded ----
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         mbar_fence_init();
-        const int n0 = min(TT, sg.t_count), n1 = min(TT, sg.t_count - TT);
+        const int n0 = min(TT, t_count), n1 = min(TT, t_count - TT);
         if (n0 > 0) {
             mbar_expect_tx(&s_bar[0], (uint32_t)n0 * 32u);
             bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)sg.t_row0, (uint32_t)n0 * 32u, &s_bar[0]);
@@ -464,8 +470,8 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
 #pragma unroll
     for (int r = 0; r < R; ++r) lb[r] = (BOUND && valid[r]) ? __ldg(p.lower + sg.out_row0 + r * NT + tid) : 0u;
 
-    const int nchunks = (sg.t_count + TT - 1) / TT;
-    auto chunk_rows = [&](int c) { return min(TT, sg.t_count - c * TT); };
+    const int nchunks = (t_count + TT - 1) / TT;
+    auto chunk_rows = [&](int c) { return min(TT, t_count - c * TT); };
     auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer c&1
         const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes

@@ -1,0 +1,161 @@
+// bfm_localmap.cuh - frame-to-local-map tracking on the device.
+// (included by bfm_api.cu inside its anonymous namespace, after run_device)
+//
+// What it replaces: the candidate loop of reference slam/tracking.py:96-111 (for every (keyframe,
+// map point) edge of the local map: g2o pose * point, CameraParameters.cam_map, image-bounds test,
+// viewing-angle test, collect descriptor + 3-D point), the np.stack + matcher.match + distance gate
+// of :119-121, and the index gathers of :126-128 that feed CamOnlyBA.  Here the map points live
+// in device memory (bfm_map_t: descriptor, 3-D point, normal per slot; reference slam/nodes.py:115-118)
+// and one call runs
+//     project + visibility      one thread per edge (fp64, explicit IEEE operations - no FMA
+//                               contraction - so the CPU oracle reproduces every decision bit for bit)
+//     ordered compaction        surviving edges keep the reference's iteration order, so train row j
+//                               is the j-th appended feature exactly as in the reference's list;
+//                               descriptors, pixels and points are gathered into contiguous arrays
+//     match                     the fused matching kernel, train-set size read from device memory
+//     gather                    matched (3-D point, frame pixel) pairs into the contiguous float64
+//                               arrays CamOnlyBA / solvePnPRansac consume
+// with one H2D copy (pinned staging) in front and one D2H copy behind.
+
+struct MapView {
+    const uint8_t *desc;   // [capacity][32]
+    const double *pt3d;    // [capacity][3]
+    const double *normal;  // [capacity][3]
+};
+
+struct ProjectParams {
+    double qw, qx, qy, qz;   // unit quaternion of the frame pose (g2o::SE3Quat(R, t).rotation())
+    double tx, ty, tz;
+    double sx, sy, sz;       // frame.see_vector
+    double fx, fy, cx, cy;
+    double width, height;
+    double cos_max;          // keep iff dot(see_vector, normal) < cos_max   (slam/tracking.py:104, as written)
+};
+
+constexpr int LM_NT = 256;
+
+// pose * X as Eigen evaluates a quaternion-vector product (g2o::SE3Quat::map = _r * xyz + _t):
+//   uv = 2 * (q.vec x v);  r = v + w * uv + q.vec x uv
+// then g2o::CameraParameters::cam_map: (x / z) * f + c.  Every operation is an explicit
+// round-to-nearest fp64 instruction, in the order the oracle (oracle/localmap_oracle.py) uses.
+__device__ __forceinline__ bool lm_project(const ProjectParams &pp, const double X[3], const double N[3], double *px, double *py) {
+    const double ux = __dsub_rn(__dmul_rn(pp.qy, X[2]), __dmul_rn(pp.qz, X[1]));
+    const double uy = __dsub_rn(__dmul_rn(pp.qz, X[0]), __dmul_rn(pp.qx, X[2]));
+    const double uz = __dsub_rn(__dmul_rn(pp.qx, X[1]), __dmul_rn(pp.qy, X[0]));
+    const double vx = __dadd_rn(ux, ux), vy = __dadd_rn(uy, uy), vz = __dadd_rn(uz, uz);
+    const double cx_ = __dsub_rn(__dmul_rn(pp.qy, vz), __dmul_rn(pp.qz, vy));
+    const double cy_ = __dsub_rn(__dmul_rn(pp.qz, vx), __dmul_rn(pp.qx, vz));
+    const double cz_ = __dsub_rn(__dmul_rn(pp.qx, vy), __dmul_rn(pp.qy, vx));
+    const double rx = __dadd_rn(__dadd_rn(X[0], __dmul_rn(pp.qw, vx)), cx_);
+    const double ry = __dadd_rn(__dadd_rn(X[1], __dmul_rn(pp.qw, vy)), cy_);
+    const double rz = __dadd_rn(__dadd_rn(X[2], __dmul_rn(pp.qw, vz)), cz_);
+    const double x = __dadd_rn(rx, pp.tx), y = __dadd_rn(ry, pp.ty), z = __dadd_rn(rz, pp.tz);
+    const double u = __dadd_rn(__dmul_rn(__ddiv_rn(x, z), pp.fx), pp.cx);
+    const double v = __dadd_rn(__dmul_rn(__ddiv_rn(y, z), pp.fy), pp.cy);
+    *px = u;
+    *py = v;
+    const bool in_image = (0.0 <= u) && (u < pp.width) && (0.0 <= v) && (v < pp.height);   // NaN -> false
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(pp.sx, N[0]), __dmul_rn(pp.sy, N[1])), __dmul_rn(pp.sz, N[2]));
+    return in_image && (dot < pp.cos_max);
+}
+
+// pass 1: visibility flag + pixel per edge, survivors per block
+__global__ void __launch_bounds__(LM_NT) lm_project_kernel(const ProjectParams pp, const MapView map, const int32_t *edges,
+                                                           int32_t n_edges, int32_t capacity, double2 *pix, uint8_t *flag,
+                                                           int32_t *block_count) {
+    const int e = blockIdx.x * LM_NT + threadIdx.x;
+    bool vis = false;
+    if (e < n_edges) {
+        const int slot = edges[e];
+        double u = 0.0, v = 0.0;
+        if (slot >= 0 && slot < capacity) {
+            const double *Xp = map.pt3d + 3 * (size_t)slot, *Np = map.normal + 3 * (size_t)slot;
+            const double X[3] = {Xp[0], Xp[1], Xp[2]}, N[3] = {Np[0], Np[1], Np[2]};
+            vis = lm_project(pp, X, N, &u, &v);
+        }
+        pix[e] = make_double2(u, v);
+        flag[e] = vis ? 1 : 0;
+    }
+    const int c = __syncthreads_count(vis);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = c;
+}
+
+// pass 2: ordered compaction + gathers.  Survivor number j (in edge order) becomes train row j.
+__global__ void __launch_bounds__(LM_NT) lm_compact_kernel(const MapView map, const int32_t *edges, int32_t n_edges,
+                                                           const double2 *pix, const uint8_t *flag, const int32_t *block_count,
+                                                           int32_t *vis_edge, double2 *vis_pix, float2 *t_xy, uint4 *t_desc,
+                                                           double *vis_pt3d, int32_t *n_visible) {
+    __shared__ int s_red[LM_NT / 32];
+    __shared__ int s_warp[LM_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // survivors in the blocks before this one
+    int part = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += LM_NT) part += block_count[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[warp] = part;
+    const int e = blockIdx.x * LM_NT + tid;
+    const bool vis = e < n_edges && flag[e] != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int pos = 0, mine = 0;
+#pragma unroll
+    for (int w = 0; w < LM_NT / 32; ++w) {
+        pos += s_red[w];
+        if (w < warp) pos += s_warp[w];
+        mine += s_warp[w];
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        int before = 0;
+        for (int w = 0; w < LM_NT / 32; ++w) before += s_red[w];
+        *n_visible = before + mine;
+    }
+    if (!vis) return;
+    pos += __popc(bal & ((1u << lane) - 1u));
+    const int slot = edges[e];
+    const double2 p = pix[e];
+    vis_edge[pos] = e;
+    vis_pix[pos] = p;
+    t_xy[pos] = make_float2((float)p.x, (float)p.y);
+    const uint4 *d = reinterpret_cast<const uint4 *>(map.desc + 32 * (size_t)slot);
+    t_desc[2 * (size_t)pos] = d[0];
+    t_desc[2 * (size_t)pos + 1] = d[1];
+    const double *Xp = map.pt3d + 3 * (size_t)slot;
+    vis_pt3d[3 * (size_t)pos] = Xp[0];
+    vis_pt3d[3 * (size_t)pos + 1] = Xp[1];
+    vis_pt3d[3 * (size_t)pos + 2] = Xp[2];
+}
+
+// pass 4: matched (3-D point, frame pixel, edge) triples, contiguous (slam/tracking.py:126-128)
+__global__ void __launch_bounds__(LM_NT) lm_gather_kernel(const int32_t *m_query, const int32_t *m_train, const int32_t *m_count,
+                                                          const double *vis_pt3d, const int32_t *vis_edge, const double *q_kp,
+                                                          double *out_pts3d, double *out_kp, int32_t *out_edge) {
+    const int i = blockIdx.x * LM_NT + threadIdx.x;
+    if (i >= *m_count) return;
+    const int qi = m_query[i], ti = m_train[i];
+    out_pts3d[3 * (size_t)i] = vis_pt3d[3 * (size_t)ti];
+    out_pts3d[3 * (size_t)i + 1] = vis_pt3d[3 * (size_t)ti + 1];
+    out_pts3d[3 * (size_t)i + 2] = vis_pt3d[3 * (size_t)ti + 2];
+    out_kp[2 * (size_t)i] = q_kp[2 * (size_t)qi];
+    out_kp[2 * (size_t)i + 1] = q_kp[2 * (size_t)qi + 1];
+    out_edge[i] = vis_edge[ti];
+}
+
+__global__ void lm_kp_to_float_kernel(const double *kp, float2 *xy, int32_t n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) xy[i] = make_float2((float)kp[2 * (size_t)i], (float)kp[2 * (size_t)i + 1]);
+}
+
+// scatter of an update batch into the store (slots may repeat: last writer in batch order wins is NOT
+// guaranteed, callers pass each slot once per call)
+__global__ void lm_scatter_kernel(int32_t n, const int32_t *slots, int32_t capacity, const uint4 *desc, const double *pt3d,
+                                  const double *normal, uint4 *s_desc, double *s_pt3d, double *s_normal) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = slots[i];
+    if (s < 0 || s >= capacity) return;
+    if (desc) { s_desc[2 * (size_t)s] = desc[2 * (size_t)i]; s_desc[2 * (size_t)s + 1] = desc[2 * (size_t)i + 1]; }
+    if (pt3d) for (int c = 0; c < 3; ++c) s_pt3d[3 * (size_t)s + c] = pt3d[3 * (size_t)i + c];
+    if (normal) for (int c = 0; c < 3; ++c) s_normal[3 * (size_t)s + c] = normal[3 * (size_t)i + c];
+}

@@ -105,3 +105,55 @@ def keyframe_pair_batch(n_pairs: int, n_desc: int, seed: int = 0, p_flip: float 
     bit = rng.integers(0, DESC_BYTES * 8, len(r_idx))
     np.bitwise_xor.at(query, (r_idx, bit >> 3), (1 << (bit & 7)).astype(np.uint8))
     return query, train
+
+
+def local_map_scene(n_points: int, n_edges: int, n_frame: int, seed: int = 0, p_flip: float = 0.04):
+    """Synthetic local map + frame for the tracking step (reference ``slam/tracking.py:91-128``).
+
+    Returns a dict: store arrays ``desc uint8[n_points,32]``, ``pt3d float64[n_points,3]``,
+    ``normal float64[n_points,3]`` (unit, ``frame.t - point`` direction jittered, as
+    ``slam/covisibility_graph.py:127`` builds it), ``edges int32[n_edges]`` (map-point slot per (keyframe,
+    map point) edge; points seen by several local keyframes repeat - SURVEY.md finding 4), a pose
+    ``R, t, see_vector`` (``camera.py:24-29``) and a frame ``des uint8[n_frame,32]``, ``kp float64[n_frame,2]``
+    (integer-valued pixels like ``Frame.kp_arr``) whose first ~70 % rows observe random visible points.
+    """
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(-0.3, 0.3, 3)
+    cx_, sx = np.cos(ang[0]), np.sin(ang[0])
+    cy_, sy = np.cos(ang[1]), np.sin(ang[1])
+    cz_, sz = np.cos(ang[2]), np.sin(ang[2])
+    Rx = np.array([[1, 0, 0], [0, cx_, -sx], [0, sx, cx_]])
+    Ry = np.array([[cy_, 0, sy], [0, 1, 0], [-sy, 0, cy_]])
+    Rz = np.array([[cz_, -sz, 0], [sz, cz_, 0], [0, 0, 1]])
+    R = Rz @ Ry @ Rx
+    t = rng.uniform(-0.5, 0.5, 3)
+    # points in camera coordinates: a frustum a little wider than the image so some fall outside,
+    # a few behind the camera; world = R^T (Xc - t)
+    fx, fy, cx, cy = 384.239013671875, 384.239013671875, 322.432373046875, 239.6533203125
+    z = rng.uniform(0.5, 8.0, n_points)
+    z[rng.random(n_points) < 0.03] *= -1.0
+    u = rng.uniform(-120.0, WIDTH + 120.0, n_points)
+    v = rng.uniform(-90.0, HEIGHT + 90.0, n_points)
+    Xc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], axis=1)
+    pt3d = (Xc - t) @ R  # R^T applied to rows
+    see = R @ np.array([0.0, 0.0, 1.0])
+    see = see / np.linalg.norm(see)
+    normal = rng.normal(0.0, 1.0, (n_points, 3))
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    desc = rng.integers(0, 256, (n_points, DESC_BYTES), dtype=np.uint8)
+    edges = np.concatenate([rng.permutation(n_points)[:min(n_points, n_edges)],
+                            rng.integers(0, n_points, max(0, n_edges - n_points))]).astype(np.int32)
+    rng.shuffle(edges)
+    # frame: noisy observations of points that are inside the image
+    inside = np.nonzero((u >= 0) & (u < WIDTH) & (v >= 0) & (v < HEIGHT) & (z > 0))[0]
+    n_true = min(int(0.7 * n_frame), len(inside))
+    src = rng.choice(inside, n_true, replace=False) if n_true else np.zeros(0, np.int64)
+    des = rng.integers(0, 256, (n_frame, DESC_BYTES), dtype=np.uint8)
+    kp = np.stack([rng.integers(0, WIDTH, n_frame), rng.integers(0, HEIGHT, n_frame)], axis=1).astype(np.float64)
+    if n_true:
+        flips = np.packbits(rng.random((n_true, DESC_BYTES * 8)) < p_flip, axis=1)
+        des[:n_true] = desc[src] ^ flips
+        kp[:n_true, 0] = np.clip(np.round(u[src] + rng.normal(0, 2.0, n_true)), 0, WIDTH - 1)
+        kp[:n_true, 1] = np.clip(np.round(v[src] + rng.normal(0, 2.0, n_true)), 0, HEIGHT - 1)
+    return {"desc": desc, "pt3d": pt3d, "normal": normal, "edges": edges, "R": R, "t": t, "see_vector": see,
+            "des": des, "kp": kp, "fx": fx, "fy": fy, "cx": cx, "cy": cy, "width": WIDTH, "height": HEIGHT}

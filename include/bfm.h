@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define BFM_ABI_VERSION 2
+#define BFM_ABI_VERSION 3
 #define BFM_DESC_BYTES 32
 /* per-problem limits of the packed (distance, index) keys the kernels reduce over;
  * cv2 itself refuses train sets of 2^18 rows or more (matchers.cpp:860, rule R7). */
@@ -155,6 +155,49 @@ int bfm_knn(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8_t
 int bfm_match(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8_t *t, int32_t nt,
               const bfm_options_t *opts, int32_t *m_query, int32_t *m_train, int32_t *m_dist,
               int32_t *m_count, void *stream);
+
+/* ---- frame <-> local map tracking, device resident ---------------------
+ *
+ * bfm_map_t is the device copy of what the reference keeps per map point (slam/nodes.py:115-118:
+ * MapPoint.feat uint8[32], MapPoint.pt3d float64[3], MapPoint.n float64[3]), addressed by a slot
+ * number the caller assigns (e.g. the MapPoint id).  bfm_map_update is the upsert the reference
+ * performs at slam/covisibility_graph.py:128-134 (new point) and slam/nodes.py:153-154 (descriptor /
+ * normal refresh); pass NULL for a field to leave it unchanged.
+ *
+ * bfm_track_local_map replaces reference slam/tracking.py:96-128 in one call:
+ *   edges[e]          map-point slot of the e-th (local keyframe, map point) edge, in the order the
+ *                     reference's double loop visits them (duplicates are expected: SURVEY.md 0.4)
+ *   visibility        pixel = cam_map(SE3Quat(R, t) * pt3d); keep iff 0 <= u < width, 0 <= v < height
+ *                     and dot(see_vector, normal) < cos_max   (:102-104, exactly as written)
+ *   train set         the kept edges, in edge order: trainIdx j = j-th kept edge (:107-110 + np.stack)
+ *   match             opts as in bfm_match (cross_check / k, ratio / max_distance); mask_kind may be
+ *                     BFM_MASK_WINDOW: allowed iff |kp - pixel| < window_radius in both axes
+ *   outputs (host)    visible_edges[n_visible] edge numbers of the train rows (-> ids_matching_kfs /
+ *                     ids_matching_mps by the caller's own tables), visible_pixels[n_visible][2];
+ *                     m_query / m_train / m_dist [n_matches] as bfm_match; m_edge[n_matches] =
+ *                     visible_edges[m_train]; m_pts3d[n_matches][3] = pts3d[inds], m_kp[n_matches][2] =
+ *                     kp_arr[inds_frame] (:128, the arrays CamOnlyBA consumes).  Any may be NULL.
+ * The quaternion is (w, x, y, z) of g2o::SE3Quat(R, t).rotation(); arithmetic is fp64.
+ */
+typedef struct bfm_map_s *bfm_map_t;
+typedef struct bfm_track_params {
+    double q[4];            /* unit quaternion w, x, y, z */
+    double t[3];
+    double see_vector[3];   /* Frame.see_vector, camera.py:24-29 */
+    double fx, fy, cx, cy;  /* config.py:36-41 */
+    double cos_max;         /* cos(60 deg) in the reference, slam/tracking.py:20,104 */
+    int32_t width, height;  /* config.py:40-41 */
+} bfm_track_params_t;
+
+int bfm_map_create(bfm_handle_t h, int32_t capacity, bfm_map_t *out);
+int bfm_map_destroy(bfm_map_t m);
+int bfm_map_update(bfm_map_t m, int32_t n, const int32_t *slots, const uint8_t *desc, const double *pt3d,
+                   const double *normal);
+int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t *edges, int32_t n_edges,
+                        const uint8_t *q_desc, const double *q_kp, int32_t nq, const bfm_options_t *opts,
+                        int32_t *visible_edges, double *visible_pixels, int32_t *m_query, int32_t *m_train,
+                        int32_t *m_dist, int32_t *m_edge, double *m_pts3d, double *m_kp, int32_t *n_visible,
+                        int32_t *n_matches);
 
 /* ---- introspection / tuning (used by bench.py and the tests; not needed by a call site) --- */
 typedef struct bfm_launch_info {
