@@ -172,6 +172,7 @@ def time_device_loop(torch, fn, steps, barrier):
 
 def extras(eng, torch, steps):
     """Tracking / frame-to-frame / local-mapping shapes: device-resident and end-to-end frames/s."""
+    import boslam_b200 as bb
     import boslam_b200.synth as synth
     from boslam_b200.engine import make_problems
     out = {}
@@ -226,6 +227,43 @@ def extras(eng, torch, steps):
         lambda: eng.match_batched(qb, tb, tab3, k=2, ratio=RATIO),
         lambda: eng.match_batched_device(qbd, tbd, tab3, k=2, ratio=RATIO),
         1, 20 * 2000 * 2000, reps)
+    # the whole slam/tracking.py:96-128 step against a device-resident local map
+    # (20k (keyframe, map point) edges, 2000 frame descriptors): projection + visibility + compaction +
+    # cross-check match + gate + gather, one call.  CPU figure: the numpy restatement + cv2 match.
+    sc = synth.local_map_scene(20000, 20000, 2000, seed=14)
+    store = bb.MapStore(20000, engine=eng)
+    store.update(np.arange(20000), sc["desc"], sc["pt3d"], sc["normal"])
+    targs = (sc["des"], sc["kp"], sc["R"], sc["t"], sc["see_vector"], sc["edges"])
+    for _ in range(3):
+        r = store.track(*targs)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r = store.track(*targs)
+    dt = (time.perf_counter() - t0) / reps
+    out["local_map_track_20000edges_2000desc_fused"] = {
+        "frames_per_s_e2e": 1.0 / dt, "ms_e2e": dt * 1e3, "visible": int(len(r.visible_edges)), "matches": int(len(r.inds)),
+        "pairs_per_s_e2e": 2000 * len(r.visible_edges) / dt, "kernels_per_call": eng.launch_info()["kernels_launched"]}
+    try:
+        from oracle import localmap_oracle as lmo, cv2_reference as ref
+        import math
+        if ref.HAVE_CV2:
+            def cpu():
+                ok, pix = lmo.visible(sc["R"], sc["t"], sc["see_vector"], sc["pt3d"][sc["edges"]], sc["normal"][sc["edges"]],
+                                      sc["fx"], sc["fy"], sc["cx"], sc["cy"], 640, 480, math.cos(math.pi / 3))
+                vis = np.nonzero(ok)[0]
+                feats = sc["desc"][sc["edges"][vis]]
+                ms = [m for m in ref.matcher(True).match(sc["des"], feats) if m.distance <= 30]
+                return len(ms)
+            n_cpu = cpu()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                cpu()
+            dtc = (time.perf_counter() - t0) / 3
+            out["local_map_track_20000edges_2000desc_fused"].update(
+                {"cpu_ms": dtc * 1e3, "cpu_kind": "numpy restatement of the projection loop (vectorised; the reference loops in "
+                                                  "Python over g2o calls) + cv2 crossCheck match + gate", "cpu_matches": int(n_cpu)})
+    except Exception as e:  # the CPU figure is optional context
+        out["local_map_track_20000edges_2000desc_fused"]["cpu_error"] = repr(e)
     return out
 
 

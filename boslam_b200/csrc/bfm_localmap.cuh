@@ -159,3 +159,51 @@ __global__ void lm_scatter_kernel(int32_t n, const int32_t *slots, int32_t capac
     if (pt3d) for (int c = 0; c < 3; ++c) s_pt3d[3 * (size_t)s + c] = pt3d[3 * (size_t)i + c];
     if (normal) for (int c = 0; c < 3; ++c) s_normal[3 * (size_t)s + c] = normal[3 * (size_t)i + c];
 }
+
+// ---- representative descriptor of a map point ---------------------------------
+// reference slam/nodes.py:146-153 (MapPoint.add_observation): with the point's n <= 10 stored
+// observations, D[i][j] = Hamming(obs_i, obs_j) (diagonal 0), feat = obs[argmin_j median_i D[i][j]],
+// np.argmin -> lowest j on ties, np.median -> mean of the two middle values for even n.
+// One 16-lane group per map point: lane j holds observation j, the descriptors go round by shuffle,
+// every lane ranks its own column and the group takes the arg-min of 2 * median (an exact integer).
+constexpr int REP_MAX_OBS = 16;
+
+__global__ void __launch_bounds__(256) rep_select_kernel(const uint4 *obs, const int32_t *counts, int32_t n_points, int32_t max_obs,
+                                                         int32_t *out_idx) {
+    const int gid = (blockIdx.x * 256 + threadIdx.x) >> 4;       // map point
+    const int j = threadIdx.x & 15;                              // observation / column
+    const uint32_t gmask = 0xFFFFu << (threadIdx.x & 16);        // the 16 lanes of this group
+    const bool live = gid < n_points;
+    const int n = live ? min(max(counts[gid], 0), max_obs) : 0;
+    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (j < n) {
+        const uint4 a = obs[((size_t)gid * max_obs + j) * 2], b = obs[((size_t)gid * max_obs + j) * 2 + 1];
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    }
+    int d[REP_MAX_OBS];
+#pragma unroll
+    for (int i = 0; i < REP_MAX_OBS; ++i) {
+        int dist = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dist += __popc(w[c] ^ __shfl_sync(gmask, w[c], (threadIdx.x & 16) + i, 32));
+        d[i] = dist;   // rows i >= n are ignored below
+    }
+    // 2 * median of d[0..n): the elements of rank (n-1)/2 and n/2 in the stable order
+    const int r_lo = (n - 1) >> 1, r_hi = n >> 1;
+    int med2 = 0;
+#pragma unroll
+    for (int a = 0; a < REP_MAX_OBS; ++a) {
+        if (a < n) {
+            int rank = 0;
+#pragma unroll
+            for (int b = 0; b < REP_MAX_OBS; ++b)
+                if (b < n && (d[b] < d[a] || (d[b] == d[a] && b < a))) ++rank;
+            if (rank == r_lo) med2 += d[a];
+            if (rank == r_hi) med2 += d[a];
+        }
+    }
+    uint32_t key = (j < n) ? (((uint32_t)med2 << 8) | (uint32_t)j) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(gmask, key, o, 32));
+    if (live && j == 0) out_idx[gid] = n > 0 ? (int32_t)(key & 0xFFu) : -1;
+}

@@ -256,4 +256,42 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     return BFM_OK;
 }
 
+int bfm_select_representative(bfm_handle_t h, const uint8_t *obs, const int32_t *counts, int32_t n_points,
+                              int32_t max_obs, int32_t *out_idx) {
+    if (!h) return BFM_ERR_INVALID;
+    h->err.clear();
+    if (n_points < 0 || max_obs < 1 || max_obs > REP_MAX_OBS) return fail(h, BFM_ERR_INVALID, "max_obs must be 1..16");
+    if (n_points == 0) return BFM_OK;
+    if (!obs || !counts || !out_idx) return fail(h, BFM_ERR_INVALID, "NULL argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t ob = (size_t)n_points * max_obs * 32, cb = (size_t)n_points * 4;
+    const size_t o_c = align256(ob), o_out = align256(o_c + cb), total = align256(o_out + cb);
+    int rc = ensure(h, h->d_in, total);
+    if (rc) return rc;
+    if (h->h_out_cap < total) {
+        if (h->h_out) CU_TRY(h, cudaFreeHost(h->h_out));
+        h->h_out = nullptr;
+        h->h_out_cap = 0;
+        CU_TRY(h, cudaMallocHost(&h->h_out, total + total / 4 + 4096));
+        h->h_out_cap = total + total / 4 + 4096;
+    }
+    char *din = static_cast<char *>(h->d_in.p), *hs = static_cast<char *>(h->h_out);
+    std::memcpy(hs, obs, ob);
+    std::memcpy(hs + o_c, counts, cb);
+    CU_TRY(h, cudaMemcpyAsync(din, hs, o_c + cb, cudaMemcpyHostToDevice, st));
+    const int groups_per_block = 256 / 16;
+    rep_select_kernel<<<(n_points + groups_per_block - 1) / groups_per_block, 256, 0, st>>>(
+        reinterpret_cast<const uint4 *>(din), reinterpret_cast<const int32_t *>(din + o_c), n_points, max_obs,
+        reinterpret_cast<int32_t *>(din + o_out));
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(hs + o_out, din + o_out, cb, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    std::memcpy(out_idx, hs + o_out, cb);
+    h->launches += 1;
+    h->info = bfm_launch_info_t{};
+    h->info.kernels_launched = 1;
+    return BFM_OK;
+}
+
 }  // extern "C"

@@ -164,3 +164,27 @@ class MapStore:
             _ffi.check(self.engine._h, rc)
         v, m = nv.value, (0 if none_pass else nm.value)
         return TrackResult(vis_e[:v], vis_p[:v], mq[:m], mt[:m], md[:m].astype(np.float32), me[:m], mp3[:m], mkp[:m])
+
+
+def select_representative(obs, counts, engine: Optional[Engine] = None, device: int = 0) -> np.ndarray:
+    """Batched ``MapPoint.add_observation`` descriptor choice (reference ``slam/nodes.py:146-153``):
+    ``obs`` uint8[P, max_obs, 32] (each point's stored observations, first ``counts[p]`` rows valid),
+    returns int32[P]: the index of the observation with the least median Hamming distance to the
+    others (numpy median / argmin conventions), -1 for a point without observations."""
+    from .engine import default_engine
+    eng = engine if engine is not None else default_engine(device)
+    obs = np.ascontiguousarray(obs)
+    if obs.dtype != np.uint8 or obs.ndim != 3 or obs.shape[2] != 32:
+        raise ValueError("obs must be uint8[P, max_obs, 32]")
+    P, max_obs = obs.shape[0], obs.shape[1]
+    if not 1 <= max_obs <= 16:
+        raise ValueError("max_obs must be 1..16 (the reference keeps at most 10 observations)")
+    counts = np.ascontiguousarray(counts, np.int32).ravel()
+    if counts.shape[0] != P:
+        raise ValueError("counts must be int[P]")
+    out = np.full(P, -1, np.int32)
+    if P:
+        with eng._lock:
+            rc = eng._lib.bfm_select_representative(eng._h, obs.ctypes.data, counts.ctypes.data, P, max_obs, out.ctypes.data)
+            _ffi.check(eng._h, rc)
+    return out

@@ -199,6 +199,16 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
                         int32_t *m_dist, int32_t *m_edge, double *m_pts3d, double *m_kp, int32_t *n_visible,
                         int32_t *n_matches);
 
+/* ---- representative descriptor of map points --------------------------------
+ * reference slam/nodes.py:146-153 (MapPoint.add_observation), batched over the map points a new keyframe
+ * touches (slam/covisibility_graph.py:124-134): obs uint8[n_points][max_obs][32] holds each point's stored
+ * observations (first counts[p] rows valid, max_obs <= 16; the reference keeps at most 10);
+ * out_idx[p] = argmin_j median_i Hamming(obs_i, obs_j) with numpy's conventions (median of an even count
+ * = mean of the two middle values, argmin = lowest j on ties), -1 for a point without observations.
+ * Host pointers. */
+int bfm_select_representative(bfm_handle_t h, const uint8_t *obs, const int32_t *counts, int32_t n_points,
+                              int32_t max_obs, int32_t *out_idx);
+
 /* ---- introspection / tuning (used by bench.py and the tests; not needed by a call site) --- */
 typedef struct bfm_launch_info {
     int32_t kernels_launched;   /* CUDA kernels launched by the last call on this handle (1: scan and

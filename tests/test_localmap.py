@@ -121,3 +121,40 @@ def test_map_store_updates_and_poses():
         store.update([5000], desc=np.zeros((1, 32), np.uint8))
     with pytest.raises(ValueError):
         store.update([1, 1], desc=np.zeros((2, 32), np.uint8))
+
+
+# ------------------------------------------------------------------- representative descriptor (8(f) row 4)
+def _obs_batch(P, max_obs, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (P, 1, 32), dtype=np.uint8)
+    flips = np.packbits(rng.random((P, max_obs, 256)) < 0.06, axis=2)
+    obs = base ^ flips                                            # noisy views of one descriptor per point
+    counts = rng.integers(0, max_obs + 1, P).astype(np.int32)
+    obs[::7] = obs[::7, :1]                                       # all-identical observations: every median ties -> index 0
+    if max_obs > 1:
+        obs[3::11, 1] = obs[3::11, 0]                             # duplicate pairs
+    return obs, counts
+
+
+def test_representative_oracle_known_answers():
+    from oracle import representative_oracle as ro
+    z, o = np.zeros(32, np.uint8), np.full(32, 255, np.uint8)
+    assert ro.hamming(z, o) == 256 and ro.hamming(z, z) == 0
+    assert ro.select([z]) == 0 and ro.select([z, o]) == 0            # n = 2: both medians equal -> lowest index
+    far = z.copy(); far[:5] = 255                                    # 40 bits from z
+    near = z.copy(); near[31] = 1                                    # 1 bit from z
+    assert ro.select([far, z, near]) == 1                            # medians 40, 1, 1 -> lowest index of the tie
+    assert ro.select([far, near, z, near]) == 1                      # medians 40.5, 0.5, 1, 0.5
+    assert ro.select([o, z, z, z]) == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_obs", [1, 2, 5, 10, 16])
+def test_select_representative_matches_reference_loop(max_obs):
+    from oracle import representative_oracle as ro
+    obs, counts = _obs_batch(777, max_obs, seed=max_obs)
+    got = bb.select_representative(obs, counts)
+    assert np.array_equal(got, ro.select_batch(obs, counts))
+    assert (got[counts == 0] == -1).all()
+    full = np.full(777, max_obs, np.int32)
+    assert np.array_equal(bb.select_representative(obs, full), ro.select_batch(obs, full))
