@@ -1,0 +1,115 @@
+"""Device-resident keyframe descriptors.
+
+The reference keeps every keyframe's descriptors in ``KeyFrame.des`` (``slam/nodes.py:25``) and would
+hand pairs of them to the matcher for local mapping (new keyframe vs covisible keyframes,
+``slam/local_mapping.py:41-44`` + ``slam/covisibility_graph.py:51-78``) and loop closing (current
+keyframe vs BoW candidates, ``slam/loop_closing.py:13-15``).  ``KeyframeBank`` uploads a keyframe's
+descriptors once, when it is created, and pair batches then name keyframes by id: the problem table
+points both sides of every pair into the bank, so a batch moves no descriptor bytes at all - only the
+match lists come back (written by the kernel straight into pinned host memory).
+
+PyTorch is used for what it is here for: device memory and the stream.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .engine import BatchResult, Engine, HostBatchBuffers, _check_desc_np
+
+
+class KeyframeBank:
+    def __init__(self, capacity_rows: int = 1 << 16, engine: Optional[Engine] = None, device: int = 0):
+        import torch
+        self.engine = engine if engine is not None else Engine(device)
+        self._torch = torch
+        self._dev = torch.device("cuda", self.engine.device)
+        self._rows = torch.empty((max(int(capacity_rows), 1), 32), dtype=torch.uint8, device=self._dev)
+        self._used = 0
+        self._where: Dict[int, Tuple[int, int]] = {}   # keyframe id -> (first row, rows)
+        self._dead = 0                                 # rows of erased keyframes (reclaimed by compaction)
+        self._out: Optional[HostBatchBuffers] = None
+
+    def __contains__(self, kf_id) -> bool:
+        return kf_id in self._where
+
+    def __len__(self) -> int:
+        return len(self._where)
+
+    @property
+    def rows_used(self) -> int:
+        return self._used - self._dead
+
+    def add(self, kf_id: int, des) -> None:
+        """Upload ``KeyFrame.des`` (uint8[N, 32]) once; replaces an earlier entry of the same id."""
+        d = _check_desc_np(des, "des")
+        if kf_id in self._where:
+            self.erase(kf_id)
+        n = d.shape[0]
+        if self._used + n > self._rows.shape[0]:
+            self._compact(self.rows_used + n)
+        if n:
+            self._rows[self._used:self._used + n].copy_(self._torch.from_numpy(d), non_blocking=False)
+        self._where[kf_id] = (self._used, n)
+        self._used += n
+
+    def erase(self, kf_id: int) -> None:
+        """``CovisibilityGraph.erase_kf`` counterpart: the rows are reclaimed at the next compaction."""
+        b, n = self._where.pop(kf_id)
+        self._dead += n
+
+    def _compact(self, need_rows: int) -> None:
+        torch = self._torch
+        cap = self._rows.shape[0]
+        while cap < need_rows:
+            cap *= 2
+        fresh = torch.empty((cap, 32), dtype=torch.uint8, device=self._dev)
+        pos = 0
+        for kf_id, (b, n) in list(self._where.items()):
+            fresh[pos:pos + n].copy_(self._rows[b:b + n])
+            self._where[kf_id] = (pos, n)
+            pos += n
+        self._rows, self._used, self._dead = fresh, pos, 0
+
+    def descriptors(self, kf_id: int) -> np.ndarray:
+        b, n = self._where[kf_id]
+        return self._rows[b:b + n].cpu().numpy()
+
+    def match_pairs(self, pairs: Sequence[Tuple[int, int]], k: int = 1, ratio=None, cross_check: bool = False,
+                    max_distance=None, strict: bool = False, want_knn: bool = False) -> BatchResult:
+        """One batched launch over ``pairs`` = [(query keyframe id, train keyframe id), ...].
+        Returns a :class:`BatchResult` (and the dense knn tables first with ``want_knn``)."""
+        torch = self._torch
+        P = len(pairs)
+        tab = np.zeros((P, 6), np.int32)
+        out_rows = 0
+        for p, (qi, ti) in enumerate(pairs):
+            qb, qn = self._where[qi]
+            tb, tn = self._where[ti]
+            tab[p] = (qb, qn, tb, tn, out_rows, 0)
+            out_rows += qn
+        if P == 0 or out_rows == 0:
+            e = np.zeros(0, np.int32)
+            res = BatchResult(e, e.copy(), e.copy(), np.zeros(P, np.int32), tab[:, 4].copy())
+            return (np.zeros((0, k), np.int32), np.zeros((0, k), np.int32), res) if want_knn else res
+        ob = self._out
+        if ob is None or ob.n_out < out_rows or ob.n_problems < P or ob.k != k or (want_knn and ob.knn_idx is None):
+            ob = self._out = HostBatchBuffers(max(out_rows, 4096), max(P, 64), k=k, want_knn=want_knn)
+        dest = {"m_query": ob.m[0].ctypes.data, "m_train": ob.m[1].ctypes.data, "m_dist": ob.m[2].ctypes.data,
+                "count": ob.count.ctypes.data}
+        if want_knn:
+            dest["knn_idx"], dest["knn_dist"] = ob.knn_idx.ctypes.data, ob.knn_dist.ctypes.data
+        with torch.cuda.device(self._dev):
+            self.engine.match_batched_device(self._rows, self._rows, tab, k=k, ratio=ratio, cross_check=cross_check,
+                                             max_distance=max_distance, strict=strict, want_knn=want_knn, out=dest)
+            torch.cuda.current_stream(self._dev).synchronize()   # results are in pinned host memory now
+        none_pass = self.engine._gate(max_distance, strict) == -2
+        counts = ob.count[:P].copy()
+        if none_pass:
+            counts[:] = 0
+        res = BatchResult(ob.m[0][:out_rows].copy(), ob.m[1][:out_rows].copy(), ob.m[2][:out_rows].copy(), counts,
+                          tab[:, 4].copy())
+        if want_knn:
+            return ob.knn_idx[:out_rows].copy(), ob.knn_dist[:out_rows].copy(), res
+        return res

@@ -56,6 +56,7 @@ class BFMatcher:
         self._device = device
         self._engine = None
         self._train = []  # DescriptorMatcher.add() collection
+        self._train_dev = None  # (device tensor of the concatenated collection, image bounds), built on first use
 
     # engine is created lazily so constructing a matcher (as covisibility_graph.py:34 does and never
     # uses) costs nothing
@@ -68,9 +69,17 @@ class BFMatcher:
     # -- cv2.DescriptorMatcher collection API ---------------------------------------------------------
     def add(self, descriptors):
         self._train.extend(list(descriptors))
+        self._train_dev = None
 
     def clear(self):
         self._train = []
+        self._train_dev = None
+
+    def train(self):
+        """cv2: "trains" the matcher; for a brute-force matcher that means nothing on the CPU.  Here it
+        uploads the collection so the following match calls move only the query (the collection stays
+        resident on the GPU until add() / clear() - SURVEY 8(f) row 2)."""
+        self._resident()
 
     def empty(self):
         return len(self._train) == 0
@@ -81,13 +90,36 @@ class BFMatcher:
     def isMaskSupported(self):
         return True
 
+    def _resident(self):
+        if self._train_dev is None and self._train:
+            import torch
+            sizes = [len(a) for a in self._train]
+            host = np.ascontiguousarray(np.concatenate([np.asarray(a) for a in self._train]))
+            if host.dtype != np.uint8:
+                raise TypeError("descriptors must be uint8, as cv2.NORM_HAMMING requires")
+            dev = torch.from_numpy(host).to(torch.device("cuda", self._device))
+            self._train_dev = (dev, np.cumsum([0] + sizes))
+        return self._train_dev
+
     def _resolve_train(self, trainDescriptors):
         if trainDescriptors is not None:
             return trainDescriptors, None
         if not self._train:
             return np.zeros((0, 32), np.uint8), None
-        sizes = [len(a) for a in self._train]
-        return np.concatenate([np.asarray(a) for a in self._train]), np.cumsum([0] + sizes)
+        return self._resident()
+
+    def _to_engine(self, query, train):
+        """A resident (device) train set needs the query on the device too; results come back as numpy."""
+        if type(train).__module__.split(".")[0] != "torch":
+            return query, train, (lambda x: x)
+        import torch
+        q = np.ascontiguousarray(query)
+        if q.dtype != np.uint8:
+            raise TypeError("descriptors must be uint8, as cv2.NORM_HAMMING requires")
+        if q.ndim != 2 or q.shape[1] != 32:
+            q = q.reshape(-1, 32) if q.size == 0 else q
+        qd = torch.from_numpy(q).to(train.device)
+        return qd, train, (lambda x: x.cpu().numpy())
 
     @staticmethod
     def _img_index(ti, bounds):
@@ -98,7 +130,11 @@ class BFMatcher:
     def match(self, queryDescriptors, trainDescriptors=None, mask=None):
         """tuple[DMatch], ascending queryIdx; queries without a candidate are omitted (rule R3)."""
         train, bounds = self._resolve_train(trainDescriptors)
-        qi, ti, d = self.engine.match(queryDescriptors, train, k=1, cross_check=self.crossCheck, mask=mask)
+        query, train, back = self._to_engine(queryDescriptors, train)
+        if mask is not None and bounds is not None:
+            import torch
+            mask = torch.from_numpy(np.ascontiguousarray(mask)).to(train.device)
+        qi, ti, d = (back(x) for x in self.engine.match(query, train, k=1, cross_check=self.crossCheck, mask=mask))
         if bounds is None:
             return _dmatches(qi, ti, d)
         img, loc = self._img_index(ti, bounds)
@@ -109,10 +145,16 @@ class BFMatcher:
         if k is None:
             raise TypeError("knnMatch() missing required argument 'k'")
         train, bounds = self._resolve_train(trainDescriptors)
+        queryDescriptors_in = queryDescriptors
+        queryDescriptors, train, back = self._to_engine(queryDescriptors, train)
+        if mask is not None and bounds is not None:
+            import torch
+            mask = torch.from_numpy(np.ascontiguousarray(mask)).to(train.device)
         if self.crossCheck:
             if k != 1:
                 raise ValueError("crossCheck=True requires k == 1 (cv2: batch_distance.cpp:303 assertion)")
-            qi, ti, d = self.engine.match(queryDescriptors, train, k=1, cross_check=True, mask=mask)
+            qi, ti, d = (back(x) for x in self.engine.match(queryDescriptors, train, k=1, cross_check=True, mask=mask))
+            queryDescriptors = queryDescriptors_in
             nq = len(queryDescriptors)
             rows = [()] * nq
             for a, b, c in zip(qi.tolist(), ti.tolist(), d.tolist()):
@@ -120,7 +162,7 @@ class BFMatcher:
             if compactResult:
                 rows = [r for r in rows if r]
             return tuple(rows)
-        idx, dist = self.engine.knn(queryDescriptors, train, k=k, mask=mask)
+        idx, dist = (back(x) for x in self.engine.knn(queryDescriptors, train, k=k, mask=mask))
         idx_l, dist_l = idx.tolist(), dist.tolist()
         if bounds is not None:
             img_a, loc_a = self._img_index(np.maximum(idx, 0), bounds)
