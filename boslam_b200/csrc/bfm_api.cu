@@ -19,6 +19,10 @@
 #include <string>
 #include <vector>
 
+namespace bfm {
+#include "bfm_window.cuh"
+}
+
 namespace {
 
 using bfm::Problem;
@@ -99,6 +103,7 @@ struct bfm_handle_s {
     DevBuf state;    // rowstate (u64 per out row) followed by colkeys (u32 per problem-train row)
     DevBuf tables;   // device copy of [problems | segments]
     DevBuf lower;    // k > 2: per-row lower bound handed from one pass to the next
+    DevBuf bins;     // binned window search: train rows in grid-cell order + cell table
     void *h_tables[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring
     size_t h_tables_cap[N_TABLE_SLOTS] = {0, 0, 0, 0};
     cudaEvent_t table_ev[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
@@ -116,7 +121,7 @@ struct bfm_handle_s {
     unsigned long long seq = 0;              // call sequence number (watermark epoch)
 
     // tuning knobs
-    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0;
+    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
 
     bfm_launch_info_t info{};
@@ -165,6 +170,8 @@ int ensure(bfm_handle_t h, DevBuf &b, size_t bytes) {
     ++b.generation;
     return BFM_OK;
 }
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int pm_index(int pm) { return pm == 4 ? 0 : pm == 5 ? 1 : pm == 6 ? 2 : pm == 40 ? 4 : pm == 50 ? 5 : 3; }
 int r_index(int r) { return r == 1 ? 0 : r == 2 ? 1 : 2; }
@@ -337,6 +344,12 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     const int pm = (h->popc_mode && passes == 1) ? h->popc_mode : 40;  // measured best for every mode: profiles/sweep_r01.json
     int r = passes > 1 ? 1 : h->qpt;
     int slots = 0, seg_rows = 0;
+    // projection-window search over a binned train set (bfm_window.cuh): single problem, finite radius
+    const bool binned = mask == BFM_MASK_WINDOW && n_problems == 1 && passes == 1 && h->window_bins != 1 && !gate &&
+                        std::isfinite(o->window_radius) && o->window_radius > 0.0f && problems[0].q_count > 0 &&
+                        problems[0].t_count > 0 && problems[0].t_count <= bfm::WB_MAX_ROWS;
+    const int bin_grid = binned ? (problems[0].q_count + bfm::WS_NT / 32 - 1) / (bfm::WS_NT / 32) : 0;
+    if (binned) r = 1;
     if (r != 1 && r != 2 && r != 4) {
         // largest register tile that still leaves >= 2 work items per CTA slot
         for (int cand : {4, 2, 1}) {
@@ -360,11 +373,17 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
-    const int plan_sig[6] = {n_problems, r, mode, h->segment_rows, h->waves, slots};
+    const int plan_sig[6] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves, slots};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
                           h->plan_problems.size() == (size_t)n_problems &&
                           std::memcmp(h->plan_problems.data(), problems, sizeof(bfm_problem_t) * (size_t)n_problems) == 0;
-    if (!plan_hit) {
+    if (!plan_hit && binned) {
+        h->segs_host.clear();
+        h->seg_begin.assign(2, 0);
+        h->plan_seg_rows = 0;
+        h->plan_probs = h->probs_host;
+        h->plan_probs[0].n_segs = bin_grid;   // the search kernel's CTAs play the role of segments
+    } else if (!plan_hit) {
         plan_segments(h, problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows);
         h->plan_seg_rows = seg_rows;
         h->plan_probs = h->probs_host;
@@ -469,7 +488,31 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         sp.dest[d].m_count = dests[d].m_count;
     }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], st));
-    for (int pass = 0; pass < passes; ++pass) {
+    if (binned) {
+        const bfm_problem_t &pr = problems[0];
+        const size_t T = (size_t)pr.t_count;
+        const size_t o_xy = align256(T * 32), o_orig = align256(o_xy + T * 8), o_cs = align256(o_orig + T * 4),
+                     total = align256(o_cs + (bfm::WB_CELLS + 1) * 4);
+        rc = ensure(h, h->bins, total);
+        if (rc) return rc;
+        char *bb = static_cast<char *>(h->bins.p);
+        bfm::BinView bv{reinterpret_cast<uint4 *>(bb), reinterpret_cast<float2 *>(bb + o_xy),
+                        reinterpret_cast<int32_t *>(bb + o_orig), reinterpret_cast<int32_t *>(bb + o_cs)};
+        const double cell = 2.0 * (double)o->window_radius * (1.0 + 1e-6) + 1e-30;
+        const double inv_cell = 1.0 / cell;
+        bfm::wb_bin_kernel<<<1, bfm::WB_NT, 0, st>>>(sp.t + 2 * (size_t)pr.t_begin, sp.t_xy + pr.t_begin, pr.t_count, t_limit, inv_cell, bv);
+        CU_TRY(h, cudaGetLastError());
+        ScanParams sq = sp;
+        sq.q = sp.q + 2 * (size_t)pr.q_begin;
+        sq.q_xy = sp.q_xy + pr.q_begin;
+        sq.knn_col0 = 0;
+        sq.knn_cols = std::min(2, o->k);
+        if (mode == 1) bfm::wb_search_kernel<1, true><<<bin_grid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell, pr.q_count);
+        else if (mode == 2) bfm::wb_search_kernel<2, false><<<bin_grid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell, pr.q_count);
+        else bfm::wb_search_kernel<1, false><<<bin_grid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell, pr.q_count);
+        CU_TRY(h, cudaGetLastError());
+    }
+    for (int pass = 0; pass < (binned ? 0 : passes); ++pass) {
         sp.knn_col0 = 2 * pass;
         sp.knn_cols = std::min(2, o->k - 2 * pass);
         sp.lower = pass > 0 ? static_cast<const uint32_t *>(h->lower.p) : nullptr;
@@ -483,9 +526,9 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
     h->state_clean = true;  // every slot touched is restored by the CTA that finalizes its problem
 
-    h->launches += passes;
-    h->info.kernels_launched = passes;
-    h->info.scan_grid = (int32_t)n_segs;
+    h->launches += binned ? 2 : passes;
+    h->info.kernels_launched = binned ? 2 : passes;
+    h->info.scan_grid = binned ? bin_grid : (int32_t)n_segs;
     h->info.scan_block = NT;
     h->info.queries_per_thread = r;
     h->info.popc_mode = pm;
@@ -510,7 +553,6 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     return BFM_OK;
 }
 
-size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 #include "bfm_pipeline.cuh"
 #include "bfm_localmap.cuh"
@@ -579,7 +621,7 @@ int bfm_destroy(bfm_handle_t h) {
     if (!h) return BFM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower})
+    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins})
         if (b->p) cudaFree(b->p);
     if (h->d_ready) cudaFree(h->d_ready);
     if (h->h_marks) cudaFreeHost(h->h_marks);
@@ -679,6 +721,9 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "pipeline_chunks") {
         if (value < 0 || value > MAX_COPY_CHUNKS) return fail(h, BFM_ERR_INVALID, "pipeline_chunks must be 0 (auto), 1 (off) .. 64");
         h->pipeline_chunks = value;
+    } else if (k == "window_bins") {
+        if (value != 0 && value != 1) return fail(h, BFM_ERR_INVALID, "window_bins must be 0 (auto) or 1 (brute force)");
+        h->window_bins = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");
         h->waves = value;

@@ -1,0 +1,154 @@
+// bfm_window.cuh - projection-window search over a spatially binned train set.
+// (included by bfm_api.cu inside its anonymous namespace, after bfm_kernels.cuh)
+//
+// The tracking shape of the north star (a frame's descriptors against the local map's projected
+// points, each query only allowed to match points within `radius` pixels of it, in both axes) admits
+// ~0.3 % of the Q x T pairs at 2000 x 20000 / 15 px.  The brute-force kernel evaluates all of them
+// and masks; this path evaluates only the admissible ones:
+//   bin      one CTA counting-sorts the train rows by grid cell (cell edge >= 2 * radius, 64 x 64 cells,
+//            indices wrapped so ANY coordinate range maps somewhere: aliasing only adds candidates)
+//   search   one warp per query walks the <= 3 x 3 cells its window touches, applies the exact fp32
+//            predicate of the brute-force kernel, XOR+POPC on admitted rows only, per-lane top-2 of the
+//            packed keys (distance << 22 | ORIGINAL train index, so ties still break to the lowest
+//            trainIdx), warp merge, cross-check column keys by atomicMin; the last CTA finalizes.
+// Results are bit-identical to the brute-force window path (same predicate, same keys, same min).
+
+constexpr int WB_G = 64;                 // grid is WB_G x WB_G cells (wrapped)
+constexpr int WB_CELLS = WB_G * WB_G;
+constexpr int WB_NT = 1024;              // threads of the binning CTA
+constexpr int WB_MAX_ROWS = 1 << 16;     // train rows the single-CTA binning handles
+
+struct BinView {
+    uint4 *desc;        // [T][2] train descriptors, cell order
+    float2 *xy;         // [T]
+    int32_t *orig;      // [T] original train index
+    int32_t *cell_start;  // [WB_CELLS + 1]
+};
+
+// the same monotone map is used for train points and for window bounds, which is what guarantees
+// that every admissible row lies in a visited cell (see the header comment of bfm_api.cu's caller)
+__device__ __forceinline__ long long wb_cell_coord(float x, double inv_cell) {
+    const double c = floor((double)x * inv_cell);
+    return (long long)fmin(fmax(c, -4.0e15), 4.0e15);
+}
+__device__ __forceinline__ int wb_wrap(long long c) { return (int)(((c % WB_G) + WB_G) % WB_G); }
+
+__global__ void __launch_bounds__(WB_NT) wb_bin_kernel(const uint4 *t_desc, const float2 *t_xy, int32_t n_rows,
+                                                       const int32_t *t_limit, double inv_cell, BinView out) {
+    __shared__ int s_cnt[WB_CELLS];
+    __shared__ int s_warp[WB_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = t_limit ? max(0, min(n_rows, *t_limit)) : n_rows;
+    for (int c = tid; c < WB_CELLS; c += WB_NT) s_cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += WB_NT) {
+        const float2 p = t_xy[i];
+        const int cell = wb_wrap(wb_cell_coord(p.y, inv_cell)) * WB_G + wb_wrap(wb_cell_coord(p.x, inv_cell));
+        atomicAdd(&s_cnt[cell], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the 4096 counters: 4 per thread
+    int v[WB_CELLS / WB_NT], sum = 0;
+#pragma unroll
+    for (int k = 0; k < WB_CELLS / WB_NT; ++k) { v[k] = s_cnt[tid * (WB_CELLS / WB_NT) + k]; sum += v[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    int run = inc - sum + (warp ? s_warp[warp - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < WB_CELLS / WB_NT; ++k) {
+        const int c = tid * (WB_CELLS / WB_NT) + k;
+        out.cell_start[c] = run;
+        s_cnt[c] = run;          // becomes the scatter cursor
+        run += v[k];
+    }
+    if (tid == WB_NT - 1) out.cell_start[WB_CELLS] = run;
+    __syncthreads();
+    for (int i = tid; i < n; i += WB_NT) {
+        const float2 p = t_xy[i];
+        const int cell = wb_wrap(wb_cell_coord(p.y, inv_cell)) * WB_G + wb_wrap(wb_cell_coord(p.x, inv_cell));
+        const int pos = atomicAdd(&s_cnt[cell], 1);
+        out.desc[2 * (size_t)pos] = t_desc[2 * (size_t)i];
+        out.desc[2 * (size_t)pos + 1] = t_desc[2 * (size_t)i + 1];
+        out.xy[pos] = p;
+        out.orig[pos] = i;
+    }
+}
+
+constexpr int WS_NT = 256;   // 8 queries per CTA, one warp each
+
+template <int K, bool CROSS>
+__global__ void __launch_bounds__(WS_NT) wb_search_kernel(const __grid_constant__ ScanParams p, const BinView bins,
+                                                          const double inv_cell, const int32_t n_query) {
+    __shared__ int s_cnt[FIN_RPT][WS_NT / 32];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qi = blockIdx.x * (WS_NT / 32) + warp;
+    if (qi < n_query) {
+        const uint4 a = __ldg(p.q + 2 * (size_t)qi), b = __ldg(p.q + 2 * (size_t)qi + 1);
+        const uint32_t qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const float2 qxy = __ldg(p.q_xy + qi);
+        uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
+        if (!(isnan(qxy.x) || isnan(qxy.y))) {
+            const long long cx0 = wb_cell_coord(qxy.x - p.radius, inv_cell), cx1 = min(wb_cell_coord(qxy.x + p.radius, inv_cell), cx0 + 2);
+            const long long cy0 = wb_cell_coord(qxy.y - p.radius, inv_cell), cy1 = min(wb_cell_coord(qxy.y + p.radius, inv_cell), cy0 + 2);
+            for (long long cy = cy0; cy <= cy1; ++cy) {
+                for (long long cx = cx0; cx <= cx1; ++cx) {
+                    const int cell = wb_wrap(cy) * WB_G + wb_wrap(cx);
+                    const int r0 = bins.cell_start[cell], r1 = bins.cell_start[cell + 1];
+                    for (int r = r0 + lane; r < r1; r += 32) {
+                        const float2 txy = bins.xy[r];
+                        if (!((fabsf(qxy.x - txy.x) < p.radius) && (fabsf(qxy.y - txy.y) < p.radius))) continue;
+                        const uint4 ta = bins.desc[2 * (size_t)r], tb = bins.desc[2 * (size_t)r + 1];
+                        const uint32_t d = __popc(qw[0] ^ ta.x) + __popc(qw[1] ^ ta.y) + __popc(qw[2] ^ ta.z) + __popc(qw[3] ^ ta.w) +
+                                           __popc(qw[4] ^ tb.x) + __popc(qw[5] ^ tb.y) + __popc(qw[6] ^ tb.z) + __popc(qw[7] ^ tb.w);
+                        const uint32_t orig = (uint32_t)bins.orig[r];
+                        const uint32_t key = (d << DIST_SHIFT) | orig;
+                        if (K == 2) b2 = min(b2, max(b1, key));
+                        b1 = min(b1, key);
+                        if (CROSS) atomicMin(p.colkeys + orig, (d << DIST_SHIFT) | (uint32_t)qi);
+                    }
+                }
+            }
+        }
+        // merge the 32 sorted pairs (a wrapped cell may have been visited twice: equal keys collapse)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t o1 = __shfl_xor_sync(0xffffffffu, b1, o), o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+            const uint32_t m1 = min(b1, o1);
+            uint32_t m2 = min(max(b1, o1), min(b2, o2));
+            if (b1 == o1) m2 = min(b2, o2);   // the same row seen by both: not its own runner-up
+            b1 = m1;
+            b2 = m2;
+        }
+        if (lane == 0) p.rowstate[(size_t)p.problems[0].out_begin + qi] = ((unsigned long long)b1 << 32) | (K == 2 ? b2 : KEY_NONE);
+    }
+    // last CTA finalizes (problem 0; its n_segs is this grid's size)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t old = atomicAdd(p.done, 1u);
+        s_flag = (old == (uint32_t)gridDim.x - 2u) ? 1 : 0;
+        if (s_flag) p.done[0] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    if (s_flag) {
+        __threadfence();
+        finalize_problem<WS_NT>(p, 0, s_cnt);
+    }
+}

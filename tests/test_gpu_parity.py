@@ -465,3 +465,42 @@ def test_keyframe_bank_pairs_without_descriptor_traffic(eng):
         _eq(res[p], orc.match(kfs[a], kfs[b], k=2, ratio=0.9), (a, b))
         o += n
     assert len(bank.match_pairs([])) == 0
+
+
+@pytest.mark.parametrize("case", ["image", "wide", "negative", "tiny_radius", "big_radius", "nan"])
+def test_binned_window_search_equals_brute_force(eng, case):
+    """The binned projection-window path (bfm_window.cuh) and the brute-force window kernel return the
+    same bits for any coordinate range (cells wrap, so nothing is assumed about the extent)."""
+    rng = np.random.default_rng(len(case))
+    nq, nt = 700, 5000
+    q, t, qxy, txy, _ = synth.window_scene(nq, nt, 17)
+    radius = 15.0
+    if case == "wide":
+        qxy, txy = qxy * 300.0, txy * 300.0
+        radius = 4000.0
+    elif case == "negative":
+        qxy, txy = qxy - 5000.0, txy - 5000.0
+    elif case == "tiny_radius":
+        radius = 0.75
+        txy[:400] = qxy[rng.integers(0, nq, 400)] + rng.uniform(-1, 1, (400, 2)).astype(np.float32)
+    elif case == "big_radius":
+        radius = 900.0                                                   # every pair admissible
+    elif case == "nan":
+        qxy[::13, 0] = np.nan
+        txy[::7, 1] = np.nan
+    dense = orc.window_mask(qxy, txy, radius)
+    win = (qxy, txy, radius)
+    for kw, okw in (({"k": 2, "ratio": 0.8}, {"k": 2, "ratio": 0.8}), ({"cross_check": True}, {"cross_check_": True}),
+                    ({"k": 1, "max_distance": 50}, {"k": 1, "max_distance": 50})):
+        want = orc.match(q, t, mask=dense, **okw)
+        eng.set_tuning(window_bins=0)
+        got_binned = eng.match(q, t, window=win, **kw)
+        binned_kernels = eng.launch_info()["kernels_launched"]
+        eng.set_tuning(window_bins=1)
+        got_brute = eng.match(q, t, window=win, **kw)
+        eng.set_tuning(window_bins=0)
+        _eq(got_binned, want, (case, kw))
+        _eq(got_brute, want, (case, kw))
+        assert binned_kernels == 2                                       # bin + search
+    oi, od = c_oracle.knn(q, t, 2, dense)
+    _eq(eng.knn(q, t, 2, window=win), (oi, od), case)
