@@ -32,6 +32,7 @@ using bfm::Segment;
 constexpr int NT = 128;          // threads per scan CTA
 constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
 constexpr int N_TABLE_SLOTS = 4;
+constexpr int BIG_FINALIZE_ROWS = 8192;  // a single problem with this many query rows is finalized by tile-parallel kernels
 constexpr int MAX_COPY_CHUNKS = 64;  // input chunks of the pipelined host path
 
 std::string g_create_error;
@@ -103,6 +104,7 @@ struct bfm_handle_s {
     DevBuf state;    // rowstate (u64 per out row) followed by colkeys (u32 per problem-train row)
     DevBuf tables;   // device copy of [problems | segments]
     DevBuf lower;    // k > 2: per-row lower bound handed from one pass to the next
+    DevBuf fin;      // tile-parallel finalize of one very large problem: keep flags + tile counts
     DevBuf bins;     // binned window search: train rows in grid-cell order + cell table
     void *h_tables[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring
     size_t h_tables_cap[N_TABLE_SLOTS] = {0, 0, 0, 0};
@@ -409,6 +411,18 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         rc = ensure(h, h->lower, (size_t)n_out_rows * 4);
         if (rc) return rc;
     }
+    // one very large problem: tile-parallel finalize kernels instead of the single finalizing CTA
+    const bool defer = !binned && n_problems == 1 && problems[0].q_count >= BIG_FINALIZE_ROWS && problems[0].t_count > 0 && n_dests >= 1;
+    const int fin_tiles = defer ? (problems[0].q_count + bfm::FT_ROWS - 1) / bfm::FT_ROWS : 0;
+    uint8_t *d_keep = nullptr;
+    int32_t *d_tile = nullptr;
+    if (defer) {
+        const size_t o_tile = align256((size_t)problems[0].q_count);
+        rc = ensure(h, h->fin, o_tile + (size_t)fin_tiles * 4);
+        if (rc) return rc;
+        d_keep = static_cast<uint8_t *>(h->fin.p);
+        d_tile = reinterpret_cast<int32_t *>(static_cast<char *>(h->fin.p) + o_tile);
+    }
 
     const size_t prob_bytes = (size_t)n_problems * sizeof(Problem);
     const size_t table_bytes = prob_bytes + n_segs * sizeof(Segment);
@@ -491,16 +505,27 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     if (binned) {
         const bfm_problem_t &pr = problems[0];
         const size_t T = (size_t)pr.t_count;
-        const size_t o_xy = align256(T * 32), o_orig = align256(o_xy + T * 8), o_cs = align256(o_orig + T * 4),
-                     total = align256(o_cs + (bfm::WB_CELLS + 1) * 4);
+        // layout: [counters + ticket | cell offsets | rows in cell order: desc, xy, orig | cell, rank per row]
+        const size_t o_cnt = 0, o_cs = align256((bfm::WB_CELLS + 1) * 4), o_desc = align256(o_cs + (bfm::WB_CELLS + 1) * 4),
+                     o_xy = align256(o_desc + T * 32), o_orig = align256(o_xy + T * 8), o_cell = align256(o_orig + T * 4),
+                     o_rank = align256(o_cell + T * 4), total = align256(o_rank + T * 4);
+        const unsigned bins_gen = h->bins.generation;
         rc = ensure(h, h->bins, total);
         if (rc) return rc;
         char *bb = static_cast<char *>(h->bins.p);
-        bfm::BinView bv{reinterpret_cast<uint4 *>(bb), reinterpret_cast<float2 *>(bb + o_xy),
+        // the counters (and the ticket behind them) are self-cleaning: zeroed once per allocation
+        if (h->bins.generation != bins_gen) CU_TRY(h, cudaMemsetAsync(h->bins.p, 0, o_cs, st));
+        bfm::BinView bv{reinterpret_cast<uint4 *>(bb + o_desc), reinterpret_cast<float2 *>(bb + o_xy),
                         reinterpret_cast<int32_t *>(bb + o_orig), reinterpret_cast<int32_t *>(bb + o_cs)};
+        int32_t *d_cnt = reinterpret_cast<int32_t *>(bb + o_cnt);
+        uint32_t *d_ticket = reinterpret_cast<uint32_t *>(d_cnt + bfm::WB_CELLS);
+        int32_t *d_cell = reinterpret_cast<int32_t *>(bb + o_cell), *d_rank = reinterpret_cast<int32_t *>(bb + o_rank);
         const double cell = 2.0 * (double)o->window_radius * (1.0 + 1e-6) + 1e-30;
         const double inv_cell = 1.0 / cell;
-        bfm::wb_bin_kernel<<<1, bfm::WB_NT, 0, st>>>(sp.t + 2 * (size_t)pr.t_begin, sp.t_xy + pr.t_begin, pr.t_count, t_limit, inv_cell, bv);
+        const int bgrid = (pr.t_count + 255) / 256;
+        bfm::wb_count_kernel<<<bgrid, 256, 0, st>>>(sp.t_xy + pr.t_begin, pr.t_count, t_limit, inv_cell, d_cnt, d_ticket, d_cell, d_rank, bv.cell_start);
+        CU_TRY(h, cudaGetLastError());
+        bfm::wb_scatter_kernel<<<bgrid, 256, 0, st>>>(sp.t + 2 * (size_t)pr.t_begin, sp.t_xy + pr.t_begin, pr.t_count, t_limit, d_cell, d_rank, bv);
         CU_TRY(h, cudaGetLastError());
         ScanParams sq = sp;
         sq.q = sp.q + 2 * (size_t)pr.q_begin;
@@ -520,14 +545,21 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         if (pass > 0)  // the match list (gate on the nearest neighbour) was produced by the first pass
             for (int d = 0; d < n_dests; ++d) sp.dest[d].m_count = nullptr;
         const ScanFn fn = pick_scan(r, mode, mask, pm, pass > 0);
+        sp.defer_finalize = defer ? 1 : 0;
         fn<<<(unsigned)n_segs, NT, 0, st>>>(sp);
         CU_TRY(h, cudaGetLastError());
+        if (defer) {
+            bfm::fin_count_kernel<<<fin_tiles, bfm::FT_NT, 0, st>>>(sp, d_keep, d_tile);
+            CU_TRY(h, cudaGetLastError());
+            bfm::fin_write_kernel<<<fin_tiles, bfm::FT_NT, 0, st>>>(sp, d_keep, d_tile);
+            CU_TRY(h, cudaGetLastError());
+        }
     }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
     h->state_clean = true;  // every slot touched is restored by the CTA that finalizes its problem
 
-    h->launches += binned ? 2 : passes;
-    h->info.kernels_launched = binned ? 2 : passes;
+    h->launches += binned ? 3 : passes * (defer ? 3 : 1);
+    h->info.kernels_launched = binned ? 3 : passes * (defer ? 3 : 1);
     h->info.scan_grid = binned ? bin_grid : (int32_t)n_segs;
     h->info.scan_block = NT;
     h->info.queries_per_thread = r;
@@ -621,7 +653,7 @@ int bfm_destroy(bfm_handle_t h) {
     if (!h) return BFM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins})
+    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins, &h->fin})
         if (b->p) cudaFree(b->p);
     if (h->d_ready) cudaFree(h->d_ready);
     if (h->h_marks) cudaFreeHost(h->h_marks);

@@ -84,6 +84,7 @@ struct ScanParams {
     const uint32_t *lower;           // [out rows] or NULL (first pass)
     uint32_t *lower_out;             // [out rows] or NULL: finalize stores the row's second key of this pass
     int32_t knn_col0, knn_cols;      // this pass fills columns [knn_col0, knn_col0 + knn_cols) of the knn table
+    int32_t defer_finalize;          // 1: the scan kernel only reduces; fin_count / fin_write kernels finalize
     // ---- finalize (run by the CTA that completes a problem's last segment) ----------------------
     int32_t k;             // columns (row stride) of the knn table
     int32_t cross_check;
@@ -632,6 +633,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
 
     // -- problem completion: the CTA whose segment is the last of its problem finalizes it -------------
     // (threadfence + counter: every CTA's state updates are visible before its count is)
+    if (p.defer_finalize) return;   // one very large problem: finalized by the tile-parallel kernels below
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -645,6 +647,112 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         __threadfence();
         finalize_problem<NT>(p, sg.problem, s_cnt);
     }
+}
+
+// ---- tile-parallel finalize for ONE very large problem (Q >= 8192 rows: the brute-force sweep) ------------
+// The in-kernel finalize is one CTA per problem, which is right for keyframe-sized problems (a few
+// thousand rows) and serial for 64k rows.  Here tiles of FT_ROWS rows run in parallel: fin_count decodes,
+// writes the knn table, decides keep and counts per tile; fin_write places the kept rows after the kept
+// rows of all earlier tiles (ascending queryIdx is preserved) and restores the workspace.
+constexpr int FT_NT = 256, FT_RPT = 4, FT_ROWS = FT_NT * FT_RPT;
+
+__global__ void __launch_bounds__(FT_NT) fin_count_kernel(const __grid_constant__ ScanParams p, uint8_t *keep_flag, int32_t *tile_count) {
+    const Problem pr = p.problems[0];
+    const int k = p.k;
+    int kept = 0;
+#pragma unroll
+    for (int j = 0; j < FT_RPT; ++j) {
+        const int i = blockIdx.x * FT_ROWS + j * FT_NT + threadIdx.x;
+        if (i >= pr.q_count) continue;
+        const unsigned long long st = __ldcg(p.rowstate + (size_t)pr.out_begin + i);
+        const uint32_t k1 = (uint32_t)(st >> 32), k2 = (uint32_t)st;
+        const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
+        const int idx1 = has1 ? (int)(k1 & IDX_MASK) : -1, d1 = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
+        const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
+        const size_t o = ((size_t)pr.out_begin + i) * (size_t)k + (size_t)p.knn_col0;
+        for (int d = 0; d < p.n_dest; ++d) {
+            int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
+            if (!ki) continue;
+            ki[o] = idx1;
+            kd[o] = d1;
+            if (p.knn_cols > 1) { ki[o + 1] = idx2; kd[o + 1] = d2; }
+        }
+        if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
+        bool kp = has1;
+        if (kp && p.cross_check) kp = __ldcg(p.colkeys + (size_t)pr.col0 + idx1) == (((uint32_t)d1 << DIST_SHIFT) | (uint32_t)i);
+        if (kp && p.use_ratio) kp = has2 && ((double)d1 < p.ratio * (double)d2);
+        if (kp && p.max_distance >= 0) kp = d1 <= p.max_distance;
+        keep_flag[i] = kp ? 1 : 0;
+        kept += kp ? 1 : 0;
+    }
+    const int total = kept;
+    __shared__ int s_sum[FT_NT / 32];
+    int w = total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < FT_NT / 32; ++i) t += s_sum[i];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(FT_NT) fin_write_kernel(const __grid_constant__ ScanParams p, const uint8_t *keep_flag,
+                                                          const int32_t *tile_count) {
+    __shared__ int s_red[FT_NT / 32];
+    __shared__ int s_cnt[FT_RPT][FT_NT / 32];
+    const Problem pr = p.problems[0];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int part = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += FT_NT) part += tile_count[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[warp] = part;
+    bool keep[FT_RPT];
+    uint32_t bal[FT_RPT];
+    unsigned long long st[FT_RPT];
+#pragma unroll
+    for (int j = 0; j < FT_RPT; ++j) {
+        const int i = blockIdx.x * FT_ROWS + j * FT_NT + tid;
+        const bool in = i < pr.q_count;
+        keep[j] = in && keep_flag[i] != 0;
+        st[j] = in ? __ldcg(p.rowstate + (size_t)pr.out_begin + i) : ~0ull;
+        if (in) p.rowstate[(size_t)pr.out_begin + i] = ~0ull;
+        bal[j] = __ballot_sync(0xffffffffu, keep[j]);
+        if (lane == 0) s_cnt[j][warp] = __popc(bal[j]);
+    }
+    __syncthreads();
+    int before = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < FT_NT / 32; ++w) before += s_red[w];
+    const bool want_list = p.dest[0].m_count != nullptr;
+#pragma unroll
+    for (int j = 0; j < FT_RPT; ++j) {
+        int pos = before + tile_total;
+#pragma unroll
+        for (int w = 0; w < FT_NT / 32; ++w) {
+            if (w < warp) pos += s_cnt[j][w];
+            tile_total += s_cnt[j][w];
+        }
+        if (keep[j] && want_list) {
+            const size_t o = (size_t)pr.out_begin + pos + __popc(bal[j] & ((1u << lane) - 1u));
+            const uint32_t k1 = (uint32_t)(st[j] >> 32);
+            const int i = blockIdx.x * FT_ROWS + j * FT_NT + tid;
+            for (int d = 0; d < p.n_dest; ++d) {
+                if (!p.dest[d].m_count) continue;
+                p.dest[d].m_query[o] = i;
+                p.dest[d].m_train[o] = (int)(k1 & IDX_MASK);
+                p.dest[d].m_dist[o] = (int)(k1 >> DIST_SHIFT);
+            }
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0)
+        for (int d = 0; d < p.n_dest; ++d)
+            if (p.dest[d].m_count) p.dest[d].m_count[0] = before + tile_total;
+    if (p.cross_check)   // every column-key read happened in fin_count; all tiles share the reset
+        for (int j = blockIdx.x * FT_NT + tid; j < pr.t_count; j += gridDim.x * FT_NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
 }
 
 }  // namespace bfm

@@ -5,8 +5,10 @@
 // points, each query only allowed to match points within `radius` pixels of it, in both axes) admits
 // ~0.3 % of the Q x T pairs at 2000 x 20000 / 15 px.  The brute-force kernel evaluates all of them
 // and masks; this path evaluates only the admissible ones:
-//   bin      one CTA counting-sorts the train rows by grid cell (cell edge >= 2 * radius, 64 x 64 cells,
-//            indices wrapped so ANY coordinate range maps somewhere: aliasing only adds candidates)
+//   bin      counting sort of the train rows by grid cell (cell edge >= 2 * radius, 64 x 64 cells, indices
+//            wrapped so ANY coordinate range maps somewhere: aliasing only adds candidates): one pass
+//            ranks every row inside its cell with an atomic and its last CTA scans the counters, a
+//            second pass moves the rows
 //   search   one warp per query walks the <= 3 x 3 cells its window touches, applies the exact fp32
 //            predicate of the brute-force kernel, XOR+POPC on admitted rows only, per-lane top-2 of the
 //            packed keys (distance << 22 | ORIGINAL train index, so ties still break to the lowest
@@ -15,8 +17,7 @@
 
 constexpr int WB_G = 64;                 // grid is WB_G x WB_G cells (wrapped)
 constexpr int WB_CELLS = WB_G * WB_G;
-constexpr int WB_NT = 1024;              // threads of the binning CTA
-constexpr int WB_MAX_ROWS = 1 << 16;     // train rows the single-CTA binning handles
+constexpr int WB_MAX_ROWS = 1 << 20;     // above this the brute-force window kernel is used
 
 struct BinView {
     uint4 *desc;        // [T][2] train descriptors, cell order
@@ -33,24 +34,35 @@ __device__ __forceinline__ long long wb_cell_coord(float x, double inv_cell) {
 }
 __device__ __forceinline__ int wb_wrap(long long c) { return (int)(((c % WB_G) + WB_G) % WB_G); }
 
-__global__ void __launch_bounds__(WB_NT) wb_bin_kernel(const uint4 *t_desc, const float2 *t_xy, int32_t n_rows,
-                                                       const int32_t *t_limit, double inv_cell, BinView out) {
-    __shared__ int s_cnt[WB_CELLS];
-    __shared__ int s_warp[WB_NT / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// pass 1 (many CTAs): cell of every train row, rank inside its cell (the atomic's return value);
+// the last CTA to finish turns the counters into cell offsets and zeroes them for the next call.
+__global__ void __launch_bounds__(256) wb_count_kernel(const float2 *t_xy, int32_t n_rows, const int32_t *t_limit, double inv_cell,
+                                                       int32_t *cnt, uint32_t *ticket, int32_t *cell_of, int32_t *rank_of,
+                                                       int32_t *cell_start) {
+    __shared__ int s_warp[32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
     const int n = t_limit ? max(0, min(n_rows, *t_limit)) : n_rows;
-    for (int c = tid; c < WB_CELLS; c += WB_NT) s_cnt[c] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += WB_NT) {
+    const int i = blockIdx.x * 256 + tid;
+    if (i < n) {
         const float2 p = t_xy[i];
         const int cell = wb_wrap(wb_cell_coord(p.y, inv_cell)) * WB_G + wb_wrap(wb_cell_coord(p.x, inv_cell));
-        atomicAdd(&s_cnt[cell], 1);
+        cell_of[i] = cell;
+        rank_of[i] = atomicAdd(cnt + cell, 1);
     }
+    __threadfence();
     __syncthreads();
-    // exclusive scan of the 4096 counters: 4 per thread
-    int v[WB_CELLS / WB_NT], sum = 0;
+    if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) *ticket = 0;
+    // exclusive scan of the WB_CELLS counters by this CTA: 16 per thread
+    constexpr int PER = WB_CELLS / 256;
+    const int lane = tid & 31, warp = tid >> 5;
+    int v[PER], sum = 0;
 #pragma unroll
-    for (int k = 0; k < WB_CELLS / WB_NT; ++k) { v[k] = s_cnt[tid * (WB_CELLS / WB_NT) + k]; sum += v[k]; }
+    for (int k = 0; k < PER; ++k) { v[k] = __ldcg(cnt + tid * PER + k); sum += v[k]; }
     int inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -60,34 +72,36 @@ __global__ void __launch_bounds__(WB_NT) wb_bin_kernel(const uint4 *t_desc, cons
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int w = s_warp[lane];
+        int w = lane < 8 ? s_warp[lane] : 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
+        for (int o = 1; o < 8; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, w, o);
             if (lane >= o) w += y;
         }
-        s_warp[lane] = w;
+        if (lane < 8) s_warp[lane] = w;
     }
     __syncthreads();
     int run = inc - sum + (warp ? s_warp[warp - 1] : 0);
 #pragma unroll
-    for (int k = 0; k < WB_CELLS / WB_NT; ++k) {
-        const int c = tid * (WB_CELLS / WB_NT) + k;
-        out.cell_start[c] = run;
-        s_cnt[c] = run;          // becomes the scatter cursor
+    for (int k = 0; k < PER; ++k) {
+        cell_start[tid * PER + k] = run;
+        cnt[tid * PER + k] = 0;      // self-cleaning
         run += v[k];
     }
-    if (tid == WB_NT - 1) out.cell_start[WB_CELLS] = run;
-    __syncthreads();
-    for (int i = tid; i < n; i += WB_NT) {
-        const float2 p = t_xy[i];
-        const int cell = wb_wrap(wb_cell_coord(p.y, inv_cell)) * WB_G + wb_wrap(wb_cell_coord(p.x, inv_cell));
-        const int pos = atomicAdd(&s_cnt[cell], 1);
-        out.desc[2 * (size_t)pos] = t_desc[2 * (size_t)i];
-        out.desc[2 * (size_t)pos + 1] = t_desc[2 * (size_t)i + 1];
-        out.xy[pos] = p;
-        out.orig[pos] = i;
-    }
+    if (tid == 255) cell_start[WB_CELLS] = run;
+}
+
+// pass 2 (many CTAs): rows to their place in cell order
+__global__ void __launch_bounds__(256) wb_scatter_kernel(const uint4 *t_desc, const float2 *t_xy, int32_t n_rows, const int32_t *t_limit,
+                                                         const int32_t *cell_of, const int32_t *rank_of, BinView out) {
+    const int n = t_limit ? max(0, min(n_rows, *t_limit)) : n_rows;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int pos = out.cell_start[cell_of[i]] + rank_of[i];
+    out.desc[2 * (size_t)pos] = t_desc[2 * (size_t)i];
+    out.desc[2 * (size_t)pos + 1] = t_desc[2 * (size_t)i + 1];
+    out.xy[pos] = t_xy[i];
+    out.orig[pos] = i;
 }
 
 constexpr int WS_NT = 256;   // 8 queries per CTA, one warp each

@@ -501,6 +501,23 @@ def test_binned_window_search_equals_brute_force(eng, case):
         eng.set_tuning(window_bins=0)
         _eq(got_binned, want, (case, kw))
         _eq(got_brute, want, (case, kw))
-        assert binned_kernels == 2                                       # bin + search
+        assert binned_kernels == 3                                       # rank + scatter + search
     oi, od = c_oracle.knn(q, t, 2, dense)
     _eq(eng.knn(q, t, 2, window=win), (oi, od), case)
+
+
+def test_large_single_problem_tile_parallel_finalize(eng):
+    """A single problem with >= 8192 query rows is finalized by the tile-parallel kernels (the in-kernel
+    finalize is one CTA per problem): same results, workspace left clean for the next call."""
+    q, t, _ = synth.correlated(9001, 700, 123)
+    oi, od = c_oracle.knn(q, t, 3)
+    for k in (1, 2, 3):
+        idx, dist = eng.knn(q, t, k)
+        assert np.array_equal(idx, oi[:, :k]) and np.array_equal(dist, od[:, :k]), k
+        assert eng.launch_info()["kernels_launched"] == 3 * ((k + 1) // 2)
+    _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t))
+    _eq(eng.match(q, t, k=2, ratio=0.8), orc.match(q, t, k=2, ratio=0.8))
+    _eq(eng.match(q, t, cross_check=True, max_distance=25), orc.match(q, t, cross_check_=True, max_distance=25))
+    q2, t2, _ = synth.correlated(500, 800, 124)                       # a normal call right after: clean workspace
+    _eq(eng.match(q2, t2, cross_check=True), c_oracle.cross_check(q2, t2))
+    _eq(eng.knn(q2, t2, 2), c_oracle.knn(q2, t2, 2))

@@ -1,0 +1,65 @@
+"""BASELINE config 5: brute-force sweep Q, T in {1k .. 64k}^2 on uniform synthetic descriptors, k = 1, k = 2 and
+cross-check; device-resident inputs, kernel time from CUDA events around the launch.  Also checks size-
+independent properties at every point (self-match: knn(t, t) finds row i at distance 0; cross-check of a
+set with itself is the identity on de-duplicated rows)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import boslam_b200 as bb  # noqa: E402
+from boslam_b200 import synth  # noqa: E402
+
+SIZES = [1024, 4096, 16384, 65536]
+
+
+def main():
+    eng = bb.Engine(0)
+    eng.set_tuning(timing=1)
+    base = synth.uniform(65536, 7)
+    other = synth.uniform(65536, 8)
+    out = []
+    try:
+        import cv2
+    except Exception:
+        cv2 = None
+    for nq in SIZES:
+        for nt in SIZES:
+            q, t = torch.from_numpy(base[:nq]).cuda(), torch.from_numpy(other[:nt]).cuda()
+            tab = bb.make_problems([nq], [nt])
+            for mode, kw in (("k1", dict(k=1)), ("k2", dict(k=2)), ("cross", dict(cross_check=True))):
+                ts = []
+                for _ in range(5):
+                    eng.match_batched_device(q, t, tab, **kw)
+                    ts.append(eng.launch_info()["scan_ms"])
+                li = eng.launch_info()
+                ms = float(np.median(ts[1:]))
+                rec = dict(Q=nq, T=nt, mode=mode, kernel_ms=ms, gpairs=nq * nt / ms / 1e6, grid=li["scan_grid"],
+                           R=li["queries_per_thread"], seg_rows=li["train_rows_per_segment"])
+                if cv2 is not None and nq == nt and nq <= 16384 and mode in ("k2", "cross"):
+                    m = cv2.BFMatcher_create(cv2.NORM_HAMMING, crossCheck=(mode == "cross"))
+                    t0 = time.perf_counter()
+                    (m.match(base[:nq], other[:nt]) if mode == "cross" else m.knnMatch(base[:nq], other[:nt], 2))
+                    rec["cv2_ms"] = (time.perf_counter() - t0) * 1e3
+                    rec["cv2_threads"] = cv2.getNumThreads()
+                out.append(rec)
+                print(json.dumps(rec), flush=True)
+            if nq == nt:  # properties
+                idx, dist = eng.knn(q, q, 1)
+                ok_self = bool((dist[:, 0] == 0).all().item()) and bool((idx[:, 0] == torch.arange(nq, device=idx.device)).all().item())
+                qi, ti, d = eng.match(q, q, cross_check=True)
+                ok_cc = len(qi) == nq and bool((qi == ti).all().item()) and bool((d == 0).all().item())
+                print(json.dumps(dict(Q=nq, T=nt, self_match_ok=ok_self, self_cross_check_identity=ok_cc)), flush=True)
+                out.append(dict(Q=nq, T=nt, self_match_ok=ok_self, self_cross_check_identity=ok_cc))
+                assert ok_self and ok_cc
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/size_sweep.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

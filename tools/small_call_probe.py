@@ -55,3 +55,27 @@ os.environ["BFM_TRACE"] = "1"
 q, t, _ = synth.correlated(2000, 20000, 3)
 for _ in range(3):
     eng.match(q, t, cross_check=True, max_distance=30)
+
+# window (binned) vs brute force
+os.environ.pop("BFM_TRACE", None)
+q, t, qxy, txy, _ = synth.window_scene(2000, 20000, 12)
+import torch
+qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+qxyd, txyd = torch.from_numpy(qxy).cuda(), torch.from_numpy(txy).cuda()
+tab = bb.make_problems([2000], [20000])
+for wb in (0, 1):
+    eng.set_tuning(window_bins=wb, timing=1)
+    ks = []
+    for _ in range(20):
+        eng.match_batched_device(qd, td, tab, k=2, ratio=0.8, window=(qxyd, txyd, 15.0))
+        ks.append(eng.launch_info()["scan_ms"] * 1e3)
+    eng.set_tuning(timing=0)
+    e2e = timeit(lambda: eng.match(q, t, k=2, ratio=0.8, window=(qxy, txy, 15.0)))
+    print(f"track 2000x20000 window r=15 window_bins={wb}: kernels {np.median(ks):6.1f} us, Engine.match {e2e:6.1f} us", flush=True)
+eng.set_tuning(window_bins=0)
+sc = synth.local_map_scene(20000, 20000, 2000, seed=14)
+store = bb.MapStore(20000, engine=eng)
+store.update(np.arange(20000), sc["desc"], sc["pt3d"], sc["normal"])
+targs = (sc["des"], sc["kp"], sc["R"], sc["t"], sc["see_vector"], sc["edges"])
+print(f"MapStore.track cross-check gate30: {timeit(lambda: store.track(*targs)):6.1f} us;  window r=15 + ratio: "
+      f"{timeit(lambda: store.track(*targs, cross_check=False, k=2, ratio=0.8, max_distance=None, window_radius=15.0)):6.1f} us")
