@@ -113,7 +113,7 @@ def cv2_step(matcher, q, t, tab, ratio):
     return n
 
 
-def reference_arm(args):
+def reference_arm(args, emit):
     """--impl reference: cv2.BFMatcher on the host cores, same config / metric / unit."""
     rank = _env_int("RANK", 0)
     if rank != 0:
@@ -153,7 +153,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -280,8 +280,20 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    # stdout carries exactly ONE JSON line: anything a library prints there while we run (NCCL writes its
+    # version banner to stdout) goes to stderr instead; the real stdout is restored for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        reference_arm(args)
+        reference_arm(args, emit)
         return
 
     import torch
@@ -473,7 +485,7 @@ def main():
         line["frames"] = extras(eng, torch, args.steps)
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
