@@ -47,23 +47,33 @@ def _check_desc_np(a, name: str) -> np.ndarray:
     return a
 
 
+class _PinnedBlock:
+    """Owns one cudaMallocHost allocation; freed when the last reference (buffer object or numpy view) dies."""
+
+    def __init__(self, lib, nbytes: int):
+        p = ctypes.c_void_p()
+        _ffi.check(None, lib.bfm_host_alloc(max(int(nbytes), 1), ctypes.byref(p)))
+        self.ptr = p.value
+        self._fin = weakref.finalize(self, lib.bfm_host_free, ctypes.c_void_p(self.ptr))
+
+
 class PinnedBuffer:
-    """Page-locked host memory exposed as a numpy array (``.array``)."""
+    """Page-locked host memory exposed as a numpy array (``.array``).  Views of ``.array`` (for instance
+    the slices a :class:`BatchResult` hands out) keep the allocation alive on their own."""
 
     def __init__(self, shape, dtype=np.uint8):
-        self._lib = _ffi.lib()
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) * dtype.itemsize
-        p = ctypes.c_void_p()
-        _ffi.check(None, self._lib.bfm_host_alloc(max(n, 1), ctypes.byref(p)))
-        self._ptr = p.value
+        self._block = _PinnedBlock(_ffi.lib(), n)
+        self._ptr = self._block.ptr
         raw = (ctypes.c_uint8 * max(n, 1)).from_address(self._ptr)
+        raw._block = self._block  # numpy view -> ctypes array -> block: no view can outlive the memory
         self.array = np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        self._fin = weakref.finalize(self, self._lib.bfm_host_free, ctypes.c_void_p(self._ptr))
 
     def free(self):
+        """Release now.  Only safe when no view of ``.array`` is used afterwards."""
         self.array = None
-        self._fin()
+        self._block._fin()
 
 
 class BatchResult:

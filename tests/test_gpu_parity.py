@@ -521,3 +521,20 @@ def test_large_single_problem_tile_parallel_finalize(eng):
     q2, t2, _ = synth.correlated(500, 800, 124)                       # a normal call right after: clean workspace
     _eq(eng.match(q2, t2, cross_check=True), c_oracle.cross_check(q2, t2))
     _eq(eng.knn(q2, t2, 2), c_oracle.knn(q2, t2, 2))
+
+
+def test_pinned_views_keep_their_memory_alive(eng):
+    """A BatchResult built on HostBatchBuffers stays valid after the buffers object is dropped."""
+    import gc
+    qs, ts = synth.keyframe_pairs(4, 300, seed=5)
+    tab = bb.make_problems([300] * 4, [300] * 4)
+    ob = bb.HostBatchBuffers(1200, 4, k=2)
+    res = eng.match_batched(np.concatenate(qs), np.concatenate(ts), tab, k=2, ratio=0.8, out=ob)
+    want = [orc.match(qs[p], ts[p], k=2, ratio=0.8) for p in range(4)]
+    del ob
+    gc.collect()
+    junk = [bb.PinnedBuffer((1200, 3), np.int32) for _ in range(4)]   # would reuse the freed block
+    for j in junk:
+        j.array[...] = -5
+    for p in range(4):
+        _eq(res[p], want[p], p)
