@@ -227,6 +227,47 @@ def extras(eng, torch, steps):
         lambda: eng.match_batched(qb, tb, tab3, k=2, ratio=RATIO),
         lambda: eng.match_batched_device(qbd, tbd, tab3, k=2, ratio=RATIO),
         1, 20 * 2000 * 2000, reps)
+    # configs[0] in full (experiments/pnp_one_way_tracking.py:30-41): crossCheck match of two RGB-D frames, then
+    # cv2.solvePnPRansac on the matched (3-D, 2-D) pairs.  PnP stays on the host CPU in both arms (north star).
+    try:
+        import cv2
+        from oracle import cv2_reference as ref
+        prev, cur, _, _ = synth.rgbd_frame_pair(1000, seed=15)
+        cam_mat = np.array([[384.23901367, 0., 322.43237305], [0., 384.23901367, 239.65332031], [0., 0., 1.]])
+        dist_coefs = np.zeros((8, 1), np.float32)
+
+        def pnp(inds_prev, inds):
+            a = np.ascontiguousarray(prev["cloud_kp"][inds_prev, :])
+            b = np.ascontiguousarray(cur["kp_arr"][inds, :].astype(np.float64))
+            return cv2.solvePnPRansac(a, b, cam_mat, dist_coefs)
+
+        def ours():
+            qi, ti, _ = eng.match(prev["des"], cur["des"], cross_check=True)
+            return pnp(qi, ti), len(qi)
+
+        def theirs():
+            ms = ref.matcher(True).match(prev["des"], cur["des"])
+            inds_prev, inds = zip(*((m.queryIdx, m.trainIdx) for m in ms))
+            return pnp(np.asarray(inds_prev), np.asarray(inds)), len(ms)
+
+        (ok_a, _, tv_a, inl_a), n_a = ours()
+        (ok_b, _, tv_b, inl_b), n_b = theirs()
+
+        def clock(f, n):
+            t0 = time.perf_counter()
+            for _ in range(n):
+                f()
+            return (time.perf_counter() - t0) / n
+        t_ours, t_theirs = clock(ours, reps), clock(theirs, 5)
+        t_match = clock(lambda: eng.match(prev["des"], cur["des"], cross_check=True), reps)
+        out["frame_to_frame_1000x1000_match_plus_pnp"] = {
+            "frames_per_s_e2e": 1.0 / t_ours, "ms_e2e": t_ours * 1e3, "ms_match_only": t_match * 1e3,
+            "cv2_frames_per_s": 1.0 / t_theirs, "cv2_ms": t_theirs * 1e3, "matches": int(n_a), "cv2_matches": int(n_b),
+            "pnp_ok": bool(ok_a) and bool(ok_b), "pnp_inliers": int(len(inl_a)) if inl_a is not None else 0,
+            "same_matches_as_cv2": bool(n_a == n_b), "note": "solvePnPRansac runs on the host CPU in both arms"}
+    except Exception as e:  # cv2 missing: the line is context, not the metric
+        out["frame_to_frame_1000x1000_match_plus_pnp"] = {"error": repr(e)}
+
     # the whole slam/tracking.py:96-128 step against a device-resident local map
     # (20k (keyframe, map point) edges, 2000 frame descriptors): projection + visibility + compaction +
     # cross-check match + gate + gather, one call.  CPU figure: the numpy restatement + cv2 match.

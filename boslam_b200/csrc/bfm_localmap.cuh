@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(LM_NT) lm_project_kernel(const ProjectParams p
 // pass 2: ordered compaction + gathers.  Survivor number j (in edge order) becomes train row j.
 __global__ void __launch_bounds__(LM_NT) lm_compact_kernel(const MapView map, const int32_t *edges, int32_t n_edges,
                                                            const double2 *pix, const uint8_t *flag, const int32_t *block_count,
-                                                           int32_t *vis_edge, double2 *vis_pix, float2 *t_xy, uint4 *t_desc,
-                                                           double *vis_pt3d, int32_t *n_visible) {
+                                                           int32_t *vis_edge, float2 *t_xy, uint4 *t_desc, double *vis_pt3d,
+                                                           int32_t *n_visible, int32_t *h_vis_edge, double2 *h_vis_pix,
+                                                           int32_t *h_n_visible) {
     __shared__ int s_red[LM_NT / 32];
     __shared__ int s_warp[LM_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -110,13 +111,15 @@ __global__ void __launch_bounds__(LM_NT) lm_compact_kernel(const MapView map, co
         int before = 0;
         for (int w = 0; w < LM_NT / 32; ++w) before += s_red[w];
         *n_visible = before + mine;
+        *h_n_visible = before + mine;   // pinned host memory: the caller reads it after the stream drains
     }
     if (!vis) return;
     pos += __popc(bal & ((1u << lane) - 1u));
     const int slot = edges[e];
     const double2 p = pix[e];
     vis_edge[pos] = e;
-    vis_pix[pos] = p;
+    h_vis_edge[pos] = e;
+    if (h_vis_pix) h_vis_pix[pos] = p;
     t_xy[pos] = make_float2((float)p.x, (float)p.y);
     const uint4 *d = reinterpret_cast<const uint4 *>(map.desc + 32 * (size_t)slot);
     t_desc[2 * (size_t)pos] = d[0];

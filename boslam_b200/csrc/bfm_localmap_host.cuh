@@ -134,41 +134,48 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     if (n_edges == 0) return BFM_OK;
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    const bool trace = std::getenv("BFM_TRACE") != nullptr;
+    const auto cpu0 = std::chrono::steady_clock::now();
+    auto cpu_us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - cpu0).count(); };
     const int nblk = (n_edges + LM_NT - 1) / LM_NT;
     const int nqa = std::max(nq, 1);
 
-    // ---- staging layout: [inputs | scratch | outputs] on the device, inputs / outputs mirrored in pinned memory
+    // ---- layout: device block [inputs | scratch]; pinned host blocks for the inputs (one H2D copy) and for the
+    //      outputs, which the kernels write directly (zero-copy over PCIe: only what exists is transferred)
     Carver din(nullptr);
     din.take<int32_t>(n_edges);
     din.take<uint8_t>((size_t)nqa * 32);
     din.take<double>((size_t)nqa * 2);
     const size_t in_bytes = din.off;
-    Carver dout(nullptr);
-    dout.take<int32_t>(4);                        // n_visible, m_count
-    dout.take<int32_t>(n_edges);                  // vis_edge
-    dout.take<double2>(n_edges);                  // vis_pix
-    dout.take<int32_t>((size_t)nqa * 3);          // m_query | m_train | m_dist
-    dout.take<int32_t>(nqa);                      // m_edge
-    dout.take<double>((size_t)nqa * 3);           // m_pts3d
-    dout.take<double>((size_t)nqa * 2);           // m_kp
-    const size_t out_bytes = dout.off;
+    Carver hout(nullptr);
+    hout.take<int32_t>(4);                        // n_visible, m_count
+    hout.take<int32_t>(n_edges);                  // vis_edge
+    hout.take<double2>(visible_pixels ? n_edges : 0);   // vis_pix
+    hout.take<int32_t>((size_t)nqa * 3);          // m_query | m_train | m_dist
+    hout.take<int32_t>(nqa);                      // m_edge
+    hout.take<double>((size_t)nqa * 3);           // m_pts3d
+    hout.take<double>((size_t)nqa * 2);           // m_kp
+    const size_t out_bytes = hout.off;
     Carver dsc(nullptr);
+    dsc.take<int32_t>(4);                         // header: n_visible, m_count
     dsc.take<double2>(n_edges);                   // pix
     dsc.take<uint8_t>(n_edges);                   // flag
     dsc.take<int32_t>(nblk);                      // block_count
+    dsc.take<int32_t>(n_edges);                   // vis_edge
     dsc.take<float2>(n_edges);                    // t_xy
     dsc.take<uint4>((size_t)n_edges * 2);         // t_desc
     dsc.take<double>((size_t)n_edges * 3);        // vis_pt3d
     dsc.take<float2>(nqa);                        // q_xy
+    dsc.take<int32_t>((size_t)nqa * 3);           // m_query | m_train | m_dist (device copy: the gather reads it)
     const size_t scratch_bytes = dsc.off;
-    int rc = ensure(h, m->work, in_bytes + scratch_bytes + out_bytes);
+    int rc = ensure(h, m->work, in_bytes + scratch_bytes);
     if (rc) return rc;
     rc = ensure_pinned(h, &m->h_in, &m->h_in_cap, in_bytes);
     if (rc) return rc;
     rc = ensure_pinned(h, &m->h_out, &m->h_out_cap, out_bytes);
     if (rc) return rc;
     char *dbase = static_cast<char *>(m->work.p);
-    Carver di(dbase), hi(m->h_in), ds(dbase + in_bytes), dov(dbase + in_bytes + scratch_bytes), ho(m->h_out);
+    Carver di(dbase), hi(m->h_in), ds(dbase + in_bytes), ho(m->h_out);
     int32_t *d_edges = di.take<int32_t>(n_edges);
     uint8_t *d_q = di.take<uint8_t>((size_t)nqa * 32);
     double *d_kp = di.take<double>((size_t)nqa * 2);
@@ -179,21 +186,27 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
         std::memcpy(hq, q_desc, (size_t)nq * 32);
         std::memcpy(hkp, q_kp, (size_t)nq * 16);
     }
+    int32_t *d_hdr = ds.take<int32_t>(4);
     double2 *d_pix = ds.take<double2>(n_edges);
     uint8_t *d_flag = ds.take<uint8_t>(n_edges);
     int32_t *d_bc = ds.take<int32_t>(nblk);
+    int32_t *d_vedge = ds.take<int32_t>(n_edges);
     float2 *d_txy = ds.take<float2>(n_edges);
     uint4 *d_tdesc = ds.take<uint4>((size_t)n_edges * 2);
     double *d_vpt = ds.take<double>((size_t)n_edges * 3);
     float2 *d_qxy = ds.take<float2>(nqa);
-    int32_t *d_hdr = dov.take<int32_t>(4);
-    int32_t *d_vedge = dov.take<int32_t>(n_edges);
-    double2 *d_vpix = dov.take<double2>(n_edges);
-    int32_t *d_m = dov.take<int32_t>((size_t)nqa * 3);
-    int32_t *d_medge = dov.take<int32_t>(nqa);
-    double *d_mpt = dov.take<double>((size_t)nqa * 3);
-    double *d_mkp = dov.take<double>((size_t)nqa * 2);
+    int32_t *d_m = ds.take<int32_t>((size_t)nqa * 3);
+    int32_t *h_hdr = ho.take<int32_t>(4);
+    int32_t *h_vedge = ho.take<int32_t>(n_edges);
+    double2 *h_vpix = ho.take<double2>(visible_pixels ? n_edges : 0);
+    if (!visible_pixels) h_vpix = nullptr;
+    int32_t *h_m = ho.take<int32_t>((size_t)nqa * 3);
+    int32_t *h_medge = ho.take<int32_t>(nqa);
+    double *h_mpt = ho.take<double>((size_t)nqa * 3);
+    double *h_mkp = ho.take<double>((size_t)nqa * 2);
+    h_hdr[0] = h_hdr[1] = 0;
 
+    const double t_staged = cpu_us();
     CU_TRY(h, cudaMemcpyAsync(dbase, m->h_in, in_bytes, cudaMemcpyHostToDevice, st));
     CU_TRY(h, cudaMemsetAsync(d_hdr, 0, 16, st));
 
@@ -207,7 +220,8 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     MapView mv{m->desc, m->pt3d, m->normal};
     lm_project_kernel<<<nblk, LM_NT, 0, st>>>(pp, mv, d_edges, n_edges, m->capacity, d_pix, d_flag, d_bc);
     CU_TRY(h, cudaGetLastError());
-    lm_compact_kernel<<<nblk, LM_NT, 0, st>>>(mv, d_edges, n_edges, d_pix, d_flag, d_bc, d_vedge, d_vpix, d_txy, d_tdesc, d_vpt, d_hdr);
+    lm_compact_kernel<<<nblk, LM_NT, 0, st>>>(mv, d_edges, n_edges, d_pix, d_flag, d_bc, d_vedge, d_txy, d_tdesc, d_vpt, d_hdr,
+                                              h_vedge, h_vpix, h_hdr);
     CU_TRY(h, cudaGetLastError());
     int kernels = 2;
     if (nq > 0) {
@@ -220,28 +234,24 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
             od.t_xy = reinterpret_cast<const float *>(d_txy);
         }
         // the train set is the compacted survivor list: its size lives in d_hdr[0]; the plan covers
-        // all n_edges rows and every work item clamps its range on the device (no host round trip)
+        // all n_edges rows and every work item clamps its range on the device (no host round trip).
+        // Two destinations: a device copy (the gather below reads it) and the pinned host block.
         const bfm_problem_t pr = {0, nq, 0, n_edges, 0, 0};
-        const bfm_outputs_t out = {nullptr, nullptr, d_m, d_m + nqa, d_m + 2 * (size_t)nqa, d_hdr + 1};
-        rc = run_device(h, d_q, nq, reinterpret_cast<const uint8_t *>(d_tdesc), n_edges, &pr, 1, nq, &od, &out, 1, st, nullptr, d_hdr);
+        const bfm_outputs_t outs[2] = {{nullptr, nullptr, d_m, d_m + nqa, d_m + 2 * (size_t)nqa, d_hdr + 1},
+                                       {nullptr, nullptr, h_m, h_m + nqa, h_m + 2 * (size_t)nqa, h_hdr + 1}};
+        rc = run_device(h, d_q, nq, reinterpret_cast<const uint8_t *>(d_tdesc), n_edges, &pr, 1, nq, &od, outs, 2, st, nullptr, d_hdr);
         if (rc) return rc;
         kernels += h->info.kernels_launched;
-        lm_gather_kernel<<<(nq + LM_NT - 1) / LM_NT, LM_NT, 0, st>>>(d_m, d_m + nqa, d_hdr + 1, d_vpt, d_vedge, d_kp, d_mpt, d_mkp, d_medge);
+        lm_gather_kernel<<<(nq + LM_NT - 1) / LM_NT, LM_NT, 0, st>>>(d_m, d_m + nqa, d_hdr + 1, d_vpt, d_vedge, d_kp, h_mpt, h_mkp, h_medge);
         CU_TRY(h, cudaGetLastError());
         ++kernels;
     }
-    CU_TRY(h, cudaMemcpyAsync(m->h_out, dbase + in_bytes + scratch_bytes, out_bytes, cudaMemcpyDeviceToHost, st));
+    const double t_queued = cpu_us();
     CU_TRY(h, cudaStreamSynchronize(st));
+    const double t_synced = cpu_us();
     h->launches += kernels - (nq > 0 ? h->info.kernels_launched : 0);
     h->info.kernels_launched = kernels;
 
-    const int32_t *h_hdr = ho.take<int32_t>(4);
-    const int32_t *h_vedge = ho.take<int32_t>(n_edges);
-    const double2 *h_vpix = ho.take<double2>(n_edges);
-    const int32_t *h_m = ho.take<int32_t>((size_t)nqa * 3);
-    const int32_t *h_medge = ho.take<int32_t>(nqa);
-    const double *h_mpt = ho.take<double>((size_t)nqa * 3);
-    const double *h_mkp = ho.take<double>((size_t)nqa * 2);
     const int nv = h_hdr[0], nm = h_hdr[1];
     *n_visible = nv;
     *n_matches = nm;
@@ -253,6 +263,9 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     if (m_edge) std::memcpy(m_edge, h_medge, (size_t)nm * 4);
     if (m_pts3d) std::memcpy(m_pts3d, h_mpt, (size_t)nm * 24);
     if (m_kp) std::memcpy(m_kp, h_mkp, (size_t)nm * 16);
+    if (trace)
+        std::fprintf(stderr, "[bfm trace] track_local_map: inputs staged %.1f us, %d kernels + copies queued %.1f us, synced %.1f us, "
+                     "outputs copied %.1f us (in %zu B, out %zu B)\n", t_staged, kernels, t_queued, t_synced, cpu_us(), in_bytes, out_bytes);
     return BFM_OK;
 }
 

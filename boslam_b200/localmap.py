@@ -75,7 +75,7 @@ def quaternion_from_rotation(R) -> tuple:
 @dataclass
 class TrackResult:
     visible_edges: np.ndarray   # int32[V]   edge numbers that passed (train row j = visible_edges[j])
-    visible_pixels: np.ndarray  # float64[V, 2] their projections
+    visible_pixels: Optional[np.ndarray]  # float64[V, 2] their projections (only with want_pixels)
     inds_frame: np.ndarray      # int32[M]   queryIdx  (slam/tracking.py:126)
     inds: np.ndarray            # int32[M]   trainIdx into the visible list
     distance: np.ndarray        # float32[M]
@@ -125,10 +125,11 @@ class MapStore:
 
     def track(self, frame_des, frame_kp, R, t, see_vector, edges, cam: Optional[CameraModel] = None,
               cos_max: float = COS60, cross_check: bool = True, max_distance=30, strict: bool = False,
-              k: int = 1, ratio=None, window_radius=None) -> TrackResult:
+              k: int = 1, ratio=None, window_radius=None, want_pixels: bool = False) -> TrackResult:
         """One ``_track_local_map`` candidate + match step.  Defaults are the reference's: crossCheck
         matcher (``slam/tracking.py:45``), ``distance <= 30`` (``:121``).  ``window_radius`` adds the
-        projection-guided window of the north star (|kp - projected pixel| < r in both axes)."""
+        projection-guided window of the north star (|kp - projected pixel| < r in both axes).
+        ``want_pixels`` also returns the projections of the visible points (16 bytes each over PCIe)."""
         cam = cam or CameraModel()
         q = np.ascontiguousarray(frame_des)
         if q.dtype != np.uint8:
@@ -151,19 +152,20 @@ class MapStore:
         if window_radius is not None:
             opts.mask_kind, opts.window_radius = _ffi.MASK_WINDOW, float(window_radius)
         vis_e = np.empty(max(ne, 1), np.int32)
-        vis_p = np.empty((max(ne, 1), 2), np.float64)
+        vis_p = np.empty((max(ne, 1), 2), np.float64) if want_pixels else None
         mq, mt, md, me = (np.empty(max(nq, 1), np.int32) for _ in range(4))
         mp3 = np.empty((max(nq, 1), 3), np.float64)
         mkp = np.empty((max(nq, 1), 2), np.float64)
         nv, nm = ctypes.c_int32(0), ctypes.c_int32(0)
         with self.engine._lock:
             rc = self._lib.bfm_track_local_map(self._m, ctypes.byref(tp), edges.ctypes.data, ne, q.ctypes.data, kp.ctypes.data,
-                                               nq, ctypes.byref(opts), vis_e.ctypes.data, vis_p.ctypes.data, mq.ctypes.data,
+                                               nq, ctypes.byref(opts), vis_e.ctypes.data,
+                                               vis_p.ctypes.data if want_pixels else None, mq.ctypes.data,
                                                mt.ctypes.data, md.ctypes.data, me.ctypes.data, mp3.ctypes.data,
                                                mkp.ctypes.data, ctypes.byref(nv), ctypes.byref(nm))
             _ffi.check(self.engine._h, rc)
         v, m = nv.value, (0 if none_pass else nm.value)
-        return TrackResult(vis_e[:v], vis_p[:v], mq[:m], mt[:m], md[:m].astype(np.float32), me[:m], mp3[:m], mkp[:m])
+        return TrackResult(vis_e[:v], vis_p[:v] if want_pixels else None, mq[:m], mt[:m], md[:m].astype(np.float32), me[:m], mp3[:m], mkp[:m])
 
 
 def select_representative(obs, counts, engine: Optional[Engine] = None, device: int = 0) -> np.ndarray:

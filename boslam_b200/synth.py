@@ -157,3 +157,43 @@ def local_map_scene(n_points: int, n_edges: int, n_frame: int, seed: int = 0, p_
         kp[:n_true, 1] = np.clip(np.round(v[src] + rng.normal(0, 2.0, n_true)), 0, HEIGHT - 1)
     return {"desc": desc, "pt3d": pt3d, "normal": normal, "edges": edges, "R": R, "t": t, "see_vector": see,
             "des": des, "kp": kp, "fx": fx, "fy": fy, "cx": cx, "cy": cy, "width": WIDTH, "height": HEIGHT}
+
+
+def rgbd_frame_pair(n_desc: int = 1000, seed: int = 0, p_flip: float = 0.04):
+    """BASELINE config 1: two synthetic 640x480 RGB-D frames with ``n_desc`` ORB descriptors each, shaped
+    like the reference's ``Frame`` (``camera.py:6-43``): ``des uint8[N,32]``, ``kp_arr int[N,2]``,
+    ``cloud_kp float64[N,3]``.  ~70 % of the previous frame's features reappear in the current frame
+    (noisy descriptor, pixel re-projected through a small known motion), the rest are new.
+    Returns (prev, cur, R, t) with prev / cur dicts of those three arrays."""
+    rng = np.random.default_rng(seed)
+    fx = fy = 384.239013671875
+    cx, cy = 322.432373046875, 239.6533203125
+    ang = rng.uniform(-0.03, 0.03, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+    Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+    Rz = np.array([[np.cos(ang[2]), -np.sin(ang[2]), 0], [np.sin(ang[2]), np.cos(ang[2]), 0], [0, 0, 1]])
+    R = Rz @ Ry @ Rx
+    t = rng.uniform(-0.05, 0.05, 3)
+
+    def frame(n):
+        u = rng.integers(8, WIDTH - 8, n)
+        v = rng.integers(8, HEIGHT - 8, n)
+        z = rng.uniform(0.6, 6.0, n)
+        cloud = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], axis=1)
+        return {"des": rng.integers(0, 256, (n, DESC_BYTES), dtype=np.uint8), "kp_arr": np.stack([u, v], 1).astype(np.int64),
+                "cloud_kp": cloud}
+
+    prev, cur = frame(n_desc), frame(n_desc)
+    n_true = int(0.7 * n_desc)
+    src = rng.permutation(n_desc)[:n_true]
+    dst = rng.permutation(n_desc)[:n_true]
+    Xc = prev["cloud_kp"][src] @ R.T + t                      # the same 3-D points in the current camera
+    u = Xc[:, 0] / Xc[:, 2] * fx + cx + rng.normal(0, 0.5, n_true)
+    v = Xc[:, 1] / Xc[:, 2] * fy + cy + rng.normal(0, 0.5, n_true)
+    ok = (u >= 0) & (u < WIDTH) & (v >= 0) & (v < HEIGHT)
+    src, dst, u, v, Xc = src[ok], dst[ok], u[ok], v[ok], Xc[ok]
+    flips = np.packbits(rng.random((len(src), DESC_BYTES * 8)) < p_flip, axis=1)
+    cur["des"][dst] = prev["des"][src] ^ flips
+    cur["kp_arr"][dst] = np.stack([np.round(u), np.round(v)], 1).astype(np.int64)
+    cur["cloud_kp"][dst] = Xc
+    return prev, cur, R, t
