@@ -362,7 +362,9 @@ def main():
     n_out = N_PAIRS * N_DESC
     pairs_per_step = N_PAIRS * N_DESC * N_DESC
 
-    # -- inputs: N_SETS distinct synthetic batches per rank, pinned on the host + resident in HBM --
+    # -- inputs: N_SETS distinct synthetic batches per rank, pinned on the host + resident in HBM.  The resident
+    #    copies are uploaded FROM the pinned buffers, so every pinned page has been read by the device once
+    #    before any timing (a pinned page's first device access is slower; real callers reuse their staging) --
     pinned, dev_sets = [], []
     for s in range(N_SETS):
         q, t = synth.keyframe_pair_batch(N_PAIRS, N_DESC, seed=1000 * rank + s)
@@ -370,7 +372,7 @@ def main():
         pq.array[...] = q
         pt.array[...] = t
         pinned.append((pq, pt))
-        dev_sets.append((torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)))
+        dev_sets.append((torch.from_numpy(pq.array).to(dev), torch.from_numpy(pt.array).to(dev)))
     out = {"m": torch.empty((3, n_out), dtype=torch.int32, device=dev),
            "count": torch.zeros(N_PAIRS, dtype=torch.int32, device=dev)}
     gathered_m = torch.empty((world * 3, n_out), dtype=torch.int32, device=dev) if dist else None

@@ -123,7 +123,8 @@ struct bfm_handle_s {
     unsigned long long seq = 0;              // call sequence number (watermark epoch)
 
     // tuning knobs
-    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0;
+    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0;
+    uint32_t *d_prog = nullptr;   // SM-fed upload: progress words of the feeder CTAs
     cudaEvent_t ev[2] = {nullptr, nullptr};
 
     bfm_launch_info_t info{};
@@ -294,6 +295,12 @@ struct Gate {
     const unsigned long long *ready = nullptr;  // device: [0] query rows landed, [1] train rows landed (+ base)
     unsigned long long base = 0;
     uint32_t *status = nullptr;                 // pinned host word, device-visible
+    // SM-fed variant (pinned caller arrays): the first n_feed CTAs of the launch do the upload themselves
+    int n_feed = 0, rounds = 0, q_rows = 0, t_rows = 0;
+    const void *src[4] = {nullptr, nullptr, nullptr, nullptr};
+    void *dst[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t bytes[4] = {0, 0, 0, 0};
+    uint32_t *prog = nullptr;
 };
 
 // The device path: every data pointer is device-visible, work is queued on `st`.  ONE kernel launch.
@@ -476,6 +483,19 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         sp.ready_base = gate->base;
         sp.status = gate->status;
     }
+    const int n_feed = (gate && gate->n_feed > 0) ? gate->n_feed : 0;
+    if (n_feed) {
+        sp.n_feed = n_feed;
+        sp.feed_rounds = gate->rounds;
+        sp.feed_q_rows = gate->q_rows;
+        sp.feed_t_rows = gate->t_rows;
+        for (int a = 0; a < 4; ++a) {
+            sp.feed_src[a] = static_cast<const uint4 *>(gate->src[a]);
+            sp.feed_dst[a] = static_cast<uint4 *>(gate->dst[a]);
+            sp.feed_bytes[a] = gate->bytes[a];
+        }
+        sp.feed_prog = gate->prog;
+    }
     sp.mask = o->mask;
     sp.mask_stride = o->mask_row_stride;
     sp.q_xy = reinterpret_cast<const float2 *>(o->q_xy);
@@ -546,7 +566,8 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             for (int d = 0; d < n_dests; ++d) sp.dest[d].m_count = nullptr;
         const ScanFn fn = pick_scan(r, mode, mask, pm, pass > 0);
         sp.defer_finalize = defer ? 1 : 0;
-        fn<<<(unsigned)n_segs, NT, 0, st>>>(sp);
+        if (pass > 0) sp.n_feed = 0;   // the inputs are resident after the first pass
+        fn<<<(unsigned)(n_segs + (pass == 0 ? n_feed : 0)), NT, 0, st>>>(sp);
         CU_TRY(h, cudaGetLastError());
         if (defer) {
             bfm::fin_count_kernel<<<fin_tiles, bfm::FT_NT, 0, st>>>(sp, d_keep, d_tile);
@@ -632,6 +653,7 @@ int bfm_create(int device, bfm_handle_t *out) {
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_prog, 256) == cudaSuccess && cudaMemset(h->d_prog, 0, 256) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_ready, 256) == cudaSuccess && cudaMemset(h->d_ready, 0, 256) == cudaSuccess &&
          cudaMallocHost(&h->h_marks, sizeof(unsigned long long) * 2 * MAX_COPY_CHUNKS) == cudaSuccess &&
          cudaMallocHost(&h->h_status, 64) == cudaSuccess;
@@ -656,6 +678,7 @@ int bfm_destroy(bfm_handle_t h) {
     for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins, &h->fin})
         if (b->p) cudaFree(b->p);
     if (h->d_ready) cudaFree(h->d_ready);
+    if (h->d_prog) cudaFree(h->d_prog);
     if (h->h_marks) cudaFreeHost(h->h_marks);
     if (h->h_status) cudaFreeHost(h->h_status);
     for (int i = 0; i < N_TABLE_SLOTS; ++i) {
@@ -753,6 +776,12 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "pipeline_chunks") {
         if (value < 0 || value > MAX_COPY_CHUNKS) return fail(h, BFM_ERR_INVALID, "pipeline_chunks must be 0 (auto), 1 (off) .. 64");
         h->pipeline_chunks = value;
+    } else if (k == "feeders") {
+        if (value < -1 || value > bfm::FEED_MAX) return fail(h, BFM_ERR_INVALID, "feeders must be -1 (off: copy engine), 0 (auto) or 1..32");
+        h->feeders = value;
+    } else if (k == "feed_rows") {
+        if (value < 0) return fail(h, BFM_ERR_INVALID, "feed_rows must be >= 0");
+        h->feed_rows = value;
     } else if (k == "window_bins") {
         if (value != 0 && value != 1) return fail(h, BFM_ERR_INVALID, "window_bins must be 0 (auto) or 1 (brute force)");
         h->window_bins = value;

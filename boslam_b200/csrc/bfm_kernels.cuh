@@ -52,6 +52,8 @@ struct __align__(16) Problem {   // device view of bfm_problem_t
 };
 
 constexpr int MAX_DEST = 8;  // result replicas (this GPU + NVLink peers)
+constexpr int FEED_MAX = 32; // feeder CTAs of the SM-fed upload (their progress words share one 128-byte line)
+constexpr int FEED_HEAD = 8; // the first round of the SM-fed upload is delivered as this many short rounds
 
 // Everything one launch needs.  The kernel is scan + finalize in one: there is no second launch.
 struct ScanParams {
@@ -67,6 +69,16 @@ struct ScanParams {
     const unsigned long long *ready;
     unsigned long long ready_base;
     uint32_t *status;                // set non-zero if the gate timed out (host reports the error)
+    // SM-fed upload (host path with pinned inputs): the first n_feed CTAs of the grid stream the caller's
+    // arrays from pinned host memory into HBM in `feed_rounds` rounds and publish their progress; every
+    // other CTA waits until all feeders have passed the round that covers its rows.  See feed_rows().
+    int32_t n_feed;
+    int32_t feed_rounds;
+    int32_t feed_q_rows, feed_t_rows;        // rows of the query / train arrays delivered per round
+    const uint4 *feed_src[4];                // host-mapped: q desc, t desc, q_xy, t_xy (NULL = absent)
+    uint4 *feed_dst[4];                      // device copies
+    unsigned long long feed_bytes[4];        // total bytes of each array
+    uint32_t *feed_prog;                     // [FEED_MAX] rounds completed per feeder CTA (zeroed before the launch)
     const int32_t *t_limit;          // optional device scalar: train rows that exist (single problem), else NULL
     const uint8_t *mask;             // dense mask (single problem): [q_local][mask_stride]
     long long mask_stride;
@@ -359,6 +371,65 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
     }
 }
 
+// ---- SM-fed upload ---------------------------------------------------------------------------------------
+// A feeder CTA copies, round after round, its share of the next slice of every input array from pinned
+// host memory (zero-copy loads over PCIe, four 16-byte loads in flight per thread) into HBM, then
+// publishes "round r done".  No copy-engine operation, event or host involvement per slice, so the
+// slices can be as fine as a keyframe pair and the matching CTAs start microseconds after the launch.
+template <int NT>
+__device__ __noinline__ void feed_rows(const ScanParams &p) {
+    const int feeder = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long stride = (unsigned long long)p.n_feed * NT;       // 16-byte words per sweep
+    const unsigned long long me = (unsigned long long)feeder * NT + tid;
+    for (int r = 0; r < p.feed_rounds; ++r) {
+        // pairs of arrays (descriptors, then pixel coordinates): the loads of both are in flight together
+#pragma unroll
+        for (int pair = 0; pair < 2; ++pair) {
+            unsigned long long w0[2], w1[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int a = 2 * pair + s;
+                const unsigned long long rows = s ? (unsigned long long)p.feed_t_rows : (unsigned long long)p.feed_q_rows;
+                // rows per round is a multiple of 16; the first FEED_HEAD rounds are eighths of a round, so the
+                // matching CTAs of the first problems start after a few microseconds of upload
+                const unsigned long long per_round = rows * (pair == 0 ? 32ull : 8ull);
+                const unsigned long long b0 = r < FEED_HEAD ? (unsigned long long)r * (per_round / FEED_HEAD)
+                                                            : (unsigned long long)(r - FEED_HEAD + 1) * per_round;
+                const unsigned long long b1 = r < FEED_HEAD ? b0 + per_round / FEED_HEAD : b0 + per_round;
+                const unsigned long long lo = min(b0, p.feed_bytes[a]);
+                const unsigned long long hi = min(b1, p.feed_bytes[a]);
+                w0[s] = lo >> 4;
+                w1[s] = p.feed_src[a] ? (hi >> 4) : w0[s];
+                if (p.feed_src[a] && hi == p.feed_bytes[a] && (hi & 15) && hi > lo && me == 0) {
+                    // odd number of coordinate rows: the last 8 bytes (never read past the caller's array)
+                    const uint2 v = *reinterpret_cast<const uint2 *>(reinterpret_cast<const char *>(p.feed_src[a]) + (hi & ~15ull));
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(p.feed_dst[a]) + (hi & ~15ull)) = v;
+                }
+            }
+            const unsigned long long span = max(w1[0] - w0[0], w1[1] - w0[1]);
+            for (unsigned long long o = me; o < span; o += 4 * stride) {
+                uint4 v[2][4];
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (w0[s] + o + k * stride < w1[s]) v[s][k] = __ldcs(p.feed_src[2 * pair + s] + w0[s] + o + k * stride);
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (w0[s] + o + k * stride < w1[s]) p.feed_dst[2 * pair + s][w0[s] + o + k * stride] = v[s][k];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            volatile uint32_t *prog = p.feed_prog + feeder;
+            *prog = (uint32_t)(r + 1);
+        }
+    }
+}
+
 // ---- the distance-scan kernel --------------------------------------------------------------------
 // R     queries per thread (register tile)
 // K     1 or 2 neighbours tracked per query
@@ -383,12 +454,52 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     __shared__ int s_cnt[FIN_RPT][NW];
     __shared__ int s_flag;
 
-    const Segment sg = p.segs[blockIdx.x];
+    if ((int)blockIdx.x < p.n_feed) {   // the first CTAs of the grid feed the others (SM-fed upload)
+        feed_rows<NT>(p);
+        return;
+    }
+    const Segment sg = p.segs[blockIdx.x - p.n_feed];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     int col0 = 0;
     if (CROSS) col0 = p.problems[sg.problem].col0;
+
+    // -- input gate, SM-fed variant: wait until every feeder has finished the round that covers our rows
+    if (p.n_feed > 0) {
+        if (warp == 0) {
+            const int q_need = sg.q_row0 + sg.q_valid, t_need = sg.t_row0 + sg.t_count;
+            auto round_of = [](int rows, int per_round) {   // rounds that must be complete for rows [0, rows)
+                if (rows <= 0) return 0;
+                if (rows <= per_round) return (rows + per_round / FEED_HEAD - 1) / (per_round / FEED_HEAD);
+                return FEED_HEAD - 1 + (rows + per_round - 1) / per_round;
+            };
+            const int need = min(p.feed_rounds, max(round_of(q_need, p.feed_q_rows), round_of(t_need, p.feed_t_rows)));
+            const unsigned long long t0 = global_timer_ns();
+            int ok = 1;
+            uint32_t sleep_ns = 250u;
+            while (true) {
+                uint32_t v = 0xFFFFFFFFu;
+                if (lane < p.n_feed) v = *(volatile const uint32_t *)(p.feed_prog + lane);
+                v = __reduce_min_sync(0xffffffffu, v);
+                if ((int)v >= need) break;
+                __nanosleep(sleep_ns);                      // back off: a thousand CTAs poll one cache line
+                sleep_ns = min(sleep_ns * 2u, 4000u);
+                if (global_timer_ns() - t0 > 4000000000ull) {
+                    ok = 0;
+                    if (lane == 0) atomicExch(p.status, 1u);
+                    break;
+                }
+            }
+            // feeders: data stores, __threadfence, progress store; here: progress load, fence, data loads
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            if (lane == 0) s_flag = ok;
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        __syncthreads();   // s_flag is reused by the kernel tail
+    }
 
     // -- input gate (pipelined host path): wait until the copy engine has landed this segment's rows
     if (p.ready != nullptr) {

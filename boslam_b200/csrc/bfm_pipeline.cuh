@@ -3,19 +3,23 @@
 //
 // One kernel launch per call, however large the batch.  What overlaps with it:
 //
-//   inputs   The descriptor rows are uploaded by the copy engine in G chunks on `in_stream`; after
-//            each chunk a 16-byte watermark copy (rows landed so far) follows on the same stream.
-//            The kernel is launched right after the first chunk has been queued: every CTA waits
-//            at its input gate (bfm_kernels.cuh) until the watermarks cover the rows its segment
-//            reads.  Work items are in problem order and so are the chunks, so the SMs chase the
-//            copy engine through the batch and the wall time tends to max(copy, compute) without
-//            any per-chunk launch, event or host synchronisation.
-//   outputs  The CTA that completes a problem writes its result rows straight into pinned host
-//            memory over PCIe (the caller's arrays when those are pinned, else the handle's pinned
-//            staging block): there is no device result buffer and no D2H copy stage.
+//   inputs   (a) pinned caller arrays - SM-fed upload: the first 24 CTAs of the matching kernel stream the
+//            arrays from pinned host memory into HBM themselves (zero-copy loads over PCIe, bfm_kernels.cuh:
+//            feed_rows) in rounds of ~8k rows, the first round split in eight, and publish a per-feeder
+//            progress word; every other CTA waits at its input gate until all feeders have passed the round
+//            that covers its rows.  No copy-engine operation, event or host involvement per slice (each
+//            cudaMemcpyAsync costs ~5 us of DMA set-up here, which is what limited the chunked variant).
+//            (b) pageable caller arrays - copy-engine chunks: G chunks on `in_stream`, each followed by a
+//            16-byte watermark copy; the kernel is launched right after the first chunk has been queued and
+//            its CTAs wait on the watermarks.
+//            Work items are in problem order and so is the upload, so the SMs chase the data through the
+//            batch and the wall time tends to max(upload, compute).
+//   outputs  The CTA that completes a problem writes its result rows straight into pinned host memory over
+//            PCIe (the caller's arrays when those are pinned, else the handle's pinned staging block): there
+//            is no device result buffer and no D2H copy stage.
 //
-// Small calls (a frame against a keyframe or the local map) use one chunk on the compute stream
-// and no gate.  BFM_TRACE=1 in the environment prints the per-call timeline.
+// Small calls (a frame against a keyframe or the local map) use one copy on the compute stream and no gate.
+// BFM_TRACE=1 in the environment prints the per-call timeline.
 
 bool host_ptr_is_pinned(const void *p) {
     if (!p) return false;
@@ -98,7 +102,43 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
     const auto cpu0 = std::chrono::steady_clock::now();
     auto cpu_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - cpu0).count(); };
 
-    if (G <= 1) {
+    // SM-fed upload: pinned caller arrays are streamed into HBM by the first CTAs of the matching kernel itself
+    // (bfm_kernels.cuh: feed_rows) - no copy-engine operation per slice, so slices are as fine as a keyframe pair
+    const bool feed = G > 1 && h->feeders >= 0 && host_ptr_is_pinned(q) && host_ptr_is_pinned(t) &&
+                      (!window || (host_ptr_is_pinned(o->q_xy) && host_ptr_is_pinned(o->t_xy))) && o->k <= 2;
+    if (feed) {
+        Gate gate;
+        gate.status = h->h_status;
+        *h->h_status = 0;
+        gate.n_feed = h->feeders > 0 ? h->feeders : 24;
+        const int rows_per_round = h->feed_rows > 0 ? h->feed_rows : 8192;
+        const int S = std::max(1, (std::max(nq_rows, nt_rows) + rows_per_round - 1) / rows_per_round);
+        gate.rounds = S + bfm::FEED_HEAD - 1;   // the first round is delivered as FEED_HEAD short ones
+        gate.q_rows = std::max(16, (((nq_rows + S - 1) / S) + 15) & ~15);
+        gate.t_rows = std::max(16, (((nt_rows + S - 1) / S) + 15) & ~15);
+        gate.src[0] = q; gate.dst[0] = din + o_q; gate.bytes[0] = qb;
+        gate.src[1] = t; gate.dst[1] = din + o_t; gate.bytes[1] = tb;
+        if (window) {
+            gate.src[2] = o->q_xy; gate.dst[2] = din + o_qxy; gate.bytes[2] = qxy_b;
+            gate.src[3] = o->t_xy; gate.dst[3] = din + o_txy; gate.bytes[3] = txy_b;
+        }
+        gate.prog = h->d_prog;
+        CU_TRY(h, cudaMemsetAsync(h->d_prog, 0, 128, st));
+        rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
+                        nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st, &gate);
+        if (rc) {
+            cudaDeviceSynchronize();
+            h->state_clean = false;
+            return rc;
+        }
+        CU_TRY(h, cudaStreamSynchronize(st));
+        if (*h->h_status != 0) {
+            h->state_clean = false;
+            return fail(h, BFM_ERR_CUDA, "input gate timed out: the feeder CTAs did not deliver the descriptors");
+        }
+        h->info.copy_chunks = gate.rounds;
+        if (trace) std::fprintf(stderr, "[bfm trace] SM-fed upload: %d feeders, %d rounds, done %.3f ms (direct=%d)\n", gate.n_feed, gate.rounds, cpu_ms(), (int)direct);
+    } else if (G <= 1) {
         if (qb) CU_TRY(h, cudaMemcpyAsync(din + o_q, q, qb, cudaMemcpyHostToDevice, st));
         if (tb) CU_TRY(h, cudaMemcpyAsync(din + o_t, t, tb, cudaMemcpyHostToDevice, st));
         if (mask_b) CU_TRY(h, cudaMemcpyAsync(din + o_m, o->mask, mask_b, cudaMemcpyHostToDevice, st));

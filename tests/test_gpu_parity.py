@@ -538,3 +538,38 @@ def test_pinned_views_keep_their_memory_alive(eng):
         j.array[...] = -5
     for p in range(4):
         _eq(res[p], want[p], p)
+
+
+def test_sm_fed_upload_from_pinned_arrays(eng):
+    """Pinned caller arrays: the first CTAs of the matching kernel stream them into HBM themselves (no
+    copy-engine chunks).  Same bits as the copy-engine gate and as the plain single-copy path; window
+    coordinate arrays with an odd number of rows exercise the 8-byte tail."""
+    P, N = 9, 1111                                                     # odd row counts everywhere
+    qp, tp = synth.keyframe_pair_batch(P, N, seed=31)
+    rng = np.random.default_rng(5)
+    qxy = rng.uniform(0, 640, (P * N, 2)).astype(np.float32)
+    txy = (qxy + rng.normal(0, 6, (P * N, 2))).astype(np.float32)      # row i of t near row i of q
+    tab = bb.make_problems([N] * P, [N] * P)
+    pin = []
+    for a in (qp, tp, qxy, txy):
+        b = bb.PinnedBuffer(a.shape, a.dtype)
+        b.array[...] = a
+        pin.append(b)
+    pq, pt, pqxy, ptxy = (b.array for b in pin)
+    cases = [dict(k=2, ratio=0.8), dict(cross_check=True, max_distance=60), dict(k=2, ratio=0.9, window=(pqxy, ptxy, 12.0))]
+    for kw in cases:
+        results = []
+        for chunks, feeders in ((1, 0), (5, 0), (5, 3), (5, 32), (5, -1)):   # plain, SM-fed (16 / 3 / 32 feeders), copy engine
+            eng.set_tuning(pipeline_chunks=chunks, feeders=feeders)
+            out = bb.HostBatchBuffers(P * N, P, k=kw.get("k", 1), want_knn=True)
+            idx, dist, res = eng.match_batched(pq, pt, tab, want_knn=True, out=out, **kw)
+            results.append((idx.copy(), dist.copy(), res.counts.copy(), [tuple(x.copy() for x in res[p]) for p in range(P)]))
+        eng.set_tuning(pipeline_chunks=0, feeders=0)
+        for r in results[1:]:
+            assert np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1]) and np.array_equal(r[2], results[0][2])
+            for a, b in zip(r[3], results[0][3]):
+                _eq(a, b)
+        if "window" not in kw:
+            okw = {("cross_check_" if k_ == "cross_check" else k_): v for k_, v in kw.items()}
+            for p in (0, 4, 8):
+                _eq(results[1][3][p], orc.match(qp[p * N:(p + 1) * N], tp[p * N:(p + 1) * N], **okw), p)

@@ -34,14 +34,12 @@ for it in range(iters):
             q[qo:qo + n, 0] ^= rng.integers(0, 4, n).astype(np.uint8)
     tab = bb.make_problems(qn.tolist(), tn.tolist())
     mode = it % 4
-    print(f'iter {it}: P={P} mode={mode} rows q={len(q)} t={len(t)}', flush=True)
     kw = [dict(k=1, max_distance=40), dict(k=2, ratio=0.8), dict(cross_check=True), dict(k=3)][mode]
     want_knn = mode != 2
     ref = None
     runs = []
     for chunks in (1, int(rng.integers(2, 25))):
-        eng.set_tuning(pipeline_chunks=chunks)
-        print("  host pageable", chunks, flush=True)
+        eng.set_tuning(pipeline_chunks=chunks, feeders=[0, -1, int(rng.integers(1, 33))][it % 3])
         runs.append(("host pageable chunks=%d" % chunks, eng.match_batched(q, t, tab, want_knn=want_knn, **kw)))
         n_out = int(qn.sum())
         if n_out and len(q) and len(t):
@@ -49,10 +47,9 @@ for it in range(iters):
             pq.array[...] = q
             pt.array[...] = t
             ob = bb.HostBatchBuffers(n_out, P, k=kw.get("k", 1), want_knn=want_knn)
-            print("  host pinned", chunks, flush=True)
             r = eng.match_batched(pq.array, pt.array, tab, want_knn=want_knn, out=ob, **kw)
             runs.append(("host pinned chunks=%d" % chunks, r))
-    eng.set_tuning(pipeline_chunks=0)
+    eng.set_tuning(pipeline_chunks=0, feeders=0)
     if len(q) and len(t):
         runs.append(("device", eng.match_batched(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), tab, want_knn=want_knn, **kw)))
 
