@@ -104,8 +104,9 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
 
     // SM-fed upload: pinned caller arrays are streamed into HBM by the first CTAs of the matching kernel itself
     // (bfm_kernels.cuh: feed_rows) - no copy-engine operation per slice, so slices are as fine as a keyframe pair
-    const bool feed = G > 1 && h->feeders >= 0 && host_ptr_is_pinned(q) && host_ptr_is_pinned(t) &&
-                      (!window || (host_ptr_is_pinned(o->q_xy) && host_ptr_is_pinned(o->t_xy))) && o->k <= 2;
+    auto feedable = [](const void *p) { return host_ptr_is_pinned(p) && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    const bool feed = G > 1 && h->feeders >= 0 && feedable(q) && feedable(t) &&
+                      (!window || (feedable(o->q_xy) && feedable(o->t_xy))) && o->k <= 2;
     if (feed) {
         Gate gate;
         gate.status = h->h_status;
