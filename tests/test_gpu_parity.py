@@ -573,3 +573,26 @@ def test_sm_fed_upload_from_pinned_arrays(eng):
             okw = {("cross_check_" if k_ == "cross_check" else k_): v for k_, v in kw.items()}
             for p in (0, 4, 8):
                 _eq(results[1][3][p], orc.match(qp[p * N:(p + 1) * N], tp[p * N:(p + 1) * N], **okw), p)
+
+
+@pytest.mark.skipif(not ref.HAVE_CV2, reason="cv2 not importable")
+def test_maximum_train_size_against_cv2(eng):
+    """Rule R7: cv2 accepts up to 2^18 - 1 train rows; this engine up to 2^22 - 1.  At cv2's maximum the
+    results must agree (trainIdx needs 18 bits of the packed key), and the limits raise where documented."""
+    nt = (1 << 18) - 1
+    t = synth.uniform(nt, 77)
+    q = synth.uniform(48, 78)
+    q[:24] = t[np.random.default_rng(1).integers(0, nt, 24)]          # exact hits, some far into the array
+    q[0] = t[nt - 1]
+    ri, rd = ref.knn(q, t, 2)
+    idx, dist = eng.knn(q, t, 2)
+    assert np.array_equal(idx, ri) and np.array_equal(dist, rd)
+    assert idx[0, 0] == nt - 1 and dist[0, 0] == 0
+    rq, rt, rdd = ref.match(q, t, cross_check=True)
+    _eq(eng.match(q, t, cross_check=True), (rq, rt, rdd))
+    with pytest.raises(ValueError):
+        eng.knn(q, np.zeros((1 << 22, 32), np.uint8), 1)                # beyond the packed-key index range
+    big_t = np.zeros(((1 << 22) - 1, 32), np.uint8)                     # the engine's own maximum
+    big_t[-1] = 255
+    idx, dist = eng.knn(np.full((2, 32), 255, np.uint8), big_t, 2)
+    assert idx.tolist() == [[(1 << 22) - 2, 0]] * 2 and dist.tolist() == [[0, 256]] * 2
