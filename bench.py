@@ -157,13 +157,15 @@ def reference_arm(args, emit):
 
 
 # --------------------------------------------------------------------------------------------------
-def time_device_loop(torch, fn, steps, barrier):
+def time_device_loop(torch, fn, steps, barrier, finish=None):
     barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
         fn(i)
+    if finish is not None:
+        finish()   # e.g. order the timed stream after the last step's (side-stream) barrier
     e1.record()
     torch.cuda.synchronize()
     barrier()
@@ -397,7 +399,7 @@ def main():
             fused.barrier()
             return
         eng.match_batched_device(q, t, tab, k=2, ratio=RATIO, out=out)
-        if dist:
+        if dist and gather_mode != "none":   # "none": diagnostic only (no exchange: not a valid multi-GPU number)
             dist.all_gather_into_tensor(gathered_m, out["m"])
             dist.all_gather_into_tensor(gathered_c, out["count"])
 
@@ -407,9 +409,11 @@ def main():
     sampler = ClockSampler(local_rank)
     for i in range(args.warmup):
         device_step(i)
+    if fused is not None:
+        fused.wait()
     launches0 = eng.kernel_launch_count()
     sampler.start()
-    ms = time_device_loop(torch, device_step, args.steps, barrier)
+    ms = time_device_loop(torch, device_step, args.steps, barrier, finish=(fused.wait if fused is not None else None))
     clocks = sampler.stop()
     launches = eng.kernel_launch_count() - launches0
     info = eng.launch_info()
@@ -490,7 +494,8 @@ def main():
                    "ratio": RATIO, "pairs_per_step_per_gpu": pairs_per_step,
                    "l2": f"{N_SETS} rotating input sets, {N_SETS * 2 * n_out * 32 / 1e6:.0f} MB > 126 MB L2",
                    "parallelism": (f"pair-sharded x{world}, match tables gathered by the kernel epilogue over NVLink peer memory + barrier"
-                                   if fused is not None else f"pair-sharded x{world}, NCCL all_gather of match tables")
+                                   if fused is not None else f"pair-sharded x{world}, NCCL all_gather of match tables"
+                                   if gather_mode == "nccl" else f"DIAGNOSTIC: pair-sharded x{world} with NO exchange")
                    if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "launch": {k: info[k] for k in ("scan_grid", "scan_block", "queries_per_thread", "popc_mode",

@@ -82,14 +82,15 @@ class FusedGather:
     kernel (:meth:`Engine.match_batched_device` with ``replicas``) writes this rank's match lists
     into slice ``rank`` of EVERY rank's buffer from its epilogue, so when all kernels have finished
     each rank holds the full table - there is no separate collective, only :meth:`barrier`.
-    Two slots alternate between steps so a peer may still be reading step n while step n + 1 is
-    being written (one barrier per step is then sufficient).
+    Three slots rotate between steps and the barrier runs on a side stream, so barrier n overlaps the
+    kernel of step n + 1: consumers read step n between barrier n and barrier n + 1 (on the side stream or
+    after ``wait``), and the kernel of step n + 3, which reuses the slot, first waits for barrier n + 1.
 
     Per-rank table (int32): ``m[3][n_out]`` (queryIdx, trainIdx, distance), ``count[P]`` and,
     with ``want_knn``, ``knn_idx[n_out][k]`` / ``knn_dist[n_out][k]``.
     """
 
-    SLOTS = 2
+    SLOTS = 3
 
     def __init__(self, n_out: int, n_problems: int, k: int = 1, want_knn: bool = False, group=None, device=None):
         import torch
@@ -111,8 +112,12 @@ class FusedGather:
         self.hdl = symm.rendezvous(self.buf, self.group)
         self._ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.step = 0
+        self._torch = torch
+        self._side = torch.cuda.Stream(device=dev)
+        self._barrier_done = []          # event of barrier n (index n)
         torch.cuda.synchronize(dev)
         self.hdl.barrier()
+        torch.cuda.synchronize(dev)
 
     def _dest(self, base_ptr: int, slot: int) -> dict:
         b = base_ptr + 4 * (slot * self.world + self.rank) * self.table
@@ -130,15 +135,37 @@ class FusedGather:
         return own, peers
 
     def run(self, engine, q, t, problems, **kw):
-        """One sharded step: match this rank's block, results land in every rank's table."""
+        """One sharded step: match this rank's block, results land in every rank's table.  Queued on the
+        current stream; before overwriting a slot it waits for the barrier that released its last readers."""
+        n = self.step
+        if n >= self.SLOTS:
+            self._torch.cuda.current_stream().wait_event(self._barrier_done[n - self.SLOTS + 1])
         own, peers = self.destinations()
         engine.match_batched_device(q, t, problems, out=own, replicas=peers, want_knn=self.want_knn, **kw)
 
     def barrier(self):
-        """All ranks' kernels of this step have finished (and their NVLink writes with them): the
-        slot is complete on every rank.  Queued on the current stream; advances to the other slot."""
-        self.hdl.barrier()
+        """All ranks' kernels of this step have finished (and their NVLink writes with them): the slot is
+        complete on every rank once this barrier has run.  It is queued on a side stream behind this step's
+        kernel, so the next step's kernel does not wait for it; :meth:`wait` orders the current stream
+        after it.  Advances to the next slot."""
+        torch = self._torch
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ev)
+            self.hdl.barrier()
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._barrier_done.append(done)
+        if len(self._barrier_done) > 4 * self.SLOTS:       # keep indices aligned: replace old events by None
+            self._barrier_done[len(self._barrier_done) - 4 * self.SLOTS - 1] = None
         self.step += 1
+
+    def wait(self, step=None):
+        """Order the current stream after the barrier of ``step`` (default: the last one): after this,
+        :meth:`tables` of that step may be read on the current stream."""
+        step = self.step - 1 if step is None else step
+        self._torch.cuda.current_stream().wait_event(self._barrier_done[step])
 
     def tables(self, step=None):
         """Views of the gathered tables of ``step`` (default: the last completed one):

@@ -21,9 +21,10 @@
  *                       asynchronous on `stream` (a cudaStream_t passed as void*; NULL is CUDA's
  *                       legacy default stream, exactly as in the runtime API; BFM_STREAM_OWN =
  *                       the handle's own stream) and outputs are valid once it has drained.
- *       BFM_MEM_HOST    all data pointers are host pointers; the call stages through pinned
- *                       memory, runs on the handle's stream and returns after the results are
- *                       back in the caller's buffers (this is the e2e path bench.py times).
+ *       BFM_MEM_HOST    all data pointers are host pointers; the upload overlaps the ONE kernel
+ *                       launch of the call (see bfm_host_alloc below), the kernel writes results into
+ *                       pinned host memory, and the call returns after the results are in the
+ *                       caller's buffers (this is the e2e path bench.py times).
  *     The `problems` table and the options struct are always host memory.
  *   - the caller owns every input and output buffer; the handle owns only its workspace.
  *   - a handle is NOT re-entrant: one thread at a time per handle.  Different handles are
@@ -219,7 +220,8 @@ typedef struct bfm_launch_info {
     int32_t popc_mode;          /* popcount evaluation: 8 plain, 6/5/4 carry-save, 50/40 transformed carry-save */
     int32_t segments;           /* (query block, train range) work items */
     int32_t train_rows_per_segment;
-    int32_t copy_chunks;        /* BFM_MEM_HOST: input chunks the copy engine fed the kernel with (1 = no overlap) */
+    int32_t copy_chunks;        /* BFM_MEM_HOST: slices the upload was delivered in while the kernel ran - feed rounds
+                                   (pinned inputs) or copy-engine chunks (pageable inputs); 1 = no overlap */
     float scan_ms;              /* device time of the kernel of the last call when timing is on */
     float total_ms;             /* same (kept for ABI stability) */
 } bfm_launch_info_t;
@@ -240,8 +242,9 @@ int64_t bfm_kernel_launch_count(bfm_handle_t h);
  * the SM clock in MHz implied by the two. */
 int bfm_microbench(int device, int test, int iters, double *ops_per_clk_per_sm,
                    double *ops_per_s, double *sm_mhz);
-/* Pinned (page-locked) host memory for callers that want full-rate, truly asynchronous H2D/D2H
- * on the BFM_MEM_HOST path (bench.py's e2e leg stages its inputs in such buffers). */
+/* Pinned (page-locked) host memory.  On the BFM_MEM_HOST path pinned inputs are streamed into HBM by the
+ * matching kernel's own feeder CTAs and pinned outputs are written by the kernel directly (bench.py's e2e
+ * leg uses such buffers); pageable buffers work too, through copy-engine chunks and a pinned staging block. */
 int bfm_host_alloc(uint64_t bytes, void **out);
 int bfm_host_free(void *p);
 int bfm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor, int *clock_khz,

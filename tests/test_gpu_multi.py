@@ -42,11 +42,12 @@ def _worker(rank, world, port, ret):
         tab = bb.make_problems([N] * P, [N] * P)
         fg = FusedGather(P * N, P, k=2, want_knn=True)
         ok = True
-        for step in range(3):                      # three steps: both slots get reused
+        for step in range(7):                      # seven steps: every slot gets reused twice
             data = [synth.keyframe_pair_batch(P, N, seed=100 * step + r) for r in range(world)]
             q, t = data[rank]
             fg.run(eng, torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), tab, k=2, ratio=0.8)
             fg.barrier()
+            fg.wait()
             torch.cuda.synchronize()
             tb = {k: v.cpu().numpy() for k, v in fg.tables().items()}
             for r in range(world):
