@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbfm_b200.so")
+LIB_PATH = os.environ.get("BFM_LIB_PATH") or os.path.join(_HERE, "libbfm_b200.so")  # the override is for A/B builds of the kernels
 
 BFM_OK, BFM_ERR_INVALID, BFM_ERR_CUDA, BFM_ERR_NOMEM, BFM_ERR_UNSUPPORTED = range(5)
 MEM_HOST, MEM_DEVICE = 0, 1

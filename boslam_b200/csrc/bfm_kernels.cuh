@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
                 sleep_ns = min(sleep_ns * 2u, 4000u);
                 if (global_timer_ns() - t0 > 4000000000ull) {
                     ok = 0;
-                    if (lane == 0) atomicExch(p.status, 1u);
+                    if (lane == 0) *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
                     break;
                 }
             }
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
                 __nanosleep(200);
                 if (global_timer_ns() - t0 > 4000000000ull) {   // 4 s: the copies were never queued
                     ok = 0;
-                    atomicExch(p.status, 1u);
+                    *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
                     break;
                 }
             }
