@@ -123,7 +123,7 @@ struct bfm_handle_s {
     unsigned long long seq = 0;              // call sequence number (watermark epoch)
 
     // tuning knobs
-    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0;
+    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0;
     uint32_t *d_prog = nullptr;   // SM-fed upload: progress words of the feeder CTAs
     cudaEvent_t ev[2] = {nullptr, nullptr};
 
@@ -495,6 +495,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             sp.feed_bytes[a] = gate->bytes[a];
         }
         sp.feed_prog = gate->prog;
+        sp.feed_stall = h->test_stall;
     }
     sp.mask = o->mask;
     sp.mask_stride = o->mask_row_stride;
@@ -779,6 +780,8 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "feeders") {
         if (value < -1 || value > bfm::FEED_MAX) return fail(h, BFM_ERR_INVALID, "feeders must be -1 (off: copy engine), 0 (auto) or 1..32");
         h->feeders = value;
+    } else if (k == "test_stall") {   // test hook: the next SM-fed call's feeders deliver nothing (gate time-out path)
+        h->test_stall = value != 0;
     } else if (k == "feed_rows") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "feed_rows must be >= 0");
         h->feed_rows = value;

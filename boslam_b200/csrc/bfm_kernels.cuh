@@ -79,6 +79,7 @@ struct ScanParams {
     uint4 *feed_dst[4];                      // device copies
     unsigned long long feed_bytes[4];        // total bytes of each array
     uint32_t *feed_prog;                     // [FEED_MAX] rounds completed per feeder CTA (zeroed before the launch)
+    int32_t feed_stall;                      // test hook: feeders deliver nothing, so the gate's time-out path runs
     const int32_t *t_limit;          // optional device scalar: train rows that exist (single problem), else NULL
     const uint8_t *mask;             // dense mask (single problem): [q_local][mask_stride]
     long long mask_stride;
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     __shared__ int s_flag;
 
     if ((int)blockIdx.x < p.n_feed) {   // the first CTAs of the grid feed the others (SM-fed upload)
-        feed_rows<NT>(p);
+        if (!p.feed_stall) feed_rows<NT>(p);
         return;
     }
     const Segment sg = p.segs[blockIdx.x - p.n_feed];

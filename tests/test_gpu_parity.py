@@ -596,3 +596,26 @@ def test_maximum_train_size_against_cv2(eng):
     big_t[-1] = 255
     idx, dist = eng.knn(np.full((2, 32), 255, np.uint8), big_t, 2)
     assert idx.tolist() == [[(1 << 22) - 2, 0]] * 2 and dist.tolist() == [[0, 256]] * 2
+
+
+def test_input_gate_times_out_instead_of_hanging(eng):
+    """If the upload never arrives the waiting CTAs give up after 4 s, the call fails with a clear error and the
+    engine stays usable (the workspace is re-initialised on the next call)."""
+    P, N = 6, 600
+    qp, tp = synth.keyframe_pair_batch(P, N, seed=41)
+    tab = bb.make_problems([N] * P, [N] * P)
+    pq, pt = bb.PinnedBuffer(qp.shape), bb.PinnedBuffer(tp.shape)
+    pq.array[...] = qp
+    pt.array[...] = tp
+    eng.set_tuning(pipeline_chunks=4, test_stall=1)
+    try:
+        with pytest.raises(bb.BfmError) as ei:
+            eng.match_batched(pq.array, pt.array, tab, k=2, ratio=0.8)
+        assert "timed out" in str(ei.value)
+    finally:
+        eng.set_tuning(pipeline_chunks=0, test_stall=0)
+    res = eng.match_batched(pq.array, pt.array, tab, k=2, ratio=0.8)
+    for p in range(P):
+        _eq(res[p], orc.match(qp[p * N:(p + 1) * N], tp[p * N:(p + 1) * N], k=2, ratio=0.8), p)
+    q, t, _ = synth.correlated(300, 500, 42)
+    _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t))
