@@ -457,9 +457,6 @@ class Engine:
         if k > _ffi.MAX_K:
             raise NotImplementedError(f"k > {_ffi.MAX_K} is not supported by this build")
         opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
-        if none_pass:
-            opts.max_distance = 0
-            opts.ratio = -1.0
         keep = []
         if window is not None:
             self._mask_args_torch(opts, None, window, q.shape[0], t.shape[0], keep)
@@ -482,11 +479,15 @@ class Engine:
                                                            pp, P, n_out, ctypes.byref(opts), dests, len(dests),
                                                            self._stream())
                     _ffi.check(self._h, rc)
-                return out
-            m = out["m"]
-            self._call(_ffi.MEM_DEVICE, q.data_ptr(), q.shape[0], t.data_ptr(), t.shape[0], probs, n_out, opts,
-                       (out["knn_idx"].data_ptr(), out["knn_dist"].data_ptr()) if want_knn else None,
-                       (m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(), out["count"].data_ptr()), self._stream())
+            else:
+                m = out["m"]
+                self._call(_ffi.MEM_DEVICE, q.data_ptr(), q.shape[0], t.data_ptr(), t.shape[0], probs, n_out, opts,
+                           (out["knn_idx"].data_ptr(), out["knn_dist"].data_ptr()) if want_knn else None,
+                           (m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(), out["count"].data_ptr()), self._stream())
+            if none_pass:   # a gate nothing can pass (e.g. distance < 0): no matches, on the same stream
+                for o in [out] + list(replicas or []):
+                    if not isinstance(o["count"], int):
+                        o["count"].zero_()
         return out
 
     @staticmethod

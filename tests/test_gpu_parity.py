@@ -222,6 +222,10 @@ def test_device_tensor_path(eng):
     assert np.array_equal(idx.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
     got = eng.match(qd, td, cross_check=True, max_distance=30)
     _eq([g.cpu().numpy() for g in got], orc.match(q, t, cross_check_=True, max_distance=30))
+    tab = bb.make_problems([800], [800])                             # a gate nothing can pass (d < 0), device form
+    assert int(eng.match_batched_device(qd, qd, tab, max_distance=0, strict=True)["count"][0]) == 0
+    assert len(eng.match(qd, qd, max_distance=0, strict=True)[0]) == 0
+    assert int(eng.match_batched_device(qd, qd, tab, max_distance=0)["count"][0]) == 800   # d <= 0: the self matches
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):                                       # honours torch's current stream
         idx2, dist2 = eng.knn(qd, td, 2)
