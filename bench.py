@@ -493,7 +493,8 @@ def main():
         "config": {"workload": "loop_closing", "pairs_per_gpu": N_PAIRS, "desc_per_keyframe": N_DESC, "k": 2,
                    "ratio": RATIO, "pairs_per_step_per_gpu": pairs_per_step,
                    "l2": f"{N_SETS} rotating input sets, {N_SETS * 2 * n_out * 32 / 1e6:.0f} MB > 126 MB L2",
-                   "parallelism": (f"pair-sharded x{world}, match tables gathered by the kernel epilogue over NVLink peer memory + barrier"
+                   "parallelism": (f"pair-sharded x{world}, match tables gathered by the kernel epilogue over NVLink "
+                                   f"({'NVSwitch multicast stores' if fused.multicast_ptr else 'peer stores'}) + overlapped barrier"
                                    if fused is not None else f"pair-sharded x{world}, NCCL all_gather of match tables"
                                    if gather_mode == "nccl" else f"DIAGNOSTIC: pair-sharded x{world} with NO exchange")
                    if world > 1 else "single GPU"},

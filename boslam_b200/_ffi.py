@@ -18,7 +18,7 @@ MASK_NONE, MASK_DENSE, MASK_WINDOW = 0, 1, 2
 MAX_TRAIN_ROWS = 1 << 22
 MAX_QUERY_ROWS = 1 << 22
 MAX_K = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/bfm.h declares; tests/test_abi.py checks the library exports all of them
 EXPORTED_SYMBOLS = (
@@ -49,7 +49,8 @@ class Options(ctypes.Structure):
 
 class Outputs(ctypes.Structure):
     _fields_ = [("knn_idx", ctypes.c_void_p), ("knn_dist", ctypes.c_void_p), ("m_query", ctypes.c_void_p),
-                ("m_train", ctypes.c_void_p), ("m_dist", ctypes.c_void_p), ("m_count", ctypes.c_void_p)]
+                ("m_train", ctypes.c_void_p), ("m_dist", ctypes.c_void_p), ("m_count", ctypes.c_void_p),
+                ("multicast", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class TrackParams(ctypes.Structure):

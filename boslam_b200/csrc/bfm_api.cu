@@ -521,6 +521,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         sp.dest[d].m_train = dests[d].m_train;
         sp.dest[d].m_dist = dests[d].m_dist;
         sp.dest[d].m_count = dests[d].m_count;
+        if (dests[d].multicast) sp.dest_multicast |= 1u << d;
     }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], st));
     if (binned) {
@@ -717,7 +718,7 @@ int bfm_match_batched(bfm_handle_t h, int mem, const uint8_t *q, int32_t n_query
     h->err.clear();
     int rc = check_call(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts);
     if (rc) return rc;
-    const bfm_outputs_t out = {knn_idx, knn_dist, m_query, m_train, m_dist, m_count};
+    const bfm_outputs_t out = {knn_idx, knn_dist, m_query, m_train, m_dist, m_count, 0, 0};
     if (mem == BFM_MEM_DEVICE)
         return run_device(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, &out, 1,
                           stream == BFM_STREAM_OWN ? h->stream : static_cast<cudaStream_t>(stream));

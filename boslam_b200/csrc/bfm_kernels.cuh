@@ -108,6 +108,7 @@ struct ScanParams {
     // written over PCIe on the host path); dest[1..] are the same buffers of NVLink peers
     // (multi-GPU gather fused into the epilogue).  Each pointer may be NULL.
     int32_t n_dest;
+    uint32_t dest_multicast;   // bit d set: dest[d] holds NVSwitch multicast addresses (one multimem.st reaches every GPU)
     struct Dest {
         int32_t *knn_idx, *knn_dist;                 // [out rows][k]
         int32_t *m_query, *m_train, *m_dist;         // [out rows]
@@ -247,6 +248,14 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t (&q)[8], const uin
     }
 }
 
+// A result store.  Ordinary destinations take a plain store; a multicast destination (an address of an
+// NVSwitch multicast object spanning the symmetric buffers of all ranks) takes multimem.st, which the switch
+// replicates into every GPU's copy: one store instead of one per peer.
+__device__ __forceinline__ void put_i32(int32_t *p, int v, bool multicast) {
+    if (multicast) asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    else *p = v;
+}
+
 // ---- finalize: decode keys, cross-check / ratio / distance gate, ordered compaction -----------------
 // Run by ONE CTA per problem: the one whose segment completed the problem (last-arriver pattern,
 // see the kernel tail).  Decodes the packed keys into the dense cv2 knnMatch table, applies
@@ -304,13 +313,14 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
                 for (int d = 0; d < p.n_dest; ++d) {
                     int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
                     if (!ki) continue;
-                    if (k == 2) {   // 8-byte aligned: o is even
+                    const bool mc = (p.dest_multicast >> d) & 1u;
+                    if (k == 2 && !mc) {   // 8-byte aligned: o is even
                         *reinterpret_cast<int2 *>(ki + o) = make_int2(idx1[j], idx2);
                         *reinterpret_cast<int2 *>(kd + o) = make_int2(d1[j], d2);
                     } else {
-                        ki[o] = idx1[j];
-                        kd[o] = d1[j];
-                        if (p.knn_cols > 1) { ki[o + 1] = idx2; kd[o + 1] = d2; }
+                        put_i32(ki + o, idx1[j], mc);
+                        put_i32(kd + o, d1[j], mc);
+                        if (p.knn_cols > 1) { put_i32(ki + o + 1, idx2, mc); put_i32(kd + o + 1, d2, mc); }
                     }
                 }
                 if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
@@ -354,9 +364,10 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
                 const int i = base + j * NT + tid;
                 for (int d = 0; d < p.n_dest; ++d) {
                     if (!p.dest[d].m_count) continue;
-                    p.dest[d].m_query[o] = i;
-                    p.dest[d].m_train[o] = idx1[j];
-                    p.dest[d].m_dist[o] = d1[j];
+                    const bool mc = (p.dest_multicast >> d) & 1u;
+                    put_i32(p.dest[d].m_query + o, i, mc);
+                    put_i32(p.dest[d].m_train + o, idx1[j], mc);
+                    put_i32(p.dest[d].m_dist + o, d1[j], mc);
                 }
             }
         }
@@ -365,7 +376,7 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
     }
     if (tid == 0)
         for (int d = 0; d < p.n_dest; ++d)
-            if (p.dest[d].m_count) p.dest[d].m_count[pi] = running;
+            if (p.dest[d].m_count) put_i32(p.dest[d].m_count + pi, running, (p.dest_multicast >> d) & 1u);
     if (p.cross_check) {
         // every column-key read of this problem happened above, in this CTA
         for (int j = tid; j < pr.t_count; j += NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
@@ -785,9 +796,10 @@ __global__ void __launch_bounds__(FT_NT) fin_count_kernel(const __grid_constant_
         for (int d = 0; d < p.n_dest; ++d) {
             int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
             if (!ki) continue;
-            ki[o] = idx1;
-            kd[o] = d1;
-            if (p.knn_cols > 1) { ki[o + 1] = idx2; kd[o + 1] = d2; }
+            const bool mc = (p.dest_multicast >> d) & 1u;
+            put_i32(ki + o, idx1, mc);
+            put_i32(kd + o, d1, mc);
+            if (p.knn_cols > 1) { put_i32(ki + o + 1, idx2, mc); put_i32(kd + o + 1, d2, mc); }
         }
         if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
         bool kp = has1;
@@ -854,15 +866,16 @@ __global__ void __launch_bounds__(FT_NT) fin_write_kernel(const __grid_constant_
             const int i = blockIdx.x * FT_ROWS + j * FT_NT + tid;
             for (int d = 0; d < p.n_dest; ++d) {
                 if (!p.dest[d].m_count) continue;
-                p.dest[d].m_query[o] = i;
-                p.dest[d].m_train[o] = (int)(k1 & IDX_MASK);
-                p.dest[d].m_dist[o] = (int)(k1 >> DIST_SHIFT);
+                const bool mc = (p.dest_multicast >> d) & 1u;
+                put_i32(p.dest[d].m_query + o, i, mc);
+                put_i32(p.dest[d].m_train + o, (int)(k1 & IDX_MASK), mc);
+                put_i32(p.dest[d].m_dist + o, (int)(k1 >> DIST_SHIFT), mc);
             }
         }
     }
     if (blockIdx.x == gridDim.x - 1 && tid == 0)
         for (int d = 0; d < p.n_dest; ++d)
-            if (p.dest[d].m_count) p.dest[d].m_count[0] = before + tile_total;
+            if (p.dest[d].m_count) put_i32(p.dest[d].m_count, before + tile_total, (p.dest_multicast >> d) & 1u);
     if (p.cross_check)   // every column-key read happened in fin_count; all tiles share the reset
         for (int j = blockIdx.x * FT_NT + tid; j < pr.t_count; j += gridDim.x * FT_NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
 }

@@ -237,8 +237,8 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
         // all n_edges rows and every work item clamps its range on the device (no host round trip).
         // Two destinations: a device copy (the gather below reads it) and the pinned host block.
         const bfm_problem_t pr = {0, nq, 0, n_edges, 0, 0};
-        const bfm_outputs_t outs[2] = {{nullptr, nullptr, d_m, d_m + nqa, d_m + 2 * (size_t)nqa, d_hdr + 1},
-                                       {nullptr, nullptr, h_m, h_m + nqa, h_m + 2 * (size_t)nqa, h_hdr + 1}};
+        const bfm_outputs_t outs[2] = {{nullptr, nullptr, d_m, d_m + nqa, d_m + 2 * (size_t)nqa, d_hdr + 1, 0, 0},
+                                       {nullptr, nullptr, h_m, h_m + nqa, h_m + 2 * (size_t)nqa, h_hdr + 1, 0, 0}};
         rc = run_device(h, d_q, nq, reinterpret_cast<const uint8_t *>(d_tdesc), n_edges, &pr, 1, nq, &od, outs, 2, st, nullptr, d_hdr);
         if (rc) return rc;
         kernels += h->info.kernels_launched;

@@ -111,6 +111,10 @@ class FusedGather:
         self.buf.fill_(-1)
         self.hdl = symm.rendezvous(self.buf, self.group)
         self._ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        # NVSwitch multicast (NVLS): one multimem.st from the kernel epilogue lands in every rank's buffer
+        import os
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self.multicast_ptr = mc if (mc and os.environ.get("BFM_MULTICAST", "1") != "0") else 0
         self.step = 0
         self._torch = torch
         self._side = torch.cuda.Stream(device=dev)
@@ -119,10 +123,10 @@ class FusedGather:
         self.hdl.barrier()
         torch.cuda.synchronize(dev)
 
-    def _dest(self, base_ptr: int, slot: int) -> dict:
+    def _dest(self, base_ptr: int, slot: int, multicast: bool = False) -> dict:
         b = base_ptr + 4 * (slot * self.world + self.rank) * self.table
         d = {"m_query": b + 4 * self._o_m, "m_train": b + 4 * (self._o_m + self.n_out),
-             "m_dist": b + 4 * (self._o_m + 2 * self.n_out), "count": b + 4 * self._o_c}
+             "m_dist": b + 4 * (self._o_m + 2 * self.n_out), "count": b + 4 * self._o_c, "multicast": multicast}
         if self.want_knn:
             d["knn_idx"], d["knn_dist"] = b + 4 * self._o_ki, b + 4 * self._o_kd
         return d
@@ -130,6 +134,8 @@ class FusedGather:
     def destinations(self):
         """(own, peers) destination dicts of raw device pointers for the current step's slot."""
         slot = self.step % self.SLOTS
+        if self.multicast_ptr:
+            return self._dest(self.multicast_ptr, slot, multicast=True), []
         own = self._dest(self._ptrs[self.rank], slot)
         peers = [self._dest(self._ptrs[r], slot) for r in range(self.world) if r != self.rank]
         return own, peers

@@ -501,6 +501,7 @@ class Engine:
         else:
             d.m_query, d.m_train, d.m_dist = ptr(o["m_query"]), ptr(o["m_train"]), ptr(o["m_dist"])
         d.m_count = ptr(o["count"])
+        d.multicast = 1 if o.get("multicast") else 0
         if want_knn:
             d.knn_idx, d.knn_dist = ptr(o["knn_idx"]), ptr(o["knn_dist"])
 

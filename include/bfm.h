@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define BFM_ABI_VERSION 3
+#define BFM_ABI_VERSION 4
 #define BFM_DESC_BYTES 32
 /* per-problem limits of the packed (distance, index) keys the kernels reduce over;
  * cv2 itself refuses train sets of 2^18 rows or more (matchers.cpp:860, rule R7). */
@@ -141,6 +141,10 @@ typedef struct bfm_outputs {
     int32_t *knn_idx, *knn_dist;             /* int32[n_out_rows][k], both or neither */
     int32_t *m_query, *m_train, *m_dist;     /* int32[n_out_rows] */
     int32_t *m_count;                        /* int32[n_problems]; NULL skips the match list */
+    int32_t multicast;                       /* 1: the pointers are addresses of an NVSwitch multicast object (NVLS)
+                                                spanning every rank's buffer; results are written with multimem.st,
+                                                one store reaching all GPUs */
+    int32_t reserved;
 } bfm_outputs_t;
 
 int bfm_match_batched_multi(bfm_handle_t h,

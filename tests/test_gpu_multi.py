@@ -25,7 +25,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, multicast="1"):
+    os.environ["BFM_MULTICAST"] = multicast
     import torch
     import torch.distributed as dist
     import boslam_b200 as bb
@@ -68,13 +69,14 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-def test_fused_gather_two_gpus():
+@pytest.mark.parametrize("multicast", ["1", "0"])     # NVSwitch multicast stores (where available) / per-peer stores
+def test_fused_gather_two_gpus(multicast):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     mgr = ctx.Manager()
     ret = mgr.dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, multicast)) for r in range(2)]
     [p.start() for p in procs]
     [p.join(300) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
