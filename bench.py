@@ -423,6 +423,28 @@ def main():
         ms = float(tms.item())
     value = pairs_per_step * world * args.steps / (ms * 1e-3)
 
+    # the fused gather must have delivered every rank's table to every rank: compare this rank's view of all
+    # per-problem match counts and index checksums with what each rank computed locally (exchanged over NCCL)
+    gather_verified = None
+    if fused is not None:
+        device_step(0)
+        fused.wait()
+        torch.cuda.synchronize()
+        tb = fused.tables()
+        mine_c = tb["count"][rank].clone()
+        mine_s = torch.stack([tb["m"][rank, j].to(torch.int64).sum() for j in range(3)])
+        all_c = torch.empty((world, N_PAIRS), dtype=torch.int32, device=dev)
+        all_s = torch.empty((world, 3), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_c, mine_c)
+        dist.all_gather_into_tensor(all_s, mine_s)
+        view_s = torch.stack([torch.stack([tb["m"][r, j].to(torch.int64).sum() for j in range(3)]) for r in range(world)])
+        ok = torch.equal(all_c, tb["count"]) and torch.equal(all_s, view_s) and bool((all_c.sum(dim=1) > 0).all())
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_verified = bool(flag.item())
+        if not gather_verified:
+            raise SystemExit("fused gather verification failed: the ranks do not hold identical tables")
+
     # -- roofline pass: per-launch scan-kernel time from CUDA events on the launching stream --
     eng.set_tuning(timing=1)
     scan_ms = []
@@ -503,6 +525,8 @@ def main():
                                         "train_rows_per_segment")},
         "frames_per_s": N_PAIRS * world * args.steps / (ms * 1e-3),
     }
+    if gather_verified is not None:
+        line["gather_verified"] = gather_verified
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cv2_reference as ref
