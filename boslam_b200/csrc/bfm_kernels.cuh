@@ -14,7 +14,13 @@
 // the CTA streams a range of train descriptors through shared memory in 4 KB chunks that a
 // single thread fetches with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double buffered),
 // and every lane reads the same train words (LDS.128 broadcast, conflict free).  HBM traffic is
-// ~1e-2 bytes per pair; the bound is the POPC issue rate.
+// ~4e-2 bytes per pair; the bound is the POPC issue rate.
+//
+// One launch does everything: the CTA that completes a problem's last work item finalizes it
+// (finalize_problem: knn table, cross-check / ratio / gate, ordered match list, workspace reset) and
+// writes the results to up to eight destinations - device memory, pinned host memory, NVLink peers or an
+// NVSwitch multicast address.  On the host path the first CTAs of the same grid stream the caller's pinned
+// arrays into HBM (feed_rows) while the others wait at an input gate for the rows they read.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -449,10 +455,12 @@ __device__ __noinline__ void feed_rows(const ScanParams &p) {
 // MASK  0 none, 1 dense uint8 mask, 2 projection window
 // PM    popcount evaluation (see hamming256)
 // NT    threads per CTA (== TT: one thread transforms one staged train row)
+// BOUND only admit keys above a per-row lower bound (passes 2.. of knnMatch with k > 2; R == 1)
 //
 // Pipeline per CTA: chunk c+2 is fetched by TMA while chunk c is scanned; one __syncthreads per
 // chunk.  Shared memory: 2 x 4 KB train rows, 2 x 1 KB pixel coords (window), 2 x 2 KB column
-// keys (cross-check).
+// keys (cross-check).  Roles inside one grid: CTAs [0, n_feed) are feeders (host path with pinned
+// inputs), the rest take work item blockIdx.x - n_feed.
 template <int R, int K, bool CROSS, int MASK, int PM, int NT, bool BOUND = false>
 __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const __grid_constant__ ScanParams p) {
     static_assert(!BOUND || R == 1, "the lower-bound variant (k > 2 passes) uses the plain 32-bit key path");
