@@ -623,3 +623,39 @@ def test_input_gate_times_out_instead_of_hanging(eng):
         _eq(res[p], orc.match(qp[p * N:(p + 1) * N], tp[p * N:(p + 1) * N], k=2, ratio=0.8), p)
     q, t, _ = synth.correlated(300, 500, 42)
     _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t))
+
+
+def test_two_threads_run_gated_batches_concurrently():
+    """Tracking thread + local-mapping thread (slam/main.py:37-47), each with its own engine, both on the host
+    path with the SM-fed upload: two gated kernels share the GPU without starving each other's feeders."""
+    import threading
+    P, N = 12, 900
+    jobs = []
+    for s in range(2):
+        qp, tp = synth.keyframe_pair_batch(P, N, seed=50 + s)
+        want = [orc.match(qp[p * N:(p + 1) * N], tp[p * N:(p + 1) * N], k=2, ratio=0.8) for p in (0, 5, 11)]
+        jobs.append((qp, tp, want))
+    tab = bb.make_problems([N] * P, [N] * P)
+    errs = []
+
+    def work(job):
+        try:
+            qp, tp, want = job
+            eng = bb.Engine(0)
+            eng.set_tuning(pipeline_chunks=6)
+            pq, pt = bb.PinnedBuffer(qp.shape), bb.PinnedBuffer(tp.shape)
+            pq.array[...] = qp
+            pt.array[...] = tp
+            out = bb.HostBatchBuffers(P * N, P, k=2)
+            for _ in range(25):
+                res = eng.match_batched(pq.array, pt.array, tab, k=2, ratio=0.8, out=out)
+                for w, p in zip(want, (0, 5, 11)):
+                    _eq(res[p], w, p)
+            eng.close()
+        except Exception as e:  # pragma: no cover
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(j,)) for j in jobs]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
