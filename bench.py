@@ -229,6 +229,19 @@ def extras(eng, torch, steps):
         lambda: eng.match_batched(qb, tb, tab3, k=2, ratio=RATIO),
         lambda: eng.match_batched_device(qbd, tbd, tab3, k=2, ratio=RATIO),
         1, 20 * 2000 * 2000, reps)
+    # the headline batch from ordinary (pageable) numpy arrays into ordinary numpy arrays: what a caller who knows
+    # nothing about pinned memory gets (worker threads stage the arrays for the kernel's feeder CTAs)
+    qpg, tpg = synth.keyframe_pair_batch(N_PAIRS, N_DESC, seed=16)
+    tabp = make_problems([N_DESC] * N_PAIRS, [N_DESC] * N_PAIRS)
+    for _ in range(3):
+        eng.match_batched(qpg, tpg, tabp, k=2, ratio=RATIO)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        eng.match_batched(qpg, tpg, tabp, k=2, ratio=RATIO)
+    dtp = (time.perf_counter() - t0) / 10
+    out["loop_closing_256x2000x2000_pageable_numpy"] = {"ms_e2e": dtp * 1e3, "pairs_per_s_e2e": N_PAIRS * N_DESC * N_DESC / dtp,
+                                                        "note": "pageable numpy in -> freshly allocated numpy out"}
+
     # configs[0] in full (experiments/pnp_one_way_tracking.py:30-41): crossCheck match of two RGB-D frames, then
     # cv2.solvePnPRansac on the matched (3-D, 2-D) pairs.  PnP stays on the host CPU in both arms (north star).
     try:
@@ -546,6 +559,18 @@ def main():
                                               f"ratio test incl. DMatch construction, os.cpu_count()={os.cpu_count()}",
                                     "ms_per_step": dt * 1e3, "matches": int(n_good)}
             assert n_good == int(eng.match_batched(q, t, tab, k=2, ratio=RATIO).counts.sum()), "cv2 and engine disagree"
+            try:  # also a 1-thread figure (8 of the 256 pairs)
+                import cv2
+                nthreads = cv2.getNumThreads()
+                cv2.setNumThreads(1)
+                cv2_step(m, q, t, tab[:2], RATIO)
+                t0 = time.perf_counter()
+                cv2_step(m, q, t, tab[:8], RATIO)
+                dt1 = time.perf_counter() - t0
+                cv2.setNumThreads(nthreads)
+                line["cpu_baseline"]["value_1_thread"] = 8 * N_DESC * N_DESC / dt1
+            except Exception:
+                pass
         else:
             from oracle import c_oracle
             t0 = time.perf_counter()

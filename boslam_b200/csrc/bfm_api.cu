@@ -8,6 +8,7 @@
 // bfm_create fails and says so.
 #include "bfm_kernels.cuh"
 #include "../../include/bfm.h"
+#include "bfm_workers.h"
 
 #include <algorithm>
 #include <chrono>
@@ -15,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -125,6 +127,12 @@ struct bfm_handle_s {
     // tuning knobs
     int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0;
     uint32_t *d_prog = nullptr;   // SM-fed upload: progress words of the feeder CTAs
+    // pageable caller arrays: host threads stage them into pinned memory slice by slice for the feeders
+    std::unique_ptr<WorkerPool> pool;
+    void *h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    uint32_t *h_ready = nullptr;  // pinned: staged rounds published by the host (read by the feeder CTAs)
+    int host_threads = 0;         // tuning: 0 auto, -1 off
     cudaEvent_t ev[2] = {nullptr, nullptr};
 
     bfm_launch_info_t info{};
@@ -301,6 +309,7 @@ struct Gate {
     void *dst[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t bytes[4] = {0, 0, 0, 0};
     uint32_t *prog = nullptr;
+    const uint32_t *host_ready = nullptr;   // pinned word: rounds the host has staged so far (NULL: all staged)
 };
 
 // The device path: every data pointer is device-visible, work is queued on `st`.  ONE kernel launch.
@@ -496,6 +505,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         }
         sp.feed_prog = gate->prog;
         sp.feed_stall = h->test_stall;
+        sp.feed_host_ready = gate->host_ready;
     }
     sp.mask = o->mask;
     sp.mask_stride = o->mask_row_stride;
@@ -658,7 +668,7 @@ int bfm_create(int device, bfm_handle_t *out) {
     ok = ok && cudaMalloc(&h->d_prog, 256) == cudaSuccess && cudaMemset(h->d_prog, 0, 256) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_ready, 256) == cudaSuccess && cudaMemset(h->d_ready, 0, 256) == cudaSuccess &&
          cudaMallocHost(&h->h_marks, sizeof(unsigned long long) * 2 * MAX_COPY_CHUNKS) == cudaSuccess &&
-         cudaMallocHost(&h->h_status, 64) == cudaSuccess;
+         cudaMallocHost(&h->h_status, 64) == cudaSuccess && cudaMallocHost(&h->h_ready, 64) == cudaSuccess;
     if (ok) *h->h_status = 0;
     for (int i = 0; ok && i < N_TABLE_SLOTS; ++i) {
         ok = cudaEventCreateWithFlags(&h->table_ev[i], cudaEventDisableTiming) == cudaSuccess;
@@ -683,6 +693,9 @@ int bfm_destroy(bfm_handle_t h) {
     if (h->d_prog) cudaFree(h->d_prog);
     if (h->h_marks) cudaFreeHost(h->h_marks);
     if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_ready) cudaFreeHost(h->h_ready);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    h->pool.reset();
     for (int i = 0; i < N_TABLE_SLOTS; ++i) {
         if (h->h_tables[i]) cudaFreeHost(h->h_tables[i]);
         if (h->table_ev[i]) cudaEventDestroy(h->table_ev[i]);
@@ -781,6 +794,10 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "feeders") {
         if (value < -1 || value > bfm::FEED_MAX) return fail(h, BFM_ERR_INVALID, "feeders must be -1 (off: copy engine), 0 (auto) or 1..32");
         h->feeders = value;
+    } else if (k == "host_threads") {
+        if (value < -1 || value > 64) return fail(h, BFM_ERR_INVALID, "host_threads must be -1 (off), 0 (auto) or 1..64");
+        if (value != h->host_threads) h->pool.reset();
+        h->host_threads = value;
     } else if (k == "test_stall") {   // test hook: the next SM-fed call's feeders deliver nothing (gate time-out path)
         h->test_stall = value != 0;
     } else if (k == "feed_rows") {

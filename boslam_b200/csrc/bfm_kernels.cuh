@@ -86,6 +86,8 @@ struct ScanParams {
     unsigned long long feed_bytes[4];        // total bytes of each array
     uint32_t *feed_prog;                     // [FEED_MAX] rounds completed per feeder CTA (zeroed before the launch)
     int32_t feed_stall;                      // test hook: feeders deliver nothing, so the gate's time-out path runs
+    const uint32_t *feed_host_ready;         // pinned host word: rounds staged by the host's worker threads so far
+                                             // (pageable caller arrays); NULL = the sources are complete
     const int32_t *t_limit;          // optional device scalar: train rows that exist (single problem), else NULL
     const uint8_t *mask;             // dense mask (single problem): [q_local][mask_stride]
     long long mask_stride;
@@ -399,7 +401,26 @@ __device__ __noinline__ void feed_rows(const ScanParams &p) {
     const int feeder = blockIdx.x, tid = threadIdx.x;
     const unsigned long long stride = (unsigned long long)p.n_feed * NT;       // 16-byte words per sweep
     const unsigned long long me = (unsigned long long)feeder * NT + tid;
+    __shared__ int s_go;
+    uint32_t staged = 0;   // rounds the host is known to have staged
     for (int r = 0; r < p.feed_rounds; ++r) {
+        if (p.feed_host_ready != nullptr && (uint32_t)r >= staged) {
+            // the host is still staging: wait for round r.  A poll is a PCIe read that queues behind the bulk
+            // loads of every feeder, so the value is remembered and polled again only when it runs out.
+            if (tid == 0) {
+                const unsigned long long t0 = global_timer_ns();
+                uint32_t v;
+                while ((v = *(volatile const uint32_t *)p.feed_host_ready) < (uint32_t)(r + 1)) {
+                    __nanosleep(500);
+                    if (global_timer_ns() - t0 > 4000000000ull) { v = 0; break; }
+                }
+                s_go = (int)v;
+            }
+            __syncthreads();
+            staged = (uint32_t)s_go;
+            __syncthreads();
+            if (staged == 0) return;   // timed out: the waiting CTAs time out on their own and report it
+        }
         // pairs of arrays (descriptors, then pixel coordinates): the loads of both are in flight together
 #pragma unroll
         for (int pair = 0; pair < 2; ++pair) {

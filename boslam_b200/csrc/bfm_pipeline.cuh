@@ -21,6 +21,12 @@
 // Small calls (a frame against a keyframe or the local map) use one copy on the compute stream and no gate.
 // BFM_TRACE=1 in the environment prints the per-call timeline.
 
+void ensure_pool(bfm_handle_t h) {
+    if (h->pool || h->host_threads < 0) return;
+    const int n = h->host_threads > 0 ? h->host_threads : (int)std::thread::hardware_concurrency() / 2;
+    h->pool.reset(new WorkerPool(std::min(std::max(n, 2), 8) - 1));   // the calling thread works too
+}
+
 bool host_ptr_is_pinned(const void *p) {
     if (!p) return false;
     cudaPointerAttributes a;
@@ -139,6 +145,100 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         }
         h->info.copy_chunks = gate.rounds;
         if (trace) std::fprintf(stderr, "[bfm trace] SM-fed upload: %d feeders, %d rounds, done %.3f ms (direct=%d)\n", gate.n_feed, gate.rounds, cpu_ms(), (int)direct);
+    } else if (G > 1 && h->feeders >= 0 && h->host_threads >= 0 && o->k <= 2) {
+        // Pageable caller arrays: worker threads stage them into pinned memory round by round while the kernel
+        // is already running; its feeder CTAs wait for the host's "rounds staged" word before each round.
+        ensure_pool(h);
+        if (h->h_stage_cap < in_total) {
+            if (h->h_stage) CU_TRY(h, cudaFreeHost(h->h_stage));
+            h->h_stage = nullptr;
+            h->h_stage_cap = 0;
+            CU_TRY(h, cudaMallocHost(&h->h_stage, in_total + in_total / 4 + 4096));
+            h->h_stage_cap = in_total + in_total / 4 + 4096;
+        }
+        char *stage = static_cast<char *>(h->h_stage);
+        Gate gate;
+        gate.status = h->h_status;
+        *h->h_status = 0;
+        gate.n_feed = h->feeders > 0 ? h->feeders : 24;
+        const int rows_per_round = h->feed_rows > 0 ? h->feed_rows : 8192;
+        const int S = std::max(1, (std::max(nq_rows, nt_rows) + rows_per_round - 1) / rows_per_round);
+        gate.rounds = S + bfm::FEED_HEAD - 1;
+        gate.q_rows = std::max(16, (((nq_rows + S - 1) / S) + 15) & ~15);
+        gate.t_rows = std::max(16, (((nt_rows + S - 1) / S) + 15) & ~15);
+        const void *user[4] = {q, t, window ? (const void *)o->q_xy : nullptr, window ? (const void *)o->t_xy : nullptr};
+        const size_t offs[4] = {o_q, o_t, o_qxy, o_txy}, bytes[4] = {qb, tb, qxy_b, txy_b};
+        for (int a = 0; a < 4; ++a) {
+            if (!user[a] || !bytes[a]) continue;
+            gate.src[a] = stage + offs[a];
+            gate.dst[a] = din + offs[a];
+            gate.bytes[a] = bytes[a];
+        }
+        gate.prog = h->d_prog;
+        gate.host_ready = h->h_ready;
+        *h->h_ready = 0;
+        // jobs: one memcpy per (round, array); the byte ranges are exactly the feeders' (feed_rows)
+        const int rounds = gate.rounds;
+        struct Shared {
+            std::vector<std::atomic<int>> left;
+            std::mutex adv;
+            int next = 0;
+            explicit Shared(int n) : left(n) {}
+        };
+        auto sh = std::make_shared<Shared>(rounds);
+        volatile uint32_t *ready = h->h_ready;
+        auto advance = [sh, ready, rounds]() {
+            std::lock_guard<std::mutex> lk(sh->adv);
+            while (sh->next < rounds && sh->left[sh->next].load(std::memory_order_acquire) == 0) ++sh->next;
+            std::atomic_thread_fence(std::memory_order_release);
+            *ready = (uint32_t)sh->next;
+        };
+        struct Job { int r; char *dst; const char *src; size_t n; };
+        std::vector<Job> jobs;
+        for (int r = 0; r < rounds; ++r) {
+            int cnt = 0;
+            for (int a = 0; a < 4; ++a) {
+                if (!user[a] || !bytes[a]) continue;
+                const size_t rows = (a & 1) ? (size_t)gate.t_rows : (size_t)gate.q_rows;
+                const size_t per_round = rows * (a < 2 ? 32 : 8);
+                const size_t b0 = r < bfm::FEED_HEAD ? (size_t)r * (per_round / bfm::FEED_HEAD) : (size_t)(r - bfm::FEED_HEAD + 1) * per_round;
+                const size_t b1 = r < bfm::FEED_HEAD ? b0 + per_round / bfm::FEED_HEAD : b0 + per_round;
+                const size_t lo = std::min(b0, bytes[a]), hi = std::min(b1, bytes[a]);
+                if (hi > lo) {
+                    jobs.push_back({r, stage + offs[a] + lo, static_cast<const char *>(user[a]) + lo, hi - lo});
+                    ++cnt;
+                }
+            }
+            sh->left[r].store(cnt, std::memory_order_relaxed);
+        }
+        for (const Job &j : jobs)
+            h->pool->submit([j, sh, advance]() {
+                stream_copy(j.dst, j.src, j.n);   // non-temporal: the next reader is the GPU, over PCIe
+                if (sh->left[j.r].fetch_sub(1, std::memory_order_acq_rel) == 1) advance();
+            });
+        advance();   // leading rounds without bytes
+        const double t_submitted = cpu_ms();
+        CU_TRY(h, cudaMemsetAsync(h->d_prog, 0, 128, st));
+        rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
+                        nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st, &gate);
+        const double t_launched = cpu_ms();
+        h->pool->help_and_wait();   // also after a failed launch: the jobs reference this call's buffers
+        advance();
+        const double t_staged = cpu_ms();
+        if (rc) {
+            cudaDeviceSynchronize();
+            h->state_clean = false;
+            return rc;
+        }
+        CU_TRY(h, cudaStreamSynchronize(st));
+        if (*h->h_status != 0) {
+            h->state_clean = false;
+            return fail(h, BFM_ERR_CUDA, "input gate timed out: the staged upload did not reach the GPU");
+        }
+        h->info.copy_chunks = gate.rounds;
+        if (trace) std::fprintf(stderr, "[bfm trace] host-staged SM-fed upload: %d threads, %d feeders, %d rounds: jobs submitted %.3f, kernel "
+                                "launched %.3f, staged %.3f, kernel done %.3f ms (direct=%d)\n",
+                                h->pool->size() + 1, gate.n_feed, gate.rounds, t_submitted, t_launched, t_staged, cpu_ms(), (int)direct);
     } else if (G <= 1) {
         if (qb) CU_TRY(h, cudaMemcpyAsync(din + o_q, q, qb, cudaMemcpyHostToDevice, st));
         if (tb) CU_TRY(h, cudaMemcpyAsync(din + o_t, t, tb, cudaMemcpyHostToDevice, st));
@@ -260,20 +360,38 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
     }
 
     if (!direct) {
+        // pinned staging -> the caller's pageable arrays; large results are copied by the worker threads
+        if (out_total >= ((size_t)1 << 20)) ensure_pool(h);
+        const bool par = h->pool && out_total >= ((size_t)1 << 20);
+        auto run = [&](std::function<void()> f) { if (par) h->pool->submit(std::move(f)); else f(); };
         if (want_knn) {
-            std::memcpy(user.knn_idx, dst.knn_idx, (size_t)n_out_rows * k * 4);
-            std::memcpy(user.knn_dist, dst.knn_dist, (size_t)n_out_rows * k * 4);
+            const size_t total = (size_t)n_out_rows * k * 4, parts = par ? 8 : 1, step = (total / parts + 63) & ~(size_t)63;
+            for (size_t b = 0; b < total; b += std::max<size_t>(step, 64)) {
+                const size_t n = std::min(std::max<size_t>(step, 64), total - b);
+                char *ui = reinterpret_cast<char *>(user.knn_idx), *ud = reinterpret_cast<char *>(user.knn_dist);
+                const char *si = reinterpret_cast<const char *>(dst.knn_idx), *sd = reinterpret_cast<const char *>(dst.knn_dist);
+                run([=]() { std::memcpy(ui + b, si + b, n); std::memcpy(ud + b, sd + b, n); });
+            }
         }
         if (want_m) {
             std::memcpy(user.m_count, dst.m_count, (size_t)n_problems * 4);
             // only the filled prefix of every problem's slice is meaningful; copy exactly that
-            for (int p = 0; p < n_problems; ++p) {
-                const size_t b = (size_t)problems[p].out_begin, n = (size_t)user.m_count[p];
-                std::memcpy(user.m_query + b, dst.m_query + b, n * 4);
-                std::memcpy(user.m_train + b, dst.m_train + b, n * 4);
-                std::memcpy(user.m_dist + b, dst.m_dist + b, n * 4);
+            const int group = par ? std::max(1, n_problems / 16) : n_problems;
+            for (int p0 = 0; p0 < n_problems; p0 += group) {
+                const int p1 = std::min(n_problems, p0 + group);
+                const bfm_outputs_t u = user, d2 = dst;
+                run([=]() {
+                    for (int p = p0; p < p1; ++p) {
+                        const size_t b = (size_t)problems[p].out_begin, n = (size_t)u.m_count[p];
+                        std::memcpy(u.m_query + b, d2.m_query + b, n * 4);
+                        std::memcpy(u.m_train + b, d2.m_train + b, n * 4);
+                        std::memcpy(u.m_dist + b, d2.m_dist + b, n * 4);
+                    }
+                });
             }
         }
+        if (par) h->pool->help_and_wait();
+        if (trace) std::fprintf(stderr, "[bfm trace] results copied to the caller's arrays at %.3f ms\n", cpu_ms());
     }
     return BFM_OK;
 }

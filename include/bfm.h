@@ -234,6 +234,7 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
 /* knob: "popc_mode" {0=auto,8,6,5,4,50,40}, "queries_per_thread" {0=auto,1,2,4}, "timing" {0,1},
  *       "segment_rows" {0=auto, n}, "waves" {0=auto, n}, "pipeline_chunks" {0=auto, 1=off, n <= 64},
  *       "feeders" {0=auto (24), -1=off: copy-engine chunks, n <= 32}, "feed_rows" {0=auto, rows per feed round},
+ *       "host_threads" {0=auto (<= 8), -1=off, n: staging threads for pageable caller arrays},
  *       "window_bins" {0=auto, 1=brute-force window kernel} */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */

@@ -18,18 +18,18 @@ def run(n=20):
     t0 = time.perf_counter()
     for i in range(n): eng.match_batched(sets[i % 6][0].array, sets[i % 6][1].array, tab, k=2, ratio=0.8, out=out)
     return (time.perf_counter() - t0) / n * 1e3
-print(f"before torch: {run():.4f} {run():.4f} ms", flush=True)
-import torch
-torch.cuda.set_device(0)
-x = torch.zeros(4, device="cuda")
-print(f"after torch import + context: {run():.4f} {run():.4f} ms", flush=True)
-dev_sets = [(torch.from_numpy(s[2]).cuda(), torch.from_numpy(s[3]).cuda()) for s in sets]
-print(f"after device sets: {run():.4f} {run():.4f} ms", flush=True)
-o = {"m": torch.empty((3, P * N), dtype=torch.int32, device="cuda"), "count": torch.zeros(P, dtype=torch.int32, device="cuda")}
-for i in range(23):
-    eng.match_batched_device(dev_sets[i % 6][0], dev_sets[i % 6][1], tab, k=2, ratio=0.8, out=o)
-torch.cuda.synchronize()
-print(f"after device loop: {run():.4f} {run():.4f} ms", flush=True)
-from boslam_b200 import _ffi
-_ffi.microbench(0, 4000, tests=("popc",))
-print(f"after microbench: {run():.4f} {run():.4f} ms", flush=True)
+print(f"pinned in/out: {run():.4f} ms", flush=True)
+def run_mix(pin_in, pin_out, n=20):
+    def call(i):
+        a = sets[i % 6]
+        qq, tt = (a[0].array, a[1].array) if pin_in else (a[2], a[3])
+        return eng.match_batched(qq, tt, tab, k=2, ratio=0.8, out=out if pin_out else None)
+    for i in range(3): call(i)
+    t0 = time.perf_counter()
+    for i in range(n): call(i)
+    return (time.perf_counter() - t0) / n * 1e3
+for pin_in in (True, False):
+    for pin_out in (True, False):
+        print(f"pinned_in={pin_in} pinned_out={pin_out}: {run_mix(pin_in, pin_out):.4f} ms", flush=True)
+os.environ["BFM_TRACE"] = "1"
+run_mix(False, True, 2)

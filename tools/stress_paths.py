@@ -39,7 +39,7 @@ for it in range(iters):
     ref = None
     runs = []
     for chunks in (1, int(rng.integers(2, 25))):
-        eng.set_tuning(pipeline_chunks=chunks, feeders=[0, -1, int(rng.integers(1, 33))][it % 3])
+        eng.set_tuning(pipeline_chunks=chunks, feeders=[0, -1, int(rng.integers(1, 33))][it % 3], host_threads=[0, 0, -1, 3][it % 4])
         runs.append(("host pageable chunks=%d" % chunks, eng.match_batched(q, t, tab, want_knn=want_knn, **kw)))
         n_out = int(qn.sum())
         if n_out and len(q) and len(t):
@@ -49,7 +49,7 @@ for it in range(iters):
             ob = bb.HostBatchBuffers(n_out, P, k=kw.get("k", 1), want_knn=want_knn)
             r = eng.match_batched(pq.array, pt.array, tab, want_knn=want_knn, out=ob, **kw)
             runs.append(("host pinned chunks=%d" % chunks, r))
-    eng.set_tuning(pipeline_chunks=0, feeders=0)
+    eng.set_tuning(pipeline_chunks=0, feeders=0, host_threads=0)
     if len(q) and len(t):
         runs.append(("device", eng.match_batched(torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), tab, want_knn=want_knn, **kw)))
 
