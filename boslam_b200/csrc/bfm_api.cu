@@ -125,7 +125,7 @@ struct bfm_handle_s {
     unsigned long long seq = 0;              // call sequence number (watermark epoch)
 
     // tuning knobs
-    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0;
+    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0, pipeline_min_kb = 0;
     uint32_t *d_prog = nullptr;   // SM-fed upload: progress words of the feeder CTAs
     // pageable caller arrays: host threads stage them into pinned memory slice by slice for the feeders
     std::unique_ptr<WorkerPool> pool;
@@ -794,6 +794,9 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "feeders") {
         if (value < -1 || value > bfm::FEED_MAX) return fail(h, BFM_ERR_INVALID, "feeders must be -1 (off: copy engine), 0 (auto) or 1..32");
         h->feeders = value;
+    } else if (k == "pipeline_min_kb") {
+        if (value < 0) return fail(h, BFM_ERR_INVALID, "pipeline_min_kb must be >= 0");
+        h->pipeline_min_kb = value;
     } else if (k == "host_threads") {
         if (value < -1 || value > 64) return fail(h, BFM_ERR_INVALID, "host_threads must be -1 (off), 0 (auto) or 1..64");
         if (value != h->host_threads) h->pool.reset();

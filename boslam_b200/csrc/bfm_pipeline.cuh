@@ -101,7 +101,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
     int G = 1;
     if (h->pipeline_chunks > 1) {
         G = std::min(h->pipeline_chunks, n_problems);
-    } else if (h->pipeline_chunks == 0 && n_problems >= 4 && !dense && qb + tb >= ((size_t)4 << 20)) {
+    } else if (h->pipeline_chunks == 0 && n_problems >= 4 && !dense && qb + tb >= ((size_t)(h->pipeline_min_kb > 0 ? h->pipeline_min_kb : 1024) << 10)) {
         G = std::min(12, n_problems);
     }
     const bool trace = std::getenv("BFM_TRACE") != nullptr;
