@@ -316,7 +316,7 @@ struct Gate {
 int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t, int32_t nt_rows,
                const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
                const bfm_options_t *o, const bfm_outputs_t *dests, int n_dests, cudaStream_t st,
-               const Gate *gate = nullptr, const int32_t *t_limit = nullptr) {
+               const Gate *gate = nullptr, const int32_t *t_limit = nullptr, int32_t t_plan_rows = 0) {
     h->info = bfm_launch_info_t{};
     if (n_problems <= 0 || n_out_rows <= 0) return BFM_OK;
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(t)) & 15)
@@ -367,6 +367,16 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
                         std::isfinite(o->window_radius) && o->window_radius > 0.0f && problems[0].q_count > 0 &&
                         problems[0].t_count > 0 && problems[0].t_count <= bfm::WB_MAX_ROWS;
     const int bin_grid = binned ? (problems[0].q_count + bfm::WS_NT / 32 - 1) / (bfm::WS_NT / 32) : 0;
+    // a device-side train count: plan the work items for the rows the caller expects to exist (the kernel re-cuts
+    // whatever does exist evenly over them, so the guess only affects efficiency, never the result)
+    bfm_problem_t hinted;
+    const bfm_problem_t *plan_problems = problems;
+    if (t_limit != nullptr && n_problems == 1 && !binned) {
+        hinted = problems[0];
+        const int guess = t_plan_rows > 0 ? t_plan_rows : std::max(1, problems[0].t_count / 2);
+        hinted.t_count = std::min(problems[0].t_count, std::max(128, (guess + 1023) & ~1023));
+        plan_problems = &hinted;
+    }
     if (binned) r = 1;
     if (r != 1 && r != 2 && r != 4) {
         // largest register tile that still leaves >= 2 work items per CTA slot
@@ -376,9 +386,9 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             if (rc) return rc;
             long long units = 0;
             for (int p = 0; p < n_problems; ++p)
-                if (problems[p].q_count > 0 && problems[p].t_count > 0)
-                    units += (long long)((problems[p].q_count + NT * cand - 1) / (NT * cand)) *
-                             ((problems[p].t_count + 2 * MIN_SEG_ROWS - 1) / (2 * MIN_SEG_ROWS));
+                if (plan_problems[p].q_count > 0 && plan_problems[p].t_count > 0)
+                    units += (long long)((plan_problems[p].q_count + NT * cand - 1) / (NT * cand)) *
+                             ((plan_problems[p].t_count + 2 * MIN_SEG_ROWS - 1) / (2 * MIN_SEG_ROWS));
             r = cand;
             if (units >= 2ll * occ * h->sm_count) break;
         }
@@ -391,7 +401,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
-    const int plan_sig[6] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves, slots};
+    const int plan_sig[6] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
                           h->plan_problems.size() == (size_t)n_problems &&
                           std::memcmp(h->plan_problems.data(), problems, sizeof(bfm_problem_t) * (size_t)n_problems) == 0;
@@ -402,7 +412,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         h->plan_probs = h->probs_host;
         h->plan_probs[0].n_segs = bin_grid;   // the search kernel's CTAs play the role of segments
     } else if (!plan_hit) {
-        plan_segments(h, problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows);
+        plan_segments(h, plan_problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows);
         h->plan_seg_rows = seg_rows;
         h->plan_probs = h->probs_host;
         for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = h->seg_begin[p + 1] - h->seg_begin[p];
@@ -487,6 +497,10 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     sp.colkeys = colkeys;
     sp.done = done;
     sp.t_limit = t_limit;
+    if (t_limit != nullptr && !binned) {
+        const int nqb = (problems[0].q_count + NT * r - 1) / (NT * r);
+        sp.limit_segs = std::max(1, (int)(n_segs / std::max(nqb, 1)));
+    }
     if (gate) {
         sp.ready = gate->ready;
         sp.ready_base = gate->base;

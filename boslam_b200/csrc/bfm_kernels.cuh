@@ -89,6 +89,7 @@ struct ScanParams {
     const uint32_t *feed_host_ready;         // pinned host word: rounds staged by the host's worker threads so far
                                              // (pageable caller arrays); NULL = the sources are complete
     const int32_t *t_limit;          // optional device scalar: train rows that exist (single problem), else NULL
+    int32_t limit_segs;              // with t_limit: work items per query block (the rows that exist are re-cut over them)
     const uint8_t *mask;             // dense mask (single problem): [q_local][mask_stride]
     long long mask_stride;
     const float2 *q_xy;              // window: pixel coordinates per query / train row
@@ -570,8 +571,17 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
 
     // train rows of this segment; with a device-side limit (a train set whose size was decided by an
     // earlier kernel on the same stream, e.g. the visible local-map points) the range is clamped here
-    int t_count = sg.t_count;
-    if (p.t_limit != nullptr) t_count = max(0, min(t_count, __ldg(p.t_limit) - sg.t_local0));
+    // (single problem).  The rows that exist are then re-cut evenly over this query block's `limit_segs` work
+    // items, so every CTA gets the same share whatever the host guessed when it planned.
+    int t_count = sg.t_count, t_row0 = sg.t_row0, t_local0 = sg.t_local0;
+    if (p.t_limit != nullptr) {
+        const int rows = max(0, __ldg(p.t_limit));
+        const int s_idx = ((int)blockIdx.x - p.n_feed) % p.limit_segs;
+        const int per = (rows + p.limit_segs - 1) / p.limit_segs;
+        t_row0 = sg.t_row0 - sg.t_local0 + s_idx * per;
+        t_local0 = s_idx * per;
+        t_count = max(0, min(per, rows - t_local0));
+    }
 
     // -- start the train stream first: the TMA of chunks 0 and 1 flies while the queries are loaded ----
     if (tid == 0) {
@@ -581,11 +591,11 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         const int n0 = min(TT, t_count), n1 = min(TT, t_count - TT);
         if (n0 > 0) {
             mbar_expect_tx(&s_bar[0], (uint32_t)n0 * 32u);
-            bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)sg.t_row0, (uint32_t)n0 * 32u, &s_bar[0]);
+            bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)t_row0, (uint32_t)n0 * 32u, &s_bar[0]);
         }
         if (n1 > 0) {
             mbar_expect_tx(&s_bar[1], (uint32_t)n1 * 32u);
-            bulk_g2s(&s_t[1][0], p.t + 2 * (size_t)(sg.t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[1]);
+            bulk_g2s(&s_t[1][0], p.t + 2 * (size_t)(t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[1]);
         }
     }
 
@@ -629,10 +639,10 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes
         mbar_expect_tx(&s_bar[c & 1], bytes);
-        bulk_g2s(&s_t[c & 1][0], p.t + 2 * (size_t)(sg.t_row0 + c * TT), bytes, &s_bar[c & 1]);
+        bulk_g2s(&s_t[c & 1][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[c & 1]);
     };
     auto stage_xy = [&](int c) {
-        if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldg(p.t_xy + sg.t_row0 + c * TT + tid);
+        if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldg(p.t_xy + t_row0 + c * TT + tid);
     };
     auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
         mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
@@ -656,7 +666,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1;
         const int n = chunk_rows(c);
-        const uint32_t jbase = (uint32_t)(sg.t_local0 + c * TT);
+        const uint32_t jbase = (uint32_t)(t_local0 + c * TT);
         if constexpr (R >= 2) {
             // ---- packed path: two queries share one register of chunk-local 16-bit keys ----------
             // key16 = d << 7 | j (j < 128), so one VIMNMX.U16x2 updates two queries at once; the
@@ -758,7 +768,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
                 uint32_t m = s_col[b][0][j];
 #pragma unroll
                 for (int w = 1; w < NW; ++w) m = min(m, s_col[b][w][j]);
-                if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)col0 + sg.t_local0 + c * TT + j, m);
+                if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)col0 + t_local0 + c * TT + j, m);
             }
         }
     }

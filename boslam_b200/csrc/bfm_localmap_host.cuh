@@ -10,6 +10,7 @@ struct bfm_map_s {
     DevBuf work;               // per-call device workspace
     void *h_in = nullptr, *h_out = nullptr;   // pinned staging
     size_t h_in_cap = 0, h_out_cap = 0;
+    int32_t last_visible = 0;  // visible edges of the previous call: the planning hint for the next one
 };
 
 namespace {
@@ -239,7 +240,8 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
         const bfm_problem_t pr = {0, nq, 0, n_edges, 0, 0};
         const bfm_outputs_t outs[2] = {{nullptr, nullptr, d_m, d_m + nqa, d_m + 2 * (size_t)nqa, d_hdr + 1, 0, 0},
                                        {nullptr, nullptr, h_m, h_m + nqa, h_m + 2 * (size_t)nqa, h_hdr + 1, 0, 0}};
-        rc = run_device(h, d_q, nq, reinterpret_cast<const uint8_t *>(d_tdesc), n_edges, &pr, 1, nq, &od, outs, 2, st, nullptr, d_hdr);
+        rc = run_device(h, d_q, nq, reinterpret_cast<const uint8_t *>(d_tdesc), n_edges, &pr, 1, nq, &od, outs, 2, st, nullptr, d_hdr,
+                        m->last_visible);
         if (rc) return rc;
         kernels += h->info.kernels_launched;
         lm_gather_kernel<<<(nq + LM_NT - 1) / LM_NT, LM_NT, 0, st>>>(d_m, d_m + nqa, d_hdr + 1, d_vpt, d_vedge, d_kp, h_mpt, h_mkp, h_medge);
@@ -255,6 +257,7 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     const int nv = h_hdr[0], nm = h_hdr[1];
     *n_visible = nv;
     *n_matches = nm;
+    m->last_visible = nv;   // tracking is temporally coherent: the next frame's plan is sized for about this many rows
     if (visible_edges) std::memcpy(visible_edges, h_vedge, (size_t)nv * 4);
     if (visible_pixels) std::memcpy(visible_pixels, h_vpix, (size_t)nv * 16);
     if (m_query) std::memcpy(m_query, h_m, (size_t)nm * 4);
