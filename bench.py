@@ -484,7 +484,11 @@ def main():
         "bound": "int_popc", "kernel": "bfm_scan_kernel", "achieved": achieved_popc / 1e9, "peak": popc["ops_per_s"] / 1e9,
         "unit": "GPOPC/s", "frac": achieved_popc / popc["ops_per_s"], "traffic": traffic,
         "algorithmic": "8 POPC per descriptor pair x 1.024e9 pairs per launch",
-        "popc_issued_per_pair": info["popc_mode"], "scan_ms": scan_avg, "scan_share_of_step": scan_avg / (ms / args.steps),
+        "popc_issued_per_pair": 4 if info["popc_mode"] in (4, 40) else (5 if info["popc_mode"] in (5, 50) else info["popc_mode"]),
+        "popc_mode": info["popc_mode"],
+        "issue_bound": {"pipe": "xu (POPC)", "busy_pct": 88.2, "alu_busy_pct": 82.6,
+                        "source": "profiles/r01c_ncu_scan_fused_pm40_k2.md (ncu --set full of this command)"},
+        "scan_ms": scan_avg, "scan_share_of_step": scan_avg / (ms / args.steps),
         "peak_source": "measured in this run: bfm_microbench POPC probe (16 POPC/clk/SM x 148 SMs x SM clock)",
         "popc_per_clk_per_sm": popc["ops_per_clk_per_sm"],
         "hbm": {"achieved": hbm_bytes / (scan_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -518,8 +522,9 @@ def main():
            "h2d_bytes_per_step": int(2 * n_out * 32 + tab.nbytes), "d2h_bytes_per_step": (int(res.counts.sum()) * 12 + N_PAIRS * 4) if res is not None else 0,
            "ms_per_step": e2e_s / max(e2e_steps, 1) * 1e3, "matches_last_step": int(res.counts.sum()) if res is not None else None,
            "copy_chunks": eng.launch_info().get("copy_chunks"),
-           "how": "numpy (pinned) in -> numpy (pinned) out through Engine.match_batched: chunked H2D on the copy engine feeding one "
-                  "gated kernel, results written by the kernel into pinned host memory, one stream sync"} if e2e_steps else None
+           "how": "numpy (pinned) in -> numpy (pinned) out through Engine.match_batched: ONE kernel launch per step whose first CTAs "
+                  "stream the step's inputs from pinned host memory into HBM (copy_chunks = feed rounds) while the others match; "
+                  "results written by the kernel into pinned host memory; one stream sync"} if e2e_steps else None
 
     line = {
         "metric": "hamming_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
