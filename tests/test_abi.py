@@ -35,6 +35,8 @@ def test_abi_version_and_struct_layout():
     assert ctypes.sizeof(_ffi.Options) == 64
     assert _ffi.Options.ratio.offset == 16 and _ffi.Options.mask.offset == 32
     assert ctypes.sizeof(_ffi.LaunchInfo) == 40
+    assert ctypes.sizeof(_ffi.Outputs) == 56 and _ffi.Outputs.multicast.offset == 48        # bfm_outputs_t
+    assert ctypes.sizeof(_ffi.TrackParams) == 128 and _ffi.TrackParams.width.offset == 120  # bfm_track_params_t
 
 
 def _has_gpu():
@@ -79,3 +81,24 @@ def test_dmatch_surface():
     assert mm.crossCheck is True
     with pytest.raises(ValueError):
         bb.BFMatcher_create(4)
+
+
+def test_struct_layout_against_the_c_header(tmp_path):
+    """Compile include/bfm.h with gcc and compare every struct's size / key offsets with the ctypes mirror."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bfm.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(bfm_problem_t), sizeof(bfm_options_t),'
+                   ' offsetof(bfm_options_t, mask), sizeof(bfm_outputs_t), offsetof(bfm_outputs_t, multicast),'
+                   ' sizeof(bfm_track_params_t), offsetof(bfm_track_params_t, cos_max), sizeof(bfm_launch_info_t),'
+                   ' offsetof(bfm_launch_info_t, scan_ms)); return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(_ffi.Problem), ctypes.sizeof(_ffi.Options), _ffi.Options.mask.offset, ctypes.sizeof(_ffi.Outputs),
+            _ffi.Outputs.multicast.offset, ctypes.sizeof(_ffi.TrackParams), _ffi.TrackParams.cos_max.offset,
+            ctypes.sizeof(_ffi.LaunchInfo), _ffi.LaunchInfo.scan_ms.offset]
+    assert got == want
