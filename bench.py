@@ -320,6 +320,28 @@ def extras(eng, torch, steps):
                                                   "Python over g2o calls) + cv2 crossCheck match + gate", "cpu_matches": int(n_cpu)})
     except Exception as e:  # the CPU figure is optional context
         out["local_map_track_20000edges_2000desc_fused"]["cpu_error"] = repr(e)
+    # MapPoint.add_observation's descriptor choice (slam/nodes.py:146-153) for the 2000 map points a new
+    # keyframe touches, 10 stored observations each; CPU figure: the reference's literal double loop on 50 of them
+    try:
+        rngr = np.random.default_rng(17)
+        base = rngr.integers(0, 256, (2000, 1, 32), dtype=np.uint8)
+        obs = base ^ np.packbits(rngr.random((2000, 10, 256)) < 0.06, axis=2)
+        cnts = np.full(2000, 10, np.int32)
+        for _ in range(3):
+            sel = bb.select_representative(obs, cnts, engine=eng)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sel = bb.select_representative(obs, cnts, engine=eng)
+        dts = (time.perf_counter() - t0) / reps
+        from oracle import representative_oracle as ro
+        t0 = time.perf_counter()
+        want = ro.select_batch(obs[:50], cnts[:50])
+        dtc = (time.perf_counter() - t0) / 50 * 2000
+        out["representative_descriptor_2000pts_10obs"] = {"ms_e2e": dts * 1e3, "points_per_s_e2e": 2000 / dts,
+                                                          "cpu_ms_literal_loop_scaled": dtc * 1e3,
+                                                          "agrees_with_reference_loop": bool(np.array_equal(sel[:50], want))}
+    except Exception as e:
+        out["representative_descriptor_2000pts_10obs"] = {"error": repr(e)}
     return out
 
 
