@@ -62,8 +62,11 @@ __device__ __forceinline__ bool lm_project(const ProjectParams &pp, const double
 // pass 1: visibility flag + pixel per edge, survivors per block
 __global__ void __launch_bounds__(LM_NT) lm_project_kernel(const ProjectParams pp, const MapView map, const int32_t *edges,
                                                            int32_t n_edges, int32_t capacity, double2 *pix, uint8_t *flag,
-                                                           int32_t *block_count) {
+                                                           int32_t *block_count, const double *q_kp, float2 *q_xy, int32_t nq) {
     const int e = blockIdx.x * LM_NT + threadIdx.x;
+    // the frame's keypoints as float2 for the window predicate (grid-stride: nq may exceed n_edges)
+    if (q_xy != nullptr)
+        for (int i = e; i < nq; i += gridDim.x * LM_NT) q_xy[i] = make_float2((float)q_kp[2 * (size_t)i], (float)q_kp[2 * (size_t)i + 1]);
     bool vis = false;
     if (e < n_edges) {
         const int slot = edges[e];
@@ -83,9 +86,8 @@ __global__ void __launch_bounds__(LM_NT) lm_project_kernel(const ProjectParams p
 // pass 2: ordered compaction + gathers.  Survivor number j (in edge order) becomes train row j.
 __global__ void __launch_bounds__(LM_NT) lm_compact_kernel(const MapView map, const int32_t *edges, int32_t n_edges,
                                                            const double2 *pix, const uint8_t *flag, const int32_t *block_count,
-                                                           int32_t *vis_edge, float2 *t_xy, uint4 *t_desc, double *vis_pt3d,
-                                                           int32_t *n_visible, int32_t *h_vis_edge, double2 *h_vis_pix,
-                                                           int32_t *h_n_visible) {
+                                                           int32_t *vis_edge, double2 *vis_pix, float2 *t_xy, uint4 *t_desc,
+                                                           double *vis_pt3d, int32_t *n_visible) {
     __shared__ int s_red[LM_NT / 32];
     __shared__ int s_warp[LM_NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -111,15 +113,13 @@ __global__ void __launch_bounds__(LM_NT) lm_compact_kernel(const MapView map, co
         int before = 0;
         for (int w = 0; w < LM_NT / 32; ++w) before += s_red[w];
         *n_visible = before + mine;
-        *h_n_visible = before + mine;   // pinned host memory: the caller reads it after the stream drains
     }
     if (!vis) return;
     pos += __popc(bal & ((1u << lane) - 1u));
     const int slot = edges[e];
     const double2 p = pix[e];
     vis_edge[pos] = e;
-    h_vis_edge[pos] = e;
-    if (h_vis_pix) h_vis_pix[pos] = p;
+    if (vis_pix) vis_pix[pos] = p;
     t_xy[pos] = make_float2((float)p.x, (float)p.y);
     const uint4 *d = reinterpret_cast<const uint4 *>(map.desc + 32 * (size_t)slot);
     t_desc[2 * (size_t)pos] = d[0];
@@ -130,24 +130,40 @@ __global__ void __launch_bounds__(LM_NT) lm_compact_kernel(const MapView map, co
     vis_pt3d[3 * (size_t)pos + 2] = Xp[2];
 }
 
-// pass 4: matched (3-D point, frame pixel, edge) triples, contiguous (slam/tracking.py:126-128)
-__global__ void __launch_bounds__(LM_NT) lm_gather_kernel(const int32_t *m_query, const int32_t *m_train, const int32_t *m_count,
-                                                          const double *vis_pt3d, const int32_t *vis_edge, const double *q_kp,
-                                                          double *out_pts3d, double *out_kp, int32_t *out_edge) {
+// pass 4: everything the caller gets, written to pinned host memory by ONE kernel (a kernel that writes host
+// memory only completes when its PCIe writes have drained, ~10 us: paying that once beats paying it in every
+// stage): header, visible edges (+ pixels), match list, and the matched (3-D point, frame pixel, edge) triples
+// gathered contiguously (slam/tracking.py:126-128).
+struct TrackHostOut {
+    int32_t *hdr;                 // n_visible, n_matches
+    int32_t *vis_edge;
+    double2 *vis_pix;             // nullable
+    int32_t *m_query, *m_train, *m_dist, *m_edge;
+    double *m_pts3d, *m_kp;
+};
+__global__ void __launch_bounds__(LM_NT) lm_gather_kernel(const int32_t *hdr, const int32_t *vis_edge, const double2 *vis_pix,
+                                                          const int32_t *m_query, const int32_t *m_train, const int32_t *m_dist,
+                                                          const double *vis_pt3d, const double *q_kp, int32_t have_matches,
+                                                          TrackHostOut out) {
+    const int nv = hdr[0], nm = have_matches ? hdr[1] : 0;
     const int i = blockIdx.x * LM_NT + threadIdx.x;
-    if (i >= *m_count) return;
-    const int qi = m_query[i], ti = m_train[i];
-    out_pts3d[3 * (size_t)i] = vis_pt3d[3 * (size_t)ti];
-    out_pts3d[3 * (size_t)i + 1] = vis_pt3d[3 * (size_t)ti + 1];
-    out_pts3d[3 * (size_t)i + 2] = vis_pt3d[3 * (size_t)ti + 2];
-    out_kp[2 * (size_t)i] = q_kp[2 * (size_t)qi];
-    out_kp[2 * (size_t)i + 1] = q_kp[2 * (size_t)qi + 1];
-    out_edge[i] = vis_edge[ti];
-}
-
-__global__ void lm_kp_to_float_kernel(const double *kp, float2 *xy, int32_t n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) xy[i] = make_float2((float)kp[2 * (size_t)i], (float)kp[2 * (size_t)i + 1]);
+    if (i == 0) { out.hdr[0] = nv; out.hdr[1] = nm; }
+    for (int e = i; e < nv; e += gridDim.x * LM_NT) {
+        out.vis_edge[e] = vis_edge[e];
+        if (out.vis_pix) out.vis_pix[e] = vis_pix[e];
+    }
+    for (int k = i; k < nm; k += gridDim.x * LM_NT) {
+        const int qi = m_query[k], ti = m_train[k];
+        out.m_query[k] = qi;
+        out.m_train[k] = ti;
+        out.m_dist[k] = m_dist[k];
+        out.m_edge[k] = vis_edge[ti];
+        out.m_pts3d[3 * (size_t)k] = vis_pt3d[3 * (size_t)ti];
+        out.m_pts3d[3 * (size_t)k + 1] = vis_pt3d[3 * (size_t)ti + 1];
+        out.m_pts3d[3 * (size_t)k + 2] = vis_pt3d[3 * (size_t)ti + 2];
+        out.m_kp[2 * (size_t)k] = q_kp[2 * (size_t)qi];
+        out.m_kp[2 * (size_t)k + 1] = q_kp[2 * (size_t)qi + 1];
+    }
 }
 
 // scatter of an update batch into the store (slots may repeat: last writer in batch order wins is NOT

@@ -167,7 +167,8 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     dsc.take<uint4>((size_t)n_edges * 2);         // t_desc
     dsc.take<double>((size_t)n_edges * 3);        // vis_pt3d
     dsc.take<float2>(nqa);                        // q_xy
-    dsc.take<int32_t>((size_t)nqa * 3);           // m_query | m_train | m_dist (device copy: the gather reads it)
+    dsc.take<int32_t>((size_t)nqa * 3);           // m_query | m_train | m_dist
+    dsc.take<double2>(visible_pixels ? n_edges : 0);   // vis_pix
     const size_t scratch_bytes = dsc.off;
     int rc = ensure(h, m->work, in_bytes + scratch_bytes);
     if (rc) return rc;
@@ -197,6 +198,8 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     double *d_vpt = ds.take<double>((size_t)n_edges * 3);
     float2 *d_qxy = ds.take<float2>(nqa);
     int32_t *d_m = ds.take<int32_t>((size_t)nqa * 3);
+    double2 *d_vpix = ds.take<double2>(visible_pixels ? n_edges : 0);
+    if (!visible_pixels) d_vpix = nullptr;
     int32_t *h_hdr = ho.take<int32_t>(4);
     int32_t *h_vedge = ho.take<int32_t>(n_edges);
     double2 *h_vpix = ho.take<double2>(visible_pixels ? n_edges : 0);
@@ -209,7 +212,6 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
 
     const double t_staged = cpu_us();
     CU_TRY(h, cudaMemcpyAsync(dbase, m->h_in, in_bytes, cudaMemcpyHostToDevice, st));
-    CU_TRY(h, cudaMemsetAsync(d_hdr, 0, 16, st));
 
     ProjectParams pp;
     pp.qw = tp->q[0]; pp.qx = tp->q[1]; pp.qy = tp->q[2]; pp.qz = tp->q[3];
@@ -219,35 +221,34 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     pp.width = (double)tp->width; pp.height = (double)tp->height;
     pp.cos_max = tp->cos_max;
     MapView mv{m->desc, m->pt3d, m->normal};
-    lm_project_kernel<<<nblk, LM_NT, 0, st>>>(pp, mv, d_edges, n_edges, m->capacity, d_pix, d_flag, d_bc);
+    const bool window = opts->mask_kind == BFM_MASK_WINDOW && nq > 0;
+    lm_project_kernel<<<nblk, LM_NT, 0, st>>>(pp, mv, d_edges, n_edges, m->capacity, d_pix, d_flag, d_bc, d_kp,
+                                              window ? d_qxy : nullptr, nq);
     CU_TRY(h, cudaGetLastError());
-    lm_compact_kernel<<<nblk, LM_NT, 0, st>>>(mv, d_edges, n_edges, d_pix, d_flag, d_bc, d_vedge, d_txy, d_tdesc, d_vpt, d_hdr,
-                                              h_vedge, h_vpix, h_hdr);
+    lm_compact_kernel<<<nblk, LM_NT, 0, st>>>(mv, d_edges, n_edges, d_pix, d_flag, d_bc, d_vedge, d_vpix, d_txy, d_tdesc, d_vpt, d_hdr);
     CU_TRY(h, cudaGetLastError());
     int kernels = 2;
     if (nq > 0) {
         bfm_options_t od = *opts;
-        if (opts->mask_kind == BFM_MASK_WINDOW) {
-            lm_kp_to_float_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_kp, d_qxy, nq);
-            CU_TRY(h, cudaGetLastError());
-            ++kernels;
+        if (window) {
             od.q_xy = reinterpret_cast<const float *>(d_qxy);
             od.t_xy = reinterpret_cast<const float *>(d_txy);
         }
         // the train set is the compacted survivor list: its size lives in d_hdr[0]; the plan covers
-        // all n_edges rows and every work item clamps its range on the device (no host round trip).
-        // Two destinations: a device copy (the gather below reads it) and the pinned host block.
+        // the rows the previous frame saw and every work item re-cuts what exists on the device (no host round trip)
         const bfm_problem_t pr = {0, nq, 0, n_edges, 0, 0};
-        const bfm_outputs_t outs[2] = {{nullptr, nullptr, d_m, d_m + nqa, d_m + 2 * (size_t)nqa, d_hdr + 1, 0, 0},
-                                       {nullptr, nullptr, h_m, h_m + nqa, h_m + 2 * (size_t)nqa, h_hdr + 1, 0, 0}};
-        rc = run_device(h, d_q, nq, reinterpret_cast<const uint8_t *>(d_tdesc), n_edges, &pr, 1, nq, &od, outs, 2, st, nullptr, d_hdr,
+        const bfm_outputs_t outs = {nullptr, nullptr, d_m, d_m + nqa, d_m + 2 * (size_t)nqa, d_hdr + 1, 0, 0};
+        rc = run_device(h, d_q, nq, reinterpret_cast<const uint8_t *>(d_tdesc), n_edges, &pr, 1, nq, &od, &outs, 1, st, nullptr, d_hdr,
                         m->last_visible);
         if (rc) return rc;
         kernels += h->info.kernels_launched;
-        lm_gather_kernel<<<(nq + LM_NT - 1) / LM_NT, LM_NT, 0, st>>>(d_m, d_m + nqa, d_hdr + 1, d_vpt, d_vedge, d_kp, h_mpt, h_mkp, h_medge);
-        CU_TRY(h, cudaGetLastError());
-        ++kernels;
     }
+    TrackHostOut ho_ptrs{h_hdr, h_vedge, h_vpix, h_m, h_m + nqa, h_m + 2 * (size_t)nqa, h_medge, h_mpt, h_mkp};
+    const int ggrid = std::min(64, (std::max(n_edges, nq) + LM_NT - 1) / LM_NT);
+    lm_gather_kernel<<<ggrid, LM_NT, 0, st>>>(d_hdr, d_vedge, d_vpix, d_m, d_m + nqa, d_m + 2 * (size_t)nqa, d_vpt, d_kp, nq > 0 ? 1 : 0,
+                                              ho_ptrs);
+    CU_TRY(h, cudaGetLastError());
+    ++kernels;
     const double t_queued = cpu_us();
     CU_TRY(h, cudaStreamSynchronize(st));
     const double t_synced = cpu_us();
