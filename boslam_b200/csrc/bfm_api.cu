@@ -405,6 +405,17 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
                           h->plan_problems.size() == (size_t)n_problems &&
                           std::memcmp(h->plan_problems.data(), problems, sizeof(bfm_problem_t) * (size_t)n_problems) == 0;
+    if (!plan_hit) {
+        // output rows belong to exactly one problem (checked once per problem table: a cached plan was checked before)
+        std::vector<std::pair<int32_t, int32_t>> spans;
+        spans.reserve(n_problems);
+        for (int p = 0; p < n_problems; ++p)
+            if (problems[p].q_count > 0) spans.emplace_back(problems[p].out_begin, problems[p].q_count);
+        std::sort(spans.begin(), spans.end());
+        for (size_t i = 1; i < spans.size(); ++i)
+            if ((long long)spans[i - 1].first + spans[i - 1].second > spans[i].first)
+                return fail(h, BFM_ERR_INVALID, "two problems share output rows (out_begin ranges overlap)");
+    }
     if (!plan_hit && binned) {
         h->segs_host.clear();
         h->seg_begin.assign(2, 0);

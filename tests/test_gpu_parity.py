@@ -659,3 +659,20 @@ def test_two_threads_run_gated_batches_concurrently():
     [x.start() for x in th]
     [x.join() for x in th]
     assert not errs, errs
+
+
+def test_misuse_is_reported_through_the_abi(eng):
+    """Bad problem tables and options come back as BfmError with a message (no crash, no exception across the ABI)."""
+    q, t, _ = synth.correlated(64, 64, 1)
+    for tab, what in ((np.array([[0, 64, 0, 64, 0, 0], [0, 64, 0, 64, 32, 0]], np.int32), "overlap"),
+                      (np.array([[0, 65, 0, 64, 0, 0]], np.int32), "out of range"),
+                      (np.array([[0, 64, 10, 64, 0, 0]], np.int32), "out of range"),
+                      (np.array([[-1, 64, 0, 64, 0, 0]], np.int32), "out of range")):
+        with pytest.raises(bb.BfmError) as ei:
+            eng.match_batched(q, t, tab)
+        assert what in str(ei.value)
+    with pytest.raises(ValueError):
+        eng.match(q, t, k=3, ratio=0.8)
+    with pytest.raises((ValueError, bb.BfmError)):
+        eng.match(q, t, window=(np.zeros((3, 2), np.float32), np.zeros((64, 2), np.float32), 5.0))
+    _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t))   # still usable
