@@ -1,4 +1,4 @@
-"""Two-GPU check of the fused gather (kernel epilogue writes into NVLink peer memory).  Needs a box
+"""Multi-GPU check of the fused gather (kernel epilogue writes into NVLink peer memory).  Needs a box
 with >= 2 GPUs; skipped otherwise (the host-side sharding logic is covered on CPU with gloo)."""
 import os
 import socket
@@ -70,14 +70,15 @@ def _worker(rank, world, port, ret, multicast="1"):
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("multicast", ["1", "0"])     # NVSwitch multicast stores (where available) / per-peer stores
-def test_fused_gather_two_gpus(multicast):
+def test_fused_gather_all_gpus(multicast):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     mgr = ctx.Manager()
     ret = mgr.dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret, multicast)) for r in range(2)]
+    world = min(_n_gpus(), 8)                          # every GPU of the box: 2, 4 or 8 ranks
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret, multicast)) for r in range(world)]
     [p.start() for p in procs]
-    [p.join(300) for p in procs]
+    [p.join(600) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
-    assert ret.get(0) is True and ret.get(1) is True
+    assert all(ret.get(r) is True for r in range(world)), dict(ret)
