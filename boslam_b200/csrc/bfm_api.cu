@@ -127,6 +127,7 @@ struct bfm_handle_s {
     // tuning knobs
     int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0, pipeline_min_kb = 0;
     uint32_t *d_prog = nullptr;   // SM-fed upload: progress words of the feeder CTAs
+    uint32_t feed_epoch = 0;      // epoch of the last SM-fed call (1..65535)
     // pageable caller arrays: host threads stage them into pinned memory slice by slice for the feeders
     std::unique_ptr<WorkerPool> pool;
     void *h_stage = nullptr;
@@ -309,6 +310,7 @@ struct Gate {
     void *dst[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t bytes[4] = {0, 0, 0, 0};
     uint32_t *prog = nullptr;
+    uint32_t epoch = 0;
     const uint32_t *host_ready = nullptr;   // pinned word: rounds the host has staged so far (NULL: all staged)
 };
 
@@ -529,6 +531,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             sp.feed_bytes[a] = gate->bytes[a];
         }
         sp.feed_prog = gate->prog;
+        sp.feed_epoch = gate->epoch;
         sp.feed_stall = h->test_stall;
         sp.feed_host_ready = gate->host_ready;
     }

@@ -84,7 +84,9 @@ struct ScanParams {
     const uint4 *feed_src[4];                // host-mapped: q desc, t desc, q_xy, t_xy (NULL = absent)
     uint4 *feed_dst[4];                      // device copies
     unsigned long long feed_bytes[4];        // total bytes of each array
-    uint32_t *feed_prog;                     // [FEED_MAX] rounds completed per feeder CTA (zeroed before the launch)
+    uint32_t *feed_prog;                     // [FEED_MAX] (epoch << 16 | rounds completed) per feeder CTA
+    uint32_t feed_epoch;                     // this call's epoch (1..65535): words of earlier calls compare lower,
+                                             // so the progress words need no reset between calls
     int32_t feed_stall;                      // test hook: feeders deliver nothing, so the gate's time-out path runs
     const uint32_t *feed_host_ready;         // pinned host word: rounds staged by the host's worker threads so far
                                              // (pageable caller arrays); NULL = the sources are complete
@@ -465,7 +467,7 @@ __device__ __noinline__ void feed_rows(const ScanParams &p) {
         __syncthreads();
         if (tid == 0) {
             volatile uint32_t *prog = p.feed_prog + feeder;
-            *prog = (uint32_t)(r + 1);
+            *prog = (p.feed_epoch << 16) | (uint32_t)(r + 1);
         }
     }
 }
@@ -516,7 +518,8 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
                 if (rows <= per_round) return (rows + per_round / FEED_HEAD - 1) / (per_round / FEED_HEAD);
                 return FEED_HEAD - 1 + (rows + per_round - 1) / per_round;
             };
-            const int need = min(p.feed_rounds, max(round_of(q_need, p.feed_q_rows), round_of(t_need, p.feed_t_rows)));
+            const uint32_t need = (p.feed_epoch << 16) |
+                                  (uint32_t)min(p.feed_rounds, max(round_of(q_need, p.feed_q_rows), round_of(t_need, p.feed_t_rows)));
             const unsigned long long t0 = global_timer_ns();
             int ok = 1;
             uint32_t sleep_ns = 250u;
@@ -524,7 +527,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
                 uint32_t v = 0xFFFFFFFFu;
                 if (lane < p.n_feed) v = *(volatile const uint32_t *)(p.feed_prog + lane);
                 v = __reduce_min_sync(0xffffffffu, v);
-                if ((int)v >= need) break;
+                if (v >= need) break;
                 __nanosleep(sleep_ns);                      // back off: a thousand CTAs poll one cache line
                 sleep_ns = min(sleep_ns * 2u, 4000u);
                 if (global_timer_ns() - t0 > 4000000000ull) {

@@ -21,6 +21,15 @@
 // Small calls (a frame against a keyframe or the local map) use one copy on the compute stream and no gate.
 // BFM_TRACE=1 in the environment prints the per-call timeline.
 
+// progress words carry the call's epoch, so they are only zeroed when the 16-bit epoch wraps
+uint32_t next_feed_epoch(bfm_handle_t h, cudaStream_t st) {
+    if (++h->feed_epoch >= 65536u) {
+        cudaMemsetAsync(h->d_prog, 0, 128, st);
+        h->feed_epoch = 1;
+    }
+    return h->feed_epoch;
+}
+
 void ensure_pool(bfm_handle_t h) {
     if (h->pool || h->host_threads < 0) return;
     const int n = h->host_threads > 0 ? h->host_threads : (int)std::thread::hardware_concurrency() / 2;
@@ -118,7 +127,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         gate.status = h->h_status;
         *h->h_status = 0;
         gate.n_feed = h->feeders > 0 ? h->feeders : 24;
-        const int rows_per_round = h->feed_rows > 0 ? h->feed_rows : 8192;
+        const int rows_per_round = std::max(h->feed_rows > 0 ? h->feed_rows : 8192, std::max(nq_rows, nt_rows) / 60000 + 1);  // rounds fit 16 bits
         const int S = std::max(1, (std::max(nq_rows, nt_rows) + rows_per_round - 1) / rows_per_round);
         gate.rounds = S + bfm::FEED_HEAD - 1;   // the first round is delivered as FEED_HEAD short ones
         gate.q_rows = std::max(16, (((nq_rows + S - 1) / S) + 15) & ~15);
@@ -130,7 +139,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
             gate.src[3] = o->t_xy; gate.dst[3] = din + o_txy; gate.bytes[3] = txy_b;
         }
         gate.prog = h->d_prog;
-        CU_TRY(h, cudaMemsetAsync(h->d_prog, 0, 128, st));
+        gate.epoch = next_feed_epoch(h, st);
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
                         nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st, &gate);
         if (rc) {
@@ -161,7 +170,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         gate.status = h->h_status;
         *h->h_status = 0;
         gate.n_feed = h->feeders > 0 ? h->feeders : 24;
-        const int rows_per_round = h->feed_rows > 0 ? h->feed_rows : 8192;
+        const int rows_per_round = std::max(h->feed_rows > 0 ? h->feed_rows : 8192, std::max(nq_rows, nt_rows) / 60000 + 1);  // rounds fit 16 bits
         const int S = std::max(1, (std::max(nq_rows, nt_rows) + rows_per_round - 1) / rows_per_round);
         gate.rounds = S + bfm::FEED_HEAD - 1;
         gate.q_rows = std::max(16, (((nq_rows + S - 1) / S) + 15) & ~15);
@@ -218,7 +227,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
             });
         advance();   // leading rounds without bytes
         const double t_submitted = cpu_ms();
-        CU_TRY(h, cudaMemsetAsync(h->d_prog, 0, 128, st));
+        gate.epoch = next_feed_epoch(h, st);
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
                         nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st, &gate);
         const double t_launched = cpu_ms();

@@ -332,6 +332,12 @@ class Engine:
         res = BatchResult(mq, mt, md, mc, probs[:, 4].copy())
         return (idx, dist, res) if want_knn else res
 
+    def plan_batch(self, problems: np.ndarray, k: int = 1, ratio=None, cross_check: bool = False, max_distance=None,
+                   strict: bool = False) -> "BatchPlan":
+        """Validate a problem table and its options once; :meth:`BatchPlan.run` is then the bare library call
+        (for loops that match the same batch shape every step: loop closing, the bench's e2e leg)."""
+        return BatchPlan(self, problems, k, ratio, cross_check, max_distance, strict)
+
     def match_pairs(self, queries: Sequence, trains: Sequence, **kw):
         """Convenience over :meth:`match_batched` for lists of per-keyframe arrays.  Identical query
         objects are stored once (loop closing: one keyframe against many candidates)."""
@@ -514,6 +520,47 @@ class Engine:
         if want_knn:
             return out["knn_idx"], out["knn_dist"], res
         return res
+
+
+class BatchPlan:
+    """A validated (problem table, options) pair bound to an engine.  ``run(q, t, out)`` takes C-contiguous
+    uint8[rows, 32] host arrays and a :class:`HostBatchBuffers`; everything else was checked at construction."""
+
+    def __init__(self, engine: Engine, problems, k, ratio, cross_check, max_distance, strict):
+        probs = np.ascontiguousarray(problems, np.int32)
+        if probs.ndim != 2 or probs.shape[1] != 6:
+            raise ValueError("problems must be int32[P, 6]")
+        if k > 2:
+            raise NotImplementedError("BatchPlan covers the match-list form (k <= 2)")
+        self.engine, self.probs, self.P = engine, probs, probs.shape[0]
+        self.n_out = int((probs[:, 4] + probs[:, 1]).max()) if self.P else 0
+        self.nq_min = int((probs[:, 0] + probs[:, 1]).max()) if self.P else 0
+        self.nt_min = int((probs[:, 2] + probs[:, 3]).max()) if self.P else 0
+        self.opts, self.none_pass = engine._options(k, ratio, cross_check, max_distance, strict)
+        self.k = k
+        self._pp = probs.ctypes.data_as(ctypes.POINTER(_ffi.Problem))
+        self._opts_ref = ctypes.byref(self.opts)
+        self._offsets = probs[:, 4].copy()
+
+    def run(self, q: np.ndarray, t: np.ndarray, out: HostBatchBuffers) -> BatchResult:
+        if (q.dtype != np.uint8 or t.dtype != np.uint8 or not q.flags.c_contiguous or not t.flags.c_contiguous or
+                q.ndim != 2 or t.ndim != 2 or q.shape[1] != DESC_BYTES or t.shape[1] != DESC_BYTES or
+                q.shape[0] < self.nq_min or t.shape[0] < self.nt_min or (q.ctypes.data | t.ctypes.data) & 15):
+            raise ValueError("BatchPlan.run needs C-contiguous, 16-byte aligned uint8[rows, 32] arrays covering the planned rows")
+        if out.n_out < self.n_out or out.n_problems < self.P:
+            raise ValueError("out= buffers are too small for this batch")
+        eng = self.engine
+        if self.P and self.n_out:
+            m = out.m
+            with eng._lock:
+                rc = eng._lib.bfm_match_batched(eng._h, _ffi.MEM_HOST, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
+                                                self._pp, self.P, self.n_out, self._opts_ref, None, None, m[0].ctypes.data,
+                                                m[1].ctypes.data, m[2].ctypes.data, out.count.ctypes.data, None)
+                _ffi.check(eng._h, rc)
+        cnt = out.count[:self.P]
+        if self.none_pass:
+            cnt[:] = 0
+        return BatchResult(out.m[0], out.m[1], out.m[2], cnt, self._offsets)
 
 
 _default_engines = {}

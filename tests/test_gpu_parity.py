@@ -676,3 +676,23 @@ def test_misuse_is_reported_through_the_abi(eng):
     with pytest.raises((ValueError, bb.BfmError)):
         eng.match(q, t, window=(np.zeros((3, 2), np.float32), np.zeros((64, 2), np.float32), 5.0))
     _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t))   # still usable
+
+
+def test_batch_plan_fast_path(eng):
+    """Engine.plan_batch validates once; BatchPlan.run returns what match_batched returns."""
+    P, N = 10, 700
+    qp, tp = synth.keyframe_pair_batch(P, N, seed=61)
+    tab = bb.make_problems([N] * P, [N] * P)
+    out = bb.HostBatchBuffers(P * N, P, k=2)
+    for kw in (dict(k=2, ratio=0.8), dict(cross_check=True, max_distance=40), dict(k=1, max_distance=0, strict=True)):
+        plan = eng.plan_batch(tab, **kw)
+        want = eng.match_batched(qp, tp, tab, **kw)
+        for _ in range(3):
+            got = plan.run(qp, tp, out)
+            assert np.array_equal(got.counts, want.counts)
+            for p in range(P):
+                _eq(got[p], want[p], p)
+    with pytest.raises(ValueError):
+        plan.run(qp[:100], tp, out)
+    with pytest.raises(ValueError):
+        plan.run(qp.astype(np.int8), tp, out)
