@@ -140,8 +140,10 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         }
         gate.prog = h->d_prog;
         gate.epoch = next_feed_epoch(h, st);
+        const double t_prep = cpu_ms();
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
                         nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st, &gate);
+        const double t_launched = cpu_ms();
         if (rc) {
             cudaDeviceSynchronize();
             h->state_clean = false;
@@ -153,7 +155,8 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
             return fail(h, BFM_ERR_CUDA, "input gate timed out: the feeder CTAs did not deliver the descriptors");
         }
         h->info.copy_chunks = gate.rounds;
-        if (trace) std::fprintf(stderr, "[bfm trace] SM-fed upload: %d feeders, %d rounds, done %.3f ms (direct=%d)\n", gate.n_feed, gate.rounds, cpu_ms(), (int)direct);
+        if (trace) std::fprintf(stderr, "[bfm trace] SM-fed upload: %d feeders, %d rounds: prepared %.3f, kernel queued %.3f, done %.3f ms (direct=%d)\n",
+                                gate.n_feed, gate.rounds, t_prep, t_launched, cpu_ms(), (int)direct);
     } else if (G > 1 && h->feeders >= 0 && h->host_threads >= 0 && o->k <= 2) {
         // Pageable caller arrays: worker threads stage them into pinned memory round by round while the kernel
         // is already running; its feeder CTAs wait for the host's "rounds staged" word before each round.
