@@ -10,10 +10,10 @@ from ._ffi import BfmError, LIB_PATH  # noqa: F401
 from .bank import KeyframeBank  # noqa: F401
 from .engine import BatchPlan, BatchResult, Engine, HostBatchBuffers, PinnedBuffer, default_engine, make_problems  # noqa: F401
 from .localmap import CameraModel, MapStore, TrackResult, quaternion_from_rotation, select_representative  # noqa: F401
-from .matcher import NORM_HAMMING, BFMatcher, BFMatcher_create, DMatch  # noqa: F401
+from .matcher import NORM_HAMMING, BFMatcher, BFMatcher_create, DMatch, install, uninstall  # noqa: F401
 
 __all__ = ["BFMatcher", "BFMatcher_create", "DMatch", "NORM_HAMMING", "Engine", "BatchPlan", "BatchResult", "PinnedBuffer", "HostBatchBuffers",
-           "make_problems", "default_engine", "KeyframeBank", "MapStore", "CameraModel", "TrackResult", "select_representative", "match", "knn_match", "match_pairs", "BfmError", "synth"]
+           "make_problems", "default_engine", "KeyframeBank", "MapStore", "CameraModel", "TrackResult", "select_representative", "match", "knn_match", "match_pairs", "BfmError", "synth", "install", "uninstall"]
 
 
 def match(query, train, k=1, ratio=None, cross_check=False, mask=None, window=None, max_distance=None,

@@ -181,3 +181,42 @@ class BFMatcher:
 def BFMatcher_create(normType: int = NORM_HAMMING, crossCheck: bool = False, device: int = 0) -> BFMatcher:
     """Same spelling as ``cv2.BFMatcher_create`` (slam/tracking.py:45)."""
     return BFMatcher(normType, crossCheck, device)
+
+
+def install(cv2_module, device: int = 0):
+    """Route ``cv2_module.BFMatcher_create`` / ``cv2_module.BFMatcher`` to this engine for ``NORM_HAMMING`` (other
+    norms keep going to OpenCV).  boslam builds its matchers with exactly that call (``slam/tracking.py:45``,
+    ``slam/local_mapping.py:21``, ``slam/covisibility_graph.py:34``), so two lines at the top of ``slam/main.py``
+    switch the whole program over without touching the call sites::
+
+        import boslam_b200
+        boslam_b200.install(cv2)          # cv2 being the module slam/main.py already imported
+
+    The module is passed in (this package never imports cv2 itself).  :func:`uninstall` restores the originals."""
+    if getattr(cv2_module, "_boslam_b200_originals", None) is not None:
+        return
+    originals = (cv2_module.BFMatcher_create, cv2_module.BFMatcher)
+
+    def _create(normType=4, crossCheck=False):  # cv2's default norm is NORM_L2 (4)
+        if normType == NORM_HAMMING:
+            return BFMatcher(normType, crossCheck, device)
+        return originals[0](normType, crossCheck)
+
+    class _BFMatcherDispatch:
+        def __new__(cls, normType=4, crossCheck=False):
+            if normType == NORM_HAMMING:
+                return BFMatcher(normType, crossCheck, device)
+            return originals[1](normType, crossCheck)
+
+        create = staticmethod(_create)
+
+    cv2_module._boslam_b200_originals = originals
+    cv2_module.BFMatcher_create = _create
+    cv2_module.BFMatcher = _BFMatcherDispatch
+
+
+def uninstall(cv2_module):
+    originals = getattr(cv2_module, "_boslam_b200_originals", None)
+    if originals is not None:
+        cv2_module.BFMatcher_create, cv2_module.BFMatcher = originals
+        cv2_module._boslam_b200_originals = None

@@ -102,3 +102,24 @@ def test_struct_layout_against_the_c_header(tmp_path):
             _ffi.Outputs.multicast.offset, ctypes.sizeof(_ffi.TrackParams), _ffi.TrackParams.cos_max.offset,
             ctypes.sizeof(_ffi.LaunchInfo), _ffi.LaunchInfo.scan_ms.offset]
     assert got == want
+
+
+def test_install_routes_cv2_constructors():
+    """boslam_b200.install(cv2): NORM_HAMMING matchers come from this package (construction needs no GPU), other
+    norms still come from OpenCV; uninstall restores the originals."""
+    cv2 = pytest.importorskip("cv2")
+    orig_create, orig_cls = cv2.BFMatcher_create, cv2.BFMatcher
+    bb.install(cv2)
+    try:
+        m = cv2.BFMatcher_create(cv2.NORM_HAMMING, crossCheck=True)          # slam/tracking.py:45, verbatim
+        assert isinstance(m, bb.BFMatcher) and m.crossCheck is True
+        assert isinstance(cv2.BFMatcher(cv2.NORM_HAMMING), bb.BFMatcher)
+        assert isinstance(cv2.BFMatcher.create(cv2.NORM_HAMMING, True), bb.BFMatcher)
+        l2 = cv2.BFMatcher_create(cv2.NORM_L2)
+        assert not isinstance(l2, bb.BFMatcher)
+        a = np.random.default_rng(0).random((5, 8)).astype(np.float32)
+        assert len(l2.match(a, a)) == 5                                       # OpenCV still does the float norms
+        bb.install(cv2)                                                       # idempotent
+    finally:
+        bb.uninstall(cv2)
+    assert cv2.BFMatcher_create is orig_create and cv2.BFMatcher is orig_cls
