@@ -696,3 +696,28 @@ def test_batch_plan_fast_path(eng):
         plan.run(qp[:100], tp, out)
     with pytest.raises(ValueError):
         plan.run(qp.astype(np.int8), tp, out)
+
+
+@pytest.mark.skipif(not ref.HAVE_CV2, reason="cv2 not importable")
+def test_installed_into_cv2_call_sites_run_verbatim():
+    """boslam_b200.install(cv2): the reference's own lines (slam/tracking.py:45,56-60) run unchanged on this
+    engine and produce what OpenCV produces."""
+    import cv2
+    d_hamming_max = 30                                                # config.py:13
+    frame_des, kf_des, _ = synth.correlated(600, 600, 71)             # camera.py:50: nfeatures=600
+
+    def call_site():
+        matcher = cv2.BFMatcher_create(cv2.NORM_HAMMING, crossCheck=True)           # slam/tracking.py:45
+        matches = matcher.match(frame_des, kf_des)                                  # :56
+        matches = [_ for _ in matches if _.distance < d_hamming_max]                # :57
+        inds_f, inds_kf = zip(*((_.queryIdx, _.trainIdx) for _ in matches))         # :60
+        return type(matcher), inds_f, inds_kf, [m.distance for m in matches]
+
+    theirs = call_site()
+    bb.install(cv2)
+    try:
+        mine = call_site()
+    finally:
+        bb.uninstall(cv2)
+    assert mine[0] is bb.BFMatcher and theirs[0] is not bb.BFMatcher
+    assert mine[1:] == theirs[1:] and len(mine[1]) > 100
