@@ -81,7 +81,10 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
     const size_t m_b = want_m ? align256((size_t)n_out_rows * 4) : 0;
     const size_t cnt_b = want_m ? align256((size_t)n_problems * 4) : 0;
     const size_t out_total = 2 * knn_b + 3 * m_b + cnt_b;
-    const bool direct = (!want_knn || (host_ptr_is_pinned(user.knn_idx) && host_ptr_is_pinned(user.knn_dist) &&
+    // small results always go through the staging block: asking the driver whether four or six pointers are pinned
+    // (~1 us each) costs more than copying a few kilobytes
+    const bool direct = out_total >= ((size_t)256 << 10) &&
+                        (!want_knn || (host_ptr_is_pinned(user.knn_idx) && host_ptr_is_pinned(user.knn_dist) &&
                                        ((reinterpret_cast<uintptr_t>(user.knn_idx) | reinterpret_cast<uintptr_t>(user.knn_dist)) & 7) == 0)) &&
                         (!want_m || (host_ptr_is_pinned(user.m_query) && host_ptr_is_pinned(user.m_train) &&
                                      host_ptr_is_pinned(user.m_dist) && host_ptr_is_pinned(user.m_count)));
