@@ -44,3 +44,28 @@ def test_b200_arm_refuses_to_run_without_a_gpu():
         pytest.skip("torch not importable")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CPU path" in (out.stderr + out.stdout)
+
+
+@pytest.mark.gpu
+def test_b200_arm_line_has_every_contract_key():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-extras"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert "impl" not in d and d["metric"] == "hamming_pairs_per_s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "u32" and d["data"] == "synthetic"
+    assert d["config"]["workload"] == "loop_closing" and "l2" in d["config"]
+    assert d["gpu_launches"] == 3                                    # one kernel per step
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["frac"] > 0.5 and r["traffic"] and r["hbm"]["peak"] > 0
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 30e6 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+    c = d["clocks"]
+    assert "sm_mhz" in c and "reasons" in c
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0
+    assert d["value"] / cb["value"] > 50                             # a GPU run that is not far above the host is not a GPU run
