@@ -7,15 +7,19 @@ JSON line from rank 0.  ``--impl reference`` times the reference's own implement
 
 Workload (config.workload = "loop_closing"): BASELINE.json configs[3], the configuration the
 metric's "at 1/2/4/8 B200" is quoted on: 256 BoW-candidate keyframe pairs x (2000 x 2000) ORB
-descriptors, knn k=2 + ratio 0.8, one batched launch per step; weak scaling (every rank runs its
-own 256 pairs, then the fixed-shape match tables are all-gathered over NCCL).  A "step" is one
-pass of the hot path over one batch; 1.024 G descriptor pairs per step per GPU.  The tracking
-(configs[1]), frame-to-frame (configs[0]) and local-mapping (configs[2]) shapes are reported as
-extra keys of the same line ("frames").
+descriptors, knn k=2 + ratio 0.8, ONE kernel launch per step; weak scaling (every rank runs its
+own 256 pairs; every rank ends up with every rank's match tables, written by the kernel epilogue into
+all ranks' symmetric buffers - NVSwitch multicast stores where available - plus an overlapped barrier;
+BFM_GATHER=nccl selects a plain NCCL all_gather instead).  A "step" is one pass of the hot path over one
+batch; 1.024 G descriptor pairs per step per GPU.  The tracking (configs[1]), frame-to-frame (configs[0],
+with and without the CPU solvePnPRansac), local-mapping (configs[2]) shapes and the device-resident
+local-map step are reported as extra keys of the same line ("frames"); configs[4] (the size sweep) is
+tools/size_sweep.py -> profiles/size_sweep_r01.json.
 
   value      pairs/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e        same metric through the public host API (numpy in -> numpy out, pinned host input
-             buffers, H2D + D2H inside the timed region)
+  e2e        same metric through the public host API (Engine.plan_batch(...).run: numpy in -> numpy out,
+             pinned host buffers; the step's inputs are read from host memory and its results written to
+             host memory inside the timed region, by the kernel itself)
   roofline   scan kernel vs the measured POPC issue peak (integer pipe; 8 POPC per pair is the
              algorithmic count) - plus the HBM view for context
   cpu_baseline  cv2.BFMatcher.knnMatch(k=2) + Python ratio test on the host cores (N = 1 only)
