@@ -118,7 +118,7 @@ class FusedGather:
         self.step = 0
         self._torch = torch
         self._side = torch.cuda.Stream(device=dev)
-        self._barrier_done = []          # event of barrier n (index n)
+        self._barrier_done = {}          # step -> event of that step's barrier (the last few steps only)
         torch.cuda.synchronize(dev)
         self.hdl.barrier()
         torch.cuda.synchronize(dev)
@@ -162,9 +162,8 @@ class FusedGather:
             self.hdl.barrier()
             done = torch.cuda.Event()
             done.record(self._side)
-        self._barrier_done.append(done)
-        if len(self._barrier_done) > 4 * self.SLOTS:       # keep indices aligned: replace old events by None
-            self._barrier_done[len(self._barrier_done) - 4 * self.SLOTS - 1] = None
+        self._barrier_done[self.step] = done
+        self._barrier_done.pop(self.step - 4 * self.SLOTS, None)
         self.step += 1
 
     def wait(self, step=None):
