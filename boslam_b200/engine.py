@@ -1,7 +1,9 @@
 """Host side of the matcher: a thin, typed layer over the C ABI (include/bfm.h).
 
 ``Engine`` owns one ``bfm_handle_t`` (own CUDA stream + workspace).  Inputs are either numpy
-arrays (host path: pinned staging + H2D/D2H inside the call) or CUDA ``torch.Tensor`` s (device
+arrays (host path: the upload overlaps the call's single kernel launch - pinned arrays are streamed by the
+kernel's own feeder CTAs, pageable ones are staged by a small host thread pool - and the kernel writes the
+results into pinned host memory) or CUDA ``torch.Tensor`` s (device
 path: zero-copy via ``data_ptr`` on torch's current stream).  All arithmetic happens in the CUDA
 library; nothing here computes distances.
 
