@@ -173,3 +173,36 @@ def test_gates_strict_and_nonstrict():
     a = orc.match(q, t, cross_check_=True, max_distance=10, strict=True)
     b = orc.match(q, t, cross_check_=True, max_distance=10, strict=False)
     assert np.array_equal(a[0], qi[d < 10]) and np.array_equal(b[0], qi[d <= 10])
+
+
+# ---- property tests: the two restatements (numpy, plain C) must agree with each other on anything -------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(nq=st.integers(1, 40), nt=st.integers(1, 60), k=st.integers(1, 5), seed=st.integers(0, 10 ** 6),
+       kind=st.sampled_from(["uniform", "ties", "dups"]), masked=st.booleans())
+def test_numpy_and_c_oracles_agree(nq, nt, k, seed, kind, masked):
+    from oracle import c_oracle
+    if kind == "uniform":
+        q, t = synth.uniform(nq, seed), synth.uniform(nt, seed + 1)
+    elif kind == "ties":
+        q, t = synth.tie_stress(nq, seed), synth.tie_stress(nt, seed + 1)
+    else:
+        q, t = synth.uniform(nq, seed), synth.duplicate_rows(max(1, nt // 2), seed + 1)
+    mask = None
+    if masked:
+        mask = (np.random.default_rng(seed).random((nq, len(t))) < 0.5).astype(np.uint8)
+    ai, ad = orc.knn(q, t, k, mask)
+    bi, bd = c_oracle.knn(q, t, k, mask)
+    assert np.array_equal(ai, bi) and np.array_equal(ad, bd)
+    # rows ascend by (distance, index); unfilled slots are -1 and trail
+    for i in range(nq):
+        keys = [(int(d), int(j)) for d, j in zip(ad[i], ai[i]) if j >= 0]
+        assert keys == sorted(keys) and all(j == -1 for j in ai[i][len(keys):])
+    a = orc.cross_check(q, t, mask) if hasattr(orc, "cross_check") else orc.match(q, t, cross_check_=True, mask=mask)
+    b = c_oracle.cross_check(q, t, mask)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # a cross-check match is mutual: the reverse problem contains the mirrored pair
+    ra = orc.match(t, q, cross_check_=True, mask=None if mask is None else np.ascontiguousarray(mask.T))
+    assert set(zip(a[0].tolist(), a[1].tolist())) == set(zip(ra[1].tolist(), ra[0].tolist()))
