@@ -506,11 +506,15 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("loop_closing_scan_bytes")
     except Exception:
         pass
+    popc_issued = 4 if info["popc_mode"] in (4, 40) else (5 if info["popc_mode"] in (5, 50) else info["popc_mode"])
     roofline = {
         "bound": "int_popc", "kernel": "bfm_scan_kernel", "achieved": achieved_popc / 1e9, "peak": popc["ops_per_s"] / 1e9,
         "unit": "GPOPC/s", "frac": achieved_popc / popc["ops_per_s"], "traffic": traffic,
         "algorithmic": "8 POPC per descriptor pair x 1.024e9 pairs per launch",
-        "popc_issued_per_pair": 4 if info["popc_mode"] in (4, 40) else (5 if info["popc_mode"] in (5, 50) else info["popc_mode"]),
+        "popc_issued_per_pair": popc_issued,
+        # the same launch against what the kernel really issues (carry-save tree: 4 POPC per pair, not 8):
+        # how close the XU pipe is to saturation, measured live; ncu's pipe-busy figure is in issue_bound
+        "frac_issued": achieved_popc * popc_issued / 8 / popc["ops_per_s"],
         "popc_mode": info["popc_mode"],
         "issue_bound": {"pipe": "xu (POPC)", "busy_pct": 88.2, "alu_busy_pct": 82.6,
                         "source": "profiles/r01c_ncu_scan_fused_pm40_k2.md (ncu --set full of this command)"},

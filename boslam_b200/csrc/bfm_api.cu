@@ -34,7 +34,10 @@ using bfm::Segment;
 constexpr int NT = 128;          // threads per scan CTA
 constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
 constexpr int N_TABLE_SLOTS = 4;
-constexpr int BIG_FINALIZE_ROWS = 8192;  // a single problem with this many query rows is finalized by tile-parallel kernels
+// a call that is ONE problem with this many query rows is finalized by the tile-parallel kernels: the single
+// finalizing CTA costs ~2.5 us per 1024 rows, two more launches ~3.5 us (tools/finalize_probe.py: 1000 rows
+// 18.6 vs 22.0 us, 2000 x 20000 cross-check 73.8 vs 66.7 us, 4096 x 4096 52 vs 42 us)
+constexpr int BIG_FINALIZE_ROWS = 1792;
 constexpr int MAX_COPY_CHUNKS = 64;  // input chunks of the pipelined host path
 
 std::string g_create_error;
@@ -125,7 +128,7 @@ struct bfm_handle_s {
     unsigned long long seq = 0;              // call sequence number (watermark epoch)
 
     // tuning knobs
-    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0, pipeline_min_kb = 0;
+    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0, pipeline_min_kb = 0, finalize_rows = 0;
     uint32_t *d_prog = nullptr;   // SM-fed upload: progress words of the feeder CTAs
     uint32_t feed_epoch = 0;      // epoch of the last SM-fed call (1..65535)
     // pageable caller arrays: host threads stage them into pinned memory slice by slice for the feeders
@@ -451,7 +454,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         if (rc) return rc;
     }
     // one very large problem: tile-parallel finalize kernels instead of the single finalizing CTA
-    const bool defer = !binned && n_problems == 1 && problems[0].q_count >= BIG_FINALIZE_ROWS && problems[0].t_count > 0 && n_dests >= 1;
+    const bool defer = !binned && n_problems == 1 && problems[0].q_count >= (h->finalize_rows > 0 ? h->finalize_rows : BIG_FINALIZE_ROWS) && problems[0].t_count > 0 && n_dests >= 1;
     const int fin_tiles = defer ? (problems[0].q_count + bfm::FT_ROWS - 1) / bfm::FT_ROWS : 0;
     uint8_t *d_keep = nullptr;
     int32_t *d_tile = nullptr;
@@ -837,6 +840,9 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "window_bins") {
         if (value != 0 && value != 1) return fail(h, BFM_ERR_INVALID, "window_bins must be 0 (auto) or 1 (brute force)");
         h->window_bins = value;
+    } else if (k == "finalize_rows") {
+        if (value < 0) return fail(h, BFM_ERR_INVALID, "finalize_rows must be >= 0");
+        h->finalize_rows = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");
         h->waves = value;

@@ -814,10 +814,12 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     }
 }
 
-// ---- tile-parallel finalize for ONE very large problem (Q >= 8192 rows: the brute-force sweep) ------------
-// The in-kernel finalize is one CTA per problem, which is right for keyframe-sized problems (a few
-// thousand rows) and serial for 64k rows.  Here tiles of FT_ROWS rows run in parallel: fin_count decodes,
-// writes the knn table, decides keep and counts per tile; fin_write places the kept rows after the kept
+// ---- tile-parallel finalize for ONE problem on its own (Q >= 1792 rows: a tracking frame, the sweep) ------
+// The in-kernel finalize is one CTA per problem, which is right for a batch of keyframe pairs (one
+// finalizing CTA per pair, all in parallel) and serial when the call is a single problem: ~2.5 us per
+// 1024 rows (tools/finalize_probe.py), against ~3.5 us for two more launches.  Here tiles of FT_ROWS rows
+// run in parallel: fin_count decodes, writes the knn table, decides keep and counts per tile; fin_write
+// places the kept rows after the kept
 // rows of all earlier tiles (ascending queryIdx is preserved) and restores the workspace.
 constexpr int FT_NT = 256, FT_RPT = 4, FT_ROWS = FT_NT * FT_RPT;
 
@@ -839,9 +841,14 @@ __global__ void __launch_bounds__(FT_NT) fin_count_kernel(const __grid_constant_
             int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
             if (!ki) continue;
             const bool mc = (p.dest_multicast >> d) & 1u;
-            put_i32(ki + o, idx1, mc);
-            put_i32(kd + o, d1, mc);
-            if (p.knn_cols > 1) { put_i32(ki + o + 1, idx2, mc); put_i32(kd + o + 1, d2, mc); }
+            if (k == 2 && !mc) {   // 8-byte aligned: o is even
+                *reinterpret_cast<int2 *>(ki + o) = make_int2(idx1, idx2);
+                *reinterpret_cast<int2 *>(kd + o) = make_int2(d1, d2);
+            } else {
+                put_i32(ki + o, idx1, mc);
+                put_i32(kd + o, d1, mc);
+                if (p.knn_cols > 1) { put_i32(ki + o + 1, idx2, mc); put_i32(kd + o + 1, d2, mc); }
+            }
         }
         if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
         bool kp = has1;

@@ -236,7 +236,8 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
  *       "feeders" {0=auto (24), -1=off: copy-engine chunks, n <= 32}, "feed_rows" {0=auto, rows per feed round},
  *       "host_threads" {0=auto (<= 8), -1=off, n: staging threads for pageable caller arrays},
  *       "pipeline_min_kb" {0=auto (1024): smallest upload, in KB, that overlaps the kernel},
- *       "window_bins" {0=auto, 1=brute-force window kernel} */
+ *       "window_bins" {0=auto, 1=brute-force window kernel},
+ *       "finalize_rows" {0=auto (1792): query rows from which ONE problem is finalized by the tile-parallel kernels} */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t bfm_kernel_launch_count(bfm_handle_t h);

@@ -510,8 +510,56 @@ def test_binned_window_search_equals_brute_force(eng, case):
     _eq(eng.knn(q, t, 2, window=win), (oi, od), case)
 
 
+def test_finalize_paths_agree(eng):
+    """A call that is one problem of >= 1792 query rows is finalized by the tile-parallel kernels, a smaller
+    one by the CTA that completes it.  Forced both ways (finalize_rows knob) every mode must return the same
+    bits as the oracle: plain, ratio, gate, cross-check, dense mask, window, k = 3, device tensors, and the
+    local-map step (train count decided on the device)."""
+    import torch
+    q, t, qxy, txy, dense = synth.window_scene(2100, 2600, 77)
+    win = (qxy, txy, 15.0)
+    rng = np.random.default_rng(3)
+    mask = (rng.random((2100, 2600)) < 0.3).astype(np.uint8) * 255
+    want = dict(knn3=c_oracle.knn(q, t, 3), cc=c_oracle.cross_check(q, t), ratio=orc.match(q, t, k=2, ratio=0.8),
+                gate=orc.match(q, t, cross_check_=True, max_distance=40), mknn=c_oracle.knn(q, t, 2, mask),
+                ccm=orc.match(q, t, cross_check_=True, mask=mask), wknn=c_oracle.knn(q, t, 2, dense),
+                wratio=orc.match(q, t, k=2, ratio=0.8, mask=dense))
+    sc = synth.local_map_scene(6000, 6000, 2000, seed=5)
+    store = bb.MapStore(6000, engine=eng)
+    store.update(np.arange(6000), sc["desc"], sc["pt3d"], sc["normal"])
+    targs = (sc["des"], sc["kp"], sc["R"], sc["t"], sc["see_vector"], sc["edges"])
+    tracks = []
+    try:
+        for thr, kernels in ((1 << 30, 1), (1, 3)):
+            eng.set_tuning(finalize_rows=thr)
+            _eq(eng.knn(q, t, 3), want["knn3"], thr)
+            assert eng.launch_info()["kernels_launched"] == 2 * kernels
+            _eq(eng.match(q, t, cross_check=True), want["cc"], thr)
+            assert eng.launch_info()["kernels_launched"] == kernels
+            _eq(eng.match(q, t, k=2, ratio=0.8), want["ratio"], thr)
+            _eq(eng.match(q, t, cross_check=True, max_distance=40), want["gate"], thr)
+            _eq(eng.knn(q, t, 2, mask=mask), want["mknn"], thr)
+            _eq(eng.match(q, t, cross_check=True, mask=mask), want["ccm"], thr)
+            eng.set_tuning(window_bins=1)                                # brute-force window kernel
+            _eq(eng.knn(q, t, 2, window=win), want["wknn"], thr)
+            _eq(eng.match(q, t, k=2, ratio=0.8, window=win), want["wratio"], thr)
+            eng.set_tuning(window_bins=0)
+            qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+            idx, dist = eng.knn(qd, td, 2)
+            _eq((idx.cpu().numpy(), dist.cpu().numpy()), (want["knn3"][0][:, :2], want["knn3"][1][:, :2]), thr)
+            r = store.track(*targs)
+            r2 = store.track(*targs, cross_check=False, k=2, ratio=0.8, max_distance=None, window_radius=15.0)
+            tracks.append([np.array(x) for x in (r.visible_edges, r.inds_frame, r.inds, r.distance, r.pts3d, r.kp,
+                                                 r2.inds_frame, r2.inds, r2.distance)])
+            _eq(eng.match(q[:300], t[:500], cross_check=True), c_oracle.cross_check(q[:300], t[:500]), thr)   # clean workspace
+        _eq(tracks[0], tracks[1], "local-map step")
+        assert len(tracks[0][1]) > 0 and len(tracks[0][6]) > 0
+    finally:
+        eng.set_tuning(finalize_rows=0, window_bins=0)
+
+
 def test_large_single_problem_tile_parallel_finalize(eng):
-    """A single problem with >= 8192 query rows is finalized by the tile-parallel kernels (the in-kernel
+    """A single problem with many query rows is finalized by the tile-parallel kernels (the in-kernel
     finalize is one CTA per problem): same results, workspace left clean for the next call."""
     q, t, _ = synth.correlated(9001, 700, 123)
     oi, od = c_oracle.knn(q, t, 3)

@@ -16,6 +16,8 @@ import boslam_b200 as bb  # noqa: E402
 from boslam_b200 import synth  # noqa: E402
 
 SIZES = [1024, 4096, 16384, 65536]
+if "--full" in sys.argv:      # every power of two, as BASELINE config 5 words it
+    SIZES = [1024 << i for i in range(7)]
 
 
 def main():
@@ -58,7 +60,7 @@ def main():
                 out.append(dict(Q=nq, T=nt, self_match_ok=ok_self, self_cross_check_identity=ok_cc))
                 assert ok_self and ok_cc
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/size_sweep.json", "w"), indent=1)
+    json.dump(out, open("gpurun_out/size_sweep_full.json" if "--full" in sys.argv else "gpurun_out/size_sweep.json", "w"), indent=1)
 
 
 if __name__ == "__main__":
