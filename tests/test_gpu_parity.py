@@ -516,8 +516,9 @@ def test_finalize_paths_agree(eng):
     bits as the oracle: plain, ratio, gate, cross-check, dense mask, window, k = 3, device tensors, and the
     local-map step (train count decided on the device)."""
     import torch
-    q, t, qxy, txy, dense = synth.window_scene(2100, 2600, 77)
+    q, t, qxy, txy, _ = synth.window_scene(2100, 2600, 77)
     win = (qxy, txy, 15.0)
+    dense = orc.window_mask(qxy, txy, 15.0)
     rng = np.random.default_rng(3)
     mask = (rng.random((2100, 2600)) < 0.3).astype(np.uint8) * 255
     want = dict(knn3=c_oracle.knn(q, t, 3), cc=c_oracle.cross_check(q, t), ratio=orc.match(q, t, k=2, ratio=0.8),
