@@ -63,6 +63,28 @@ def _worker(rank, world, port, ret, multicast="1"):
                     ok = ok and np.array_equal(tb["m"][r, 1, p * N:p * N + c], want[1])
                     ok = ok and np.array_equal(tb["knn_idx"][r, p * N:(p + 1) * N], oi)
                     ok = ok and np.array_equal(tb["knn_dist"][r, p * N:(p + 1) * N], od)
+        # one problem on its own, large enough for the tile-parallel finalize kernels (>= 1792 query rows):
+        # fin_count / fin_write write the same peer / multicast destinations
+        N1 = 2100
+        fg1 = FusedGather(N1, 1, k=2, want_knn=True)
+        tab1 = bb.make_problems([N1], [N1])
+        data = [synth.correlated(N1, N1, 900 + r)[:2] for r in range(world)]
+        q, t = data[rank]
+        for step in range(2):
+            fg1.run(eng, torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda(), tab1, k=2, ratio=0.8)
+            ok = ok and eng.launch_info()["kernels_launched"] == 3
+            fg1.barrier()
+            fg1.wait()
+            torch.cuda.synchronize()
+            tb = {k: v.cpu().numpy() for k, v in fg1.tables().items()}
+            for r in range(world):
+                a, b = data[r]
+                oi, od = c_oracle.knn(a, b, 2)
+                want = orc.match(a, b, k=2, ratio=0.8)
+                c = int(tb["count"][r, 0])
+                ok = ok and c == len(want[0])
+                ok = ok and np.array_equal(tb["m"][r, 0, :c], want[0]) and np.array_equal(tb["m"][r, 1, :c], want[1])
+                ok = ok and np.array_equal(tb["knn_idx"][r], oi) and np.array_equal(tb["knn_dist"][r], od)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
