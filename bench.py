@@ -516,8 +516,8 @@ def main():
         # how close the XU pipe is to saturation, measured live; ncu's pipe-busy figure is in issue_bound
         "frac_issued": achieved_popc * popc_issued / 8 / popc["ops_per_s"],
         "popc_mode": info["popc_mode"],
-        "issue_bound": {"pipe": "xu (POPC)", "busy_pct": 88.2, "alu_busy_pct": 82.6,
-                        "source": "profiles/r01c_ncu_scan_fused_pm40_k2.md (ncu --set full of this command)"},
+        "issue_bound": {"pipe": "xu (POPC)", "busy_pct": 89.3, "alu_busy_pct": 83.6,
+                        "source": "profiles/r01e_ncu_scan_final.md (ncu --set full of this command)"},
         "scan_ms": scan_avg, "scan_share_of_step": scan_avg / (ms / args.steps),
         "peak_source": "measured in this run: bfm_microbench POPC probe (16 POPC/clk/SM x 148 SMs x SM clock)",
         "popc_per_clk_per_sm": popc["ops_per_clk_per_sm"],
