@@ -33,6 +33,11 @@ using bfm::Segment;
 
 constexpr int NT = 128;          // threads per scan CTA
 constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
+// tapered tail of a batch (>= 8 problems): the last 10 % of the work is cut into segments of 1/2, then 1/4 of the
+// length - 256-pair batch 1046 -> 1026 us (980 -> 998 G pairs/s), pinned host path 1120 -> 1104 us
+// (tools/taper_probe.py, profiles/r01f_taper_probe.log)
+constexpr int TAPER_AUTO = 4;
+constexpr int TAPER_PCT_AUTO = 10;
 constexpr int N_TABLE_SLOTS = 4;
 // a call that is ONE problem with this many query rows is finalized by the tile-parallel kernels: the single
 // finalizing CTA costs ~2.5 us per 1024 rows, two more launches ~3.5 us (tools/finalize_probe.py: 1000 rows
@@ -128,7 +133,7 @@ struct bfm_handle_s {
     unsigned long long seq = 0;              // call sequence number (watermark epoch)
 
     // tuning knobs
-    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0, pipeline_min_kb = 0, finalize_rows = 0;
+    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0, pipeline_min_kb = 0, finalize_rows = 0, taper = 0, taper_pct = 0;
     uint32_t *d_prog = nullptr;   // SM-fed upload: progress words of the feeder CTAs
     uint32_t feed_epoch = 0;      // epoch of the last SM-fed call (1..65535)
     // pageable caller arrays: host threads stage them into pinned memory slice by slice for the feeders
@@ -146,7 +151,7 @@ struct bfm_handle_s {
     std::vector<Problem> probs_host, plan_probs;
     // plan cache + workspace hygiene
     bool plan_valid = false, state_clean = false;
-    int plan_sig[6] = {0, 0, 0, 0, 0, 0};
+    int plan_sig[7] = {0, 0, 0, 0, 0, 0, 0};
     int plan_seg_rows = 0;
     std::vector<bfm_problem_t> plan_problems;
     // pipelined host path: the copy-in stream
@@ -247,6 +252,12 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
         }
     }
     *seg_rows_out = L;
+    // taper knob: 0 = auto, 1 = off, 2 / 4 / 8 = finest divisor of the segment length in the tail
+    const int taper_div = (h->segment_rows > 0 || n_problems < 8) ? 1 : (h->taper > 0 ? h->taper : TAPER_AUTO);
+    int taper_levels = 0;
+    while ((1 << (taper_levels + 1)) <= taper_div) ++taper_levels;
+    const double taper_frac = (h->taper_pct > 0 ? h->taper_pct : TAPER_PCT_AUTO) / 100.0;
+    long long cum = 0;
     segs.clear();
     seg_begin.assign((size_t)n_problems + 1, 0);
     for (int p = 0; p < n_problems; ++p) {
@@ -262,7 +273,20 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
             seg_begin[p + 1] = (int)segs.size();
             continue;
         }
-        const int nsp = (pr.t_count + L - 1) / L;
+        // tapered tail: the problems that make up the last part of the batch are cut finer, so the CTAs that
+        // finish the launch are short and the SMs run dry together (all CTAs of one launch cost the same, their
+        // start times drift apart, and the finishing times of the last wave spread over one CTA duration)
+        int Lp = L;
+        if (taper_div > 1 && steps > 0) {
+            const double f = (double)cum / (double)steps;            // where this problem starts in the batch
+            const double tail0 = 1.0 - taper_frac;
+            if (f >= tail0) {
+                const int level = 1 + (int)((f - tail0) / taper_frac * taper_levels);
+                Lp = std::max(MIN_SEG_ROWS, L >> std::min(level, taper_levels));
+            }
+        }
+        cum += (long long)((pr.q_count + bq - 1) / bq) * pr.t_count;
+        const int nsp = (pr.t_count + Lp - 1) / Lp;
         const int base = pr.t_count / nsp, rem = pr.t_count % nsp;
         for (int qb = 0; qb * bq < pr.q_count; ++qb) {
             int t0 = 0;
@@ -406,7 +430,8 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
-    const int plan_sig[6] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots};
+    const int plan_sig[7] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots,
+                             h->taper * 1000 + h->taper_pct};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
                           h->plan_problems.size() == (size_t)n_problems &&
                           std::memcmp(h->plan_problems.data(), problems, sizeof(bfm_problem_t) * (size_t)n_problems) == 0;
@@ -843,6 +868,12 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "finalize_rows") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "finalize_rows must be >= 0");
         h->finalize_rows = value;
+    } else if (k == "taper") {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(h, BFM_ERR_INVALID, "taper must be 0 (auto), 1 (off), 2, 4 or 8");
+        h->taper = value;
+    } else if (k == "taper_pct") {
+        if (value < 0 || value > 90) return fail(h, BFM_ERR_INVALID, "taper_pct must be 0 (auto) .. 90");
+        h->taper_pct = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");
         h->waves = value;

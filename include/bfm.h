@@ -237,6 +237,8 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
  *       "host_threads" {0=auto (<= 8), -1=off, n: staging threads for pageable caller arrays},
  *       "pipeline_min_kb" {0=auto (1024): smallest upload, in KB, that overlaps the kernel},
  *       "window_bins" {0=auto, 1=brute-force window kernel},
+ *       "taper" {0=auto (4), 1=off, 2, 4, 8: finest divisor of the segment length in the tail of a batch},
+ *       "taper_pct" {0=auto (10): percent of the batch's work, at its end, that is cut finer},
  *       "finalize_rows" {0=auto (1792): query rows from which ONE problem is finalized by the tile-parallel kernels} */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */
