@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "bfm_abi_version", "bfm_create", "bfm_destroy", "bfm_last_error", "bfm_match_batched", "bfm_knn",
     "bfm_match", "bfm_match_batched_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
     "bfm_device_info", "bfm_host_alloc", "bfm_host_free", "bfm_map_create", "bfm_map_destroy", "bfm_map_update",
-    "bfm_track_local_map", "bfm_select_representative",
+    "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview",
 )
 
 
@@ -112,6 +112,8 @@ def lib():
                                       ctypes.c_int]
         L.bfm_host_alloc.argtypes = [ctypes.c_uint64, ctypes.POINTER(vp)]
         L.bfm_host_free.argtypes = [vp]
+        L.bfm_plan_preview.argtypes = [ctypes.POINTER(Problem), i32, i32, i32, i32, i32, i32, i32, vp, i32,
+                                       ctypes.POINTER(i32), ctypes.POINTER(i32)]
         if L.bfm_abi_version() != ABI_VERSION:
             raise ImportError(f"{LIB_PATH}: ABI version {L.bfm_abi_version()} != {ABI_VERSION}; rebuild")
         _lib = L
@@ -153,3 +155,24 @@ def device_info(device: int = 0):
     if rc != BFM_OK:
         raise BfmError(rc, "bfm_device_info failed (no CUDA device?)")
     return {"sm_count": sm.value, "cc": (ma.value, mi.value), "clock_khz": khz.value, "name": name.value.decode()}
+
+
+def plan_preview(problems, queries_per_thread: int = 4, slots: int = 148 * 8, segment_rows: int = 0, waves: int = 0,
+                 taper: int = 0, taper_pct: int = 0):
+    """The work items (one per CTA) the planner cuts a batch into - host only, no GPU needed.
+    ``problems``: int32[P, 6] as :func:`boslam_b200.make_problems` builds it.  Returns (items int32[n, 8] =
+    {q_row0, q_valid, q_local0, out_row0, t_row0, t_count, t_local0, problem}, segment_rows)."""
+    import numpy as np
+    L = lib()
+    tab = np.ascontiguousarray(problems, dtype=np.int32).reshape(-1, 6)
+    pp = tab.ctypes.data_as(ctypes.POINTER(Problem))
+    n, rows = ctypes.c_int32(), ctypes.c_int32()
+    args = (pp, len(tab), queries_per_thread, slots, segment_rows, waves, taper, taper_pct)
+    rc = L.bfm_plan_preview(*args, None, 0, ctypes.byref(n), ctypes.byref(rows))
+    if rc != BFM_OK:
+        raise BfmError(rc, "bfm_plan_preview: invalid arguments")
+    items = np.empty((n.value, 8), np.int32)
+    rc = L.bfm_plan_preview(*args, items.ctypes.data, n.value, ctypes.byref(n), ctypes.byref(rows))
+    if rc != BFM_OK:
+        raise BfmError(rc, "bfm_plan_preview failed")
+    return items, rows.value

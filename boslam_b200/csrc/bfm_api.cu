@@ -885,6 +885,37 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
 
 int64_t bfm_kernel_launch_count(bfm_handle_t h) { return h ? h->launches : 0; }
 
+// Host-only: the work-item plan a batch would get.  No device is touched, so the planner's invariants are
+// testable on a box without a GPU (tests/test_planner_cpu.py).
+int bfm_plan_preview(const bfm_problem_t *problems, int32_t n_problems, int32_t queries_per_thread, int32_t slots,
+                     int32_t segment_rows, int32_t waves, int32_t taper, int32_t taper_pct, int32_t *items_out,
+                     int32_t capacity, int32_t *n_items, int32_t *segment_rows_out) {
+    if (!problems || n_problems <= 0 || !n_items || slots <= 0 || capacity < 0 || (capacity > 0 && !items_out)) return BFM_ERR_INVALID;
+    if (queries_per_thread != 1 && queries_per_thread != 2 && queries_per_thread != 4) return BFM_ERR_INVALID;
+    if (segment_rows < 0 || waves < 0 || taper_pct < 0 || taper_pct > 90 ||
+        (taper != 0 && taper != 1 && taper != 2 && taper != 4 && taper != 8))
+        return BFM_ERR_INVALID;
+    for (int p = 0; p < n_problems; ++p)
+        if (problems[p].q_count < 0 || problems[p].t_count < 0 || problems[p].q_begin < 0 || problems[p].t_begin < 0 ||
+            problems[p].out_begin < 0 || problems[p].t_count >= BFM_MAX_TRAIN_ROWS || problems[p].q_count >= BFM_MAX_QUERY_ROWS)
+            return BFM_ERR_INVALID;
+    bfm_handle_s tmp;   // knobs only: plan_segments reads nothing else
+    tmp.segment_rows = segment_rows;
+    tmp.waves = waves;
+    tmp.taper = taper;
+    tmp.taper_pct = taper_pct;
+    std::vector<Segment> segs;
+    std::vector<int> seg_begin;
+    int L = 0;
+    plan_segments(&tmp, problems, n_problems, queries_per_thread, slots, segs, seg_begin, &L);
+    *n_items = (int32_t)segs.size();
+    if (segment_rows_out) *segment_rows_out = L;
+    const size_t n = std::min(segs.size(), (size_t)capacity);
+    static_assert(sizeof(Segment) == 8 * sizeof(int32_t), "a work item is eight int32");
+    if (n) std::memcpy(items_out, segs.data(), n * sizeof(Segment));
+    return BFM_OK;
+}
+
 int bfm_host_alloc(uint64_t bytes, void **out) {
     if (!out) return BFM_ERR_INVALID;
     *out = nullptr;

@@ -244,6 +244,15 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t bfm_kernel_launch_count(bfm_handle_t h);
 
+/* Host-only preview of the work-item plan of a batch (no device needed; the CPU tests of the planner use it).
+ * A work item is one CTA's share: a block of 128 x queries_per_thread query rows against a contiguous train
+ * range of one problem.  `slots` = CTAs resident on the device at once (148 SMs x 8 on a B200); the knobs have
+ * bfm_set_tuning's meaning (0 = auto).  items_out: int32[capacity][8] = {q_row0, q_valid, q_local0, out_row0,
+ * t_row0, t_count, t_local0, problem} in launch order; *n_items is the full count even when it exceeds capacity. */
+int bfm_plan_preview(const bfm_problem_t *problems, int32_t n_problems, int32_t queries_per_thread, int32_t slots,
+                     int32_t segment_rows, int32_t waves, int32_t taper, int32_t taper_pct, int32_t *items_out,
+                     int32_t capacity, int32_t *n_items, int32_t *segment_rows_out);
+
 /* Integer-pipe micro-benchmark: the roofline denominator.
  * test: 0 POPC, 1 LOP3, 2 IADD3, 3 POPC+LOP3 1:1, 4 POPC+2xLOP3, 5 REDUX.MIN, 6 IMAD, 7 VIMNMX,
  *       8 POPC+IMAD 1:1, 9 XOR+POPC+IADD pair loop (8:8:4, the plain per-pair mix).

@@ -1,0 +1,102 @@
+"""Host logic of the CUDA library, on a box without a GPU: the work-item planner (bfm_plan_preview).
+
+Every CTA of the matching kernel takes one work item = (block of 128 x R query rows) x (contiguous train range) of
+one problem.  The result is a min over packed (distance, index) keys, so ANY exact tiling gives the same bits;
+what the planner must guarantee is that the tiling IS exact - every (query row, train row) pair of every problem
+is covered exactly once - and the balance properties the kernel's throughput relies on."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import boslam_b200 as bb
+from boslam_b200 import _ffi
+
+SLOTS = 148 * 8          # CTAs resident on a B200 (148 SMs x 8 per SM)
+Q_ROW0, Q_VALID, Q_LOCAL0, OUT_ROW0, T_ROW0, T_COUNT, T_LOCAL0, PROBLEM = range(8)
+
+
+def _check_exact_tiling(tab, items, r):
+    bq = 128 * r
+    assert (np.diff(items[:, PROBLEM]) >= 0).all(), "work items are in problem order (the upload chases them)"
+    for p, (q_begin, q_count, t_begin, t_count, out_begin, _) in enumerate(tab.tolist()):
+        mine = items[items[:, PROBLEM] == p]
+        if q_count == 0 or t_count == 0:
+            # an empty problem still gets ONE item: the CTA that completes a problem finalizes it
+            assert len(mine) == 1 and mine[0, T_COUNT] == 0 and mine[0, Q_VALID] == 0
+            assert mine[0, OUT_ROW0] == out_begin
+            continue
+        n_blocks = (q_count + bq - 1) // bq
+        assert sorted(set(mine[:, Q_LOCAL0].tolist())) == [b * bq for b in range(n_blocks)]
+        for b in range(n_blocks):
+            blk = mine[mine[:, Q_LOCAL0] == b * bq]
+            assert (blk[:, Q_ROW0] == q_begin + b * bq).all() and (blk[:, OUT_ROW0] == out_begin + b * bq).all()
+            assert (blk[:, Q_VALID] == min(bq, q_count - b * bq)).all()
+            # the train ranges of one query block tile [0, t_count) exactly, in order, without gaps or overlaps
+            assert blk[0, T_LOCAL0] == 0
+            assert (blk[1:, T_LOCAL0] == blk[:-1, T_LOCAL0] + blk[:-1, T_COUNT]).all()
+            assert blk[-1, T_LOCAL0] + blk[-1, T_COUNT] == t_count
+            assert (blk[:, T_COUNT] > 0).all()
+            assert (blk[:, T_ROW0] == t_begin + blk[:, T_LOCAL0]).all()
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 5000), st.integers(0, 30000)), min_size=1, max_size=40),
+       st.sampled_from([1, 2, 4]), st.sampled_from([0, 1, 2, 4, 8]), st.sampled_from([0, 5, 10, 35, 90]),
+       st.sampled_from([0, 0, 0, 33, 128, 1000]), st.sampled_from([0, 0, 1, 3]))
+def test_plan_tiles_every_problem_exactly(shapes, r, taper, pct, seg_rows, waves):
+    tab = bb.make_problems([q for q, _ in shapes], [t for _, t in shapes])
+    items, L = _ffi.plan_preview(tab, r, SLOTS, seg_rows, waves, taper, pct)
+    assert L >= 1 and len(items) >= len(shapes)
+    _check_exact_tiling(tab, items, r)
+    if seg_rows:
+        assert L == seg_rows and items[:, T_COUNT].max() <= seg_rows
+
+
+def test_headline_batch_plan():
+    """256 x (2000 x 2000), R = 4: ~7 waves of equal CTAs, then a tapered tail (1/2, then 1/4 of the length over
+    the last 10 % of the work) - the numbers bench.py reports as launch.scan_grid."""
+    tab = bb.make_problems([2000] * 256, [2000] * 256)
+    flat, L = _ffi.plan_preview(tab, 4, SLOTS, taper=1)
+    assert len(flat) == 8192 and set(flat[:, T_COUNT].tolist()) == {250}
+    assert abs(len(flat) / SLOTS - round(len(flat) / SLOTS)) < 0.1           # close to whole waves
+    items, L2 = _ffi.plan_preview(tab, 4, SLOTS)                              # auto: tapered
+    assert L2 == L and len(items) == 9564
+    _check_exact_tiling(tab, items, 4)
+    per_problem = np.array([items[items[:, PROBLEM] == p][:, T_COUNT].max() for p in range(256)])
+    assert (per_problem[:230] == 250).all()                                   # the first 90 % of the work: full length
+    assert (np.diff(per_problem) <= 0).all()                                  # never longer towards the end
+    assert per_problem[-1] <= L // 4 and per_problem[235] <= L // 2                 # L = 285 rows asked, 250 cut
+    # work is conserved
+    assert int((items[:, Q_VALID].astype(np.int64) * items[:, T_COUNT]).sum()) == 256 * 2000 * 2000
+
+
+def test_small_and_single_problem_plans_are_not_tapered():
+    for shapes in ([(2000, 20000)], [(1000, 1000)], [(2000, 2000)] * 7):
+        tab = bb.make_problems([q for q, _ in shapes], [t for _, t in shapes])
+        a, _ = _ffi.plan_preview(tab, 2, SLOTS)
+        b, _ = _ffi.plan_preview(tab, 2, SLOTS, taper=1)
+        assert np.array_equal(a, b)
+        _check_exact_tiling(tab, a, 2)
+
+
+def test_balance_of_the_wave_aware_cut():
+    """All work items of a flat plan cost about the same (within one row per segment), whatever the shape."""
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        n = int(rng.integers(8, 300))
+        tab = bb.make_problems([2000] * n, [int(rng.integers(1500, 2500))] * n)
+        items, L = _ffi.plan_preview(tab, 4, SLOTS, taper=1)
+        full = items[items[:, Q_VALID] == 512]
+        assert full[:, T_COUNT].max() - full[:, T_COUNT].min() <= 1
+        assert full[:, T_COUNT].max() <= L
+
+
+def test_plan_preview_rejects_bad_arguments():
+    tab = bb.make_problems([10], [10])
+    for kw in (dict(queries_per_thread=3), dict(slots=0), dict(taper=3), dict(taper_pct=91), dict(segment_rows=-1)):
+        with pytest.raises(bb.BfmError):
+            _ffi.plan_preview(tab, **kw)
+    bad = tab.copy()
+    bad[0, 1] = -1
+    with pytest.raises(bb.BfmError):
+        _ffi.plan_preview(bad)
