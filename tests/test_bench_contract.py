@@ -62,6 +62,7 @@ def test_b200_arm_line_has_every_contract_key():
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in r, k
     assert r["frac"] > 0.5 and r["traffic"] and r["hbm"]["peak"] > 0
+    assert 0.5 < r["frac_issued"] <= 1.0 and r["popc_issued_per_pair"] == 4     # against the POPCs really issued
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 30e6 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
     c = d["clocks"]
