@@ -6,23 +6,29 @@ JSON line from rank 0.  ``--impl reference`` times the reference's own implement
 (cv2.BFMatcher on the box's host cores, reference slam/tracking.py:45,56) on the same config.
 
 Workload (config.workload = "loop_closing"): BASELINE.json configs[3], the configuration the
-metric's "at 1/2/4/8 B200" is quoted on: 256 BoW-candidate keyframe pairs x (2000 x 2000) ORB
-descriptors, knn k=2 + ratio 0.8, ONE kernel launch per step; weak scaling (every rank runs its
-own 256 pairs; every rank ends up with every rank's match tables, written by the kernel epilogue into
-all ranks' symmetric buffers - NVSwitch multicast stores where available - plus an overlapped barrier;
-BFM_GATHER=nccl selects a plain NCCL all_gather instead).  A "step" is one pass of the hot path over one
-batch; 1.024 G descriptor pairs per step per GPU.  The tracking (configs[1]), frame-to-frame (configs[0],
-with and without the CPU solvePnPRansac), local-mapping (configs[2]) shapes and the device-resident
-local-map step are reported as extra keys of the same line ("frames"); configs[4] (the size sweep) is
-tools/size_sweep.py -> profiles/size_sweep_r01.json.
+metric's "at 1/2/4/8 B200" is quoted on: ONE list of 256 BoW-candidate keyframe pairs x (2000 x 2000) ORB
+descriptors per step, knn k=2 + ratio 0.8.  STRONG scaling: rank r of N takes pairs[r*256/N : (r+1)*256/N]
+(SURVEY 8(e)), ONE kernel launch per rank and step, and every rank ends up with every rank's match tables -
+written by the kernel epilogue into all ranks' symmetric buffers (NVSwitch multicast stores where available)
+plus a symmetric-memory barrier per step, all inside the timed region; BFM_GATHER=nccl selects a plain NCCL
+all_gather instead.  A "step" is one pass of the hot path over the whole list: 1.024 G descriptor pairs.
+Round 1's weak-scaling form (256 pairs per rank) is the extra key "weak".  The tracking (configs[1]),
+frame-to-frame (configs[0], with and without the CPU solvePnPRansac), local-mapping (configs[2], both variants)
+shapes and the device-resident local-map step are extra keys of the same line ("frames"); configs[4] (the size
+sweep) is tools/size_sweep.py -> profiles/.
 
   value      pairs/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
   e2e        same metric through the public host API (Engine.plan_batch(...).run: numpy in -> numpy out,
              pinned host buffers; the step's inputs are read from host memory and its results written to
-             host memory inside the timed region, by the kernel itself)
+             host memory inside the timed region, by the kernel itself); at N > 1 the same call also performs
+             the exchange (host copies + match + gather + barrier in one number)
   roofline   scan kernel vs the measured POPC issue peak (integer pipe; 8 POPC per pair is the
              algorithmic count) - plus the HBM view for context
-  cpu_baseline  cv2.BFMatcher.knnMatch(k=2) + Python ratio test on the host cores (N = 1 only)
+  cpu_baseline  cv2.BFMatcher.knnMatch(k=2) + Python ratio test on the host cores (N = 1 only); the same leg
+             checks the engine's full knn tables and match lists of the batch against cv2's
+  verify     N > 1: bit-equality of every rank's gathered table with an NCCL all_gather of the locally computed
+             tables (gather_verified_full), ShardedMatcher through the CUDA engine; tables_crc32 of the whole
+             result of input set 0 is the same number for every N
 """
 from __future__ import annotations
 
@@ -40,7 +46,6 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_PAIRS, N_DESC, RATIO = 256, 2000, 0.8
-N_SETS = 6  # rotating input sets: 6 x 32.8 MB = 197 MB > 126 MB L2
 
 
 def _env_int(name, default):
@@ -117,43 +122,66 @@ def cv2_step(matcher, q, t, tab, ratio):
     return n
 
 
+def bench_config():
+    """The ONE workload both arms run (identical dict in both JSON lines): BASELINE.json configs[3]."""
+    return {"workload": "loop_closing", "pairs": N_PAIRS, "desc_per_keyframe": N_DESC, "k": 2, "ratio": RATIO,
+            "pairs_per_step": N_PAIRS * N_DESC * N_DESC,
+            "split": "ONE list of 256 candidate pairs per step; rank r of n_gpus takes pairs[r*256/n : (r+1)*256/n]",
+            "l2": "rotating input sets, > 126 MB in total per rank (more than L2)"}
+
+
+def cv2_tables(matcher, q, t, tab):
+    """cv2.knnMatch(k=2) of every pair as dense int32 tables [rows, 2] (idx, dist), -1 padded (rule R3)."""
+    n = int((tab[:, 4] + tab[:, 1]).max()) if len(tab) else 0
+    idx = np.full((n, 2), -1, np.int32)
+    dist = np.full((n, 2), -1, np.int32)
+    for p in range(tab.shape[0]):
+        qb, qc, tb, tc, ob = (int(tab[p, c]) for c in range(5))
+        for i, row in enumerate(matcher.knnMatch(q[qb:qb + qc], t[tb:tb + tc], 2)):
+            for c, dm in enumerate(row):
+                idx[ob + i, c] = dm.trainIdx
+                dist[ob + i, c] = int(dm.distance)
+    return idx, dist
+
+
 def reference_arm(args, emit):
-    """--impl reference: cv2.BFMatcher on the host cores, same config / metric / unit."""
+    """--impl reference: cv2.BFMatcher on the host cores; same config / metric / unit, the full 256-pair batch per step."""
     rank = _env_int("RANK", 0)
     if rank != 0:
         return
     import boslam_b200.synth as synth
     from boslam_b200.engine import make_problems
     from oracle import cv2_reference as ref
-    sample_pairs = 32  # bounded sample of the 256-pair batch per step (~0.2-0.4 s of CPU work)
-    q, t = synth.keyframe_pair_batch(sample_pairs, N_DESC, seed=1)
-    tab = make_problems([N_DESC] * sample_pairs, [N_DESC] * sample_pairs)
-    pairs = sample_pairs * N_DESC * N_DESC
+    n_sets = 2   # rotating input sets (L2 is irrelevant to a host run; kept so both arms read fresh data every step)
+    sets = [synth.keyframe_pair_batch(N_PAIRS, N_DESC, seed=s) for s in range(n_sets)]
+    tab = make_problems([N_DESC] * N_PAIRS, [N_DESC] * N_PAIRS)
+    pairs = N_PAIRS * N_DESC * N_DESC
     if ref.HAVE_CV2:
         m = ref.matcher(False)
         kind, cores = "reference", ref.threads()
-        step = lambda: cv2_step(m, q, t, tab, RATIO)
-    else:  # plain-C port of the same algorithm, single thread
+        step = lambda i: cv2_step(m, sets[i % n_sets][0], sets[i % n_sets][1], tab, RATIO)
+        sample = (f"the full {N_PAIRS}-pair batch per step, cv2 {ref.version()} knnMatch(k=2) + Python ratio test incl. DMatch "
+                  f"construction, os.cpu_count()={os.cpu_count()}")
+    else:  # plain-C port of the same algorithm, single thread: a bounded sample of the batch
         from oracle import c_oracle
-        kind, cores = "port", 1
-        step = lambda: sum(len(c_oracle.knn(q[p * N_DESC:(p + 1) * N_DESC], t[p * N_DESC:(p + 1) * N_DESC], 2)[0])
-                           for p in range(sample_pairs))
-    for _ in range(max(args.warmup, 1)):
-        step()
+        kind, cores, sp = "port", 1, 8
+        pairs = sp * N_DESC * N_DESC
+        step = lambda i: sum(len(c_oracle.knn(sets[0][0][p * N_DESC:(p + 1) * N_DESC], sets[0][1][p * N_DESC:(p + 1) * N_DESC], 2)[0])
+                             for p in range(sp))
+        sample = f"{sp} of {N_PAIRS} pairs per step, plain-C oracle, 1 thread"
+    for i in range(max(args.warmup, 1)):
+        step(i)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
+    for i in range(args.steps):
+        step(i)
     dt = time.perf_counter() - t0
     value = pairs * args.steps / dt
     line = {
         "impl": "reference", "metric": "hamming_pairs_per_s", "value": value, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "loop_closing", "pairs": N_PAIRS, "desc_per_keyframe": N_DESC, "k": 2, "ratio": RATIO,
-                   "sample": f"{sample_pairs} of {N_PAIRS} pairs per step"},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample_pairs} pairs x ({N_DESC}x{N_DESC}) per step, cv2 {ref.version()} knnMatch(k=2) + "
-                                   f"Python ratio test, os.cpu_count()={os.cpu_count()}"},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": bench_config(),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -232,6 +260,10 @@ def extras(eng, torch, steps):
     run("local_mapping_20x2000x2000_k2_ratio",
         lambda: eng.match_batched(qb, tb, tab3, k=2, ratio=RATIO),
         lambda: eng.match_batched_device(qbd, tbd, tab3, k=2, ratio=RATIO),
+        1, 20 * 2000 * 2000, reps)
+    run("local_mapping_20x2000x2000_crosscheck_gate30",   # the reference's local-mapping matcher is crossCheck=True (slam/local_mapping.py:21)
+        lambda: eng.match_batched(qb, tb, tab3, cross_check=True, max_distance=30),
+        lambda: eng.match_batched_device(qbd, tbd, tab3, cross_check=True, max_distance=30),
         1, 20 * 2000 * 2000, reps)
     # the headline batch from ordinary (pageable) numpy arrays into ordinary numpy arrays: what a caller who knows
     # nothing about pinned memory gets (worker threads stage the arrays for the kernel's feeder CTAs)
@@ -349,6 +381,16 @@ def extras(eng, torch, steps):
     return out
 
 
+def _masked_lists(torch, m, count, n_desc):
+    """Match lists [.., 3, P*n_desc] with everything past each problem's count zeroed (only the filled prefix of a
+    problem's slice is defined), so two tables can be compared bit for bit."""
+    lead = m.shape[:-2]
+    P = count.shape[-1]
+    v = m.reshape(*lead, 3, P, n_desc)
+    keep = torch.arange(n_desc, device=m.device).view(*([1] * len(lead)), 1, 1, n_desc) < count.reshape(*lead, 1, P, 1)
+    return torch.where(keep, v, torch.zeros_like(v)).reshape(m.shape)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -358,7 +400,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true",
-                    help="skip the host-path leg (for ncu runs: its kernel waits on the copy engine, which a profiler replay cannot reproduce)")
+                    help="skip the host-path leg (for ncu runs: its kernel waits on uploads a profiler replay cannot reproduce)")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling extra (256 pairs per rank)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -378,10 +422,12 @@ def main():
         reference_arm(args, emit)
         return
 
+    import zlib
     import torch
     import boslam_b200 as bb
     import boslam_b200.synth as synth
     from boslam_b200 import _ffi
+    from boslam_b200.distributed import partition_pairs
     from boslam_b200.engine import PinnedBuffer, make_problems
 
     world = _env_int("WORLD_SIZE", 1)
@@ -397,42 +443,61 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     barrier = (lambda: dist.barrier()) if dist else (lambda: None)
 
+    def max_over_ranks(x):
+        if not dist:
+            return float(x)
+        tms = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        return float(tms.item())
+
     eng = bb.Engine(local_rank)
     dev = torch.device("cuda", local_rank)
-    tab = make_problems([N_DESC] * N_PAIRS, [N_DESC] * N_PAIRS)
-    n_out = N_PAIRS * N_DESC
-    pairs_per_step = N_PAIRS * N_DESC * N_DESC
+    # -- the workload: ONE list of 256 pairs per step; this rank's contiguous block of it ------
+    blk0, blk1 = partition_pairs([N_DESC * N_DESC] * N_PAIRS, world)[rank]
+    P_loc = blk1 - blk0
+    tab = make_problems([N_DESC] * P_loc, [N_DESC] * P_loc)
+    n_out = P_loc * N_DESC
+    pairs_per_step = N_PAIRS * N_DESC * N_DESC             # the whole list, all ranks together
+    set_bytes = 2 * n_out * 32
+    n_sets = max(6, -(-130_000_000 // max(set_bytes, 1)))   # rotating input sets: > 126 MB L2 in total per rank
 
-    # -- inputs: N_SETS distinct synthetic batches per rank, pinned on the host + resident in HBM.  The resident
-    #    copies are uploaded FROM the pinned buffers, so every pinned page has been read by the device once
-    #    before any timing (a pinned page's first device access is slower; real callers reuse their staging) --
+    # -- inputs.  Set 0 is this rank's block of the SAME global list for every world size (seed 1000), so the
+    #    gathered tables can be compared across N (tables_crc32); the other sets are per-(set, rank) draws.  Pinned on
+    #    the host + resident in HBM; the resident copies are uploaded FROM the pinned buffers, so every pinned page
+    #    has been read by the device once before any timing --
     pinned, dev_sets = [], []
-    for s in range(N_SETS):
-        q, t = synth.keyframe_pair_batch(N_PAIRS, N_DESC, seed=1000 * rank + s)
+    for s_ in range(n_sets):
+        if s_ == 0:
+            gq, gt = synth.keyframe_pair_batch(N_PAIRS, N_DESC, seed=1000)
+            q, t = gq[blk0 * N_DESC:blk1 * N_DESC], gt[blk0 * N_DESC:blk1 * N_DESC]
+        else:
+            q, t = synth.keyframe_pair_batch(P_loc, N_DESC, seed=1000 + 97 * s_ + 7919 * rank)
         pq, pt = PinnedBuffer(q.shape), PinnedBuffer(t.shape)
         pq.array[...] = q
         pt.array[...] = t
         pinned.append((pq, pt))
         dev_sets.append((torch.from_numpy(pq.array).to(dev), torch.from_numpy(pt.array).to(dev)))
     out = {"m": torch.empty((3, n_out), dtype=torch.int32, device=dev),
-           "count": torch.zeros(N_PAIRS, dtype=torch.int32, device=dev)}
-    gathered_m = torch.empty((world * 3, n_out), dtype=torch.int32, device=dev) if dist else None
-    gathered_c = torch.empty(world * N_PAIRS, dtype=torch.int32, device=dev) if dist else None
+           "count": torch.zeros(P_loc, dtype=torch.int32, device=dev)}
     # the path's one exchange: every rank ends up with every rank's match tables.
     # Default: fused into the matching kernel's epilogue (stores to NVLink peer memory + one barrier);
     # BFM_GATHER=nccl selects the plain NCCL all_gather for comparison.
     fused = None
     gather_mode = os.environ.get("BFM_GATHER", "fused") if dist else "none"
+    gathered_m = gathered_c = None
     if dist and gather_mode == "fused":
         try:
             from boslam_b200.distributed import FusedGather
-            fused = FusedGather(n_out, N_PAIRS, k=2)
+            fused = FusedGather(n_out, P_loc, k=2)
         except Exception as e:  # symmetric memory unavailable on this box: say so and use NCCL
             print(f"[bench] fused gather unavailable ({type(e).__name__}: {e}); using NCCL all_gather", file=sys.stderr)
             gather_mode = "nccl"
+    if dist and gather_mode == "nccl":
+        gathered_m = torch.empty((world * 3, n_out), dtype=torch.int32, device=dev)
+        gathered_c = torch.empty(world * P_loc, dtype=torch.int32, device=dev)
 
     def device_step(i):
-        q, t = dev_sets[i % N_SETS]
+        q, t = dev_sets[i % n_sets]
         if fused is not None:
             fused.run(eng, q, t, tab, k=2, ratio=RATIO)
             fused.barrier()
@@ -456,126 +521,258 @@ def main():
     clocks = sampler.stop()
     launches = eng.kernel_launch_count() - launches0
     info = eng.launch_info()
-    if dist:
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    value = pairs_per_step * world * args.steps / (ms * 1e-3)
+    ms = max_over_ranks(ms)
+    value = pairs_per_step * args.steps / (ms * 1e-3)
 
-    # the fused gather must have delivered every rank's table to every rank: compare this rank's view of all
-    # per-problem match counts and index checksums with what each rank computed locally (exchanged over NCCL)
-    gather_verified = None
+    # -- the same loop with every step's exchange completed before the next step starts (no overlap of barrier n with
+    #    kernel n+1): the latency form of the step --
+    sync_ms = None
     if fused is not None:
+        def sync_step(i):
+            device_step(i)
+            fused.wait()
+        sync_ms = max_over_ranks(time_device_loop(torch, sync_step, args.steps, barrier)) / args.steps
+
+    # -- verification of the exchange, outside the timed loops: bit-equality of every rank's symmetric table (match
+    #    lists, counts AND the dense knn tables) with an NCCL all_gather of the tables each rank computes locally --
+    verify = {}
+    q0, t0_ = dev_sets[0]
+    loc = eng.match_batched_device(q0, t0_, tab, k=2, ratio=RATIO, want_knn=True)
+    torch.cuda.synchronize()
+    loc_m = _masked_lists(torch, loc["m"][:, :n_out], loc["count"][:P_loc], N_DESC)
+    if dist:
+        all_m = torch.empty((world, 3, n_out), dtype=torch.int32, device=dev)
+        all_c = torch.empty((world, P_loc), dtype=torch.int32, device=dev)
+        all_ki = torch.empty((world, n_out, 2), dtype=torch.int32, device=dev)
+        all_kd = torch.empty((world, n_out, 2), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(all_m, loc_m.contiguous())
+        dist.all_gather_into_tensor(all_c, loc["count"][:P_loc].contiguous())
+        dist.all_gather_into_tensor(all_ki, loc["knn_idx"][:n_out].contiguous())
+        dist.all_gather_into_tensor(all_kd, loc["knn_dist"][:n_out].contiguous())
+    else:
+        all_m, all_c = loc_m[None], loc["count"][None, :P_loc]
+        all_ki, all_kd = loc["knn_idx"][None, :n_out], loc["knn_dist"][None, :n_out]
+    if fused is not None:
+        from boslam_b200.distributed import FusedGather
+        fv = FusedGather(n_out, P_loc, k=2, want_knn=True)
+        ok = True
+        for rep in range(4):                     # four steps: every slot is reused at least once
+            fv.run(eng, q0, t0_, tab, k=2, ratio=RATIO)
+            fv.barrier()
+            fv.wait()
+            torch.cuda.synchronize()
+            tb = fv.tables()
+            ok = ok and torch.equal(tb["count"], all_c) and torch.equal(tb["knn_idx"], all_ki) and \
+                torch.equal(tb["knn_dist"], all_kd) and torch.equal(_masked_lists(torch, tb["m"], tb["count"], N_DESC), all_m)
+        # and the timed configuration's own table (match lists only), as left by one more step
         device_step(0)
         fused.wait()
         torch.cuda.synchronize()
         tb = fused.tables()
-        mine_c = tb["count"][rank].clone()
-        mine_s = torch.stack([tb["m"][rank, j].to(torch.int64).sum() for j in range(3)])
-        all_c = torch.empty((world, N_PAIRS), dtype=torch.int32, device=dev)
-        all_s = torch.empty((world, 3), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_c, mine_c)
-        dist.all_gather_into_tensor(all_s, mine_s)
-        view_s = torch.stack([torch.stack([tb["m"][r, j].to(torch.int64).sum() for j in range(3)]) for r in range(world)])
-        ok = torch.equal(all_c, tb["count"]) and torch.equal(all_s, view_s) and bool((all_c.sum(dim=1) > 0).all())
+        ok = ok and torch.equal(tb["count"], all_c) and torch.equal(_masked_lists(torch, tb["m"], tb["count"], N_DESC), all_m)
+        ok = ok and bool((all_c.sum(dim=1) > 0).all())
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        gather_verified = bool(flag.item())
-        if not gather_verified:
-            raise SystemExit("fused gather verification failed: the ranks do not hold identical tables")
+        verify["gather_verified_full"] = bool(flag.item())
+        verify["gather_verified"] = verify["gather_verified_full"]
+        if not verify["gather_verified_full"]:
+            raise SystemExit("fused gather verification failed: a rank's symmetric table differs from the NCCL gather of the local tables")
+    # one checksum of the WHOLE gathered result of input set 0: identical for every world size (W = 1, 2, 4, 8
+    # must be byte-identical)
+    crc = 0
+    for a in (all_ki, all_kd, all_c, all_m):
+        crc = zlib.crc32(a.cpu().numpy().tobytes(), crc)
+    verify["tables_crc32"] = int(crc)
+    verify["matches_set0"] = int(all_c.sum().item())
+    if dist:
+        # ShardedMatcher (the host-level binding of 8(e)) through the real CUDA engine: sharded == unsharded
+        from boslam_b200.distributed import ShardedMatcher
+        rng = np.random.default_rng(77)
+        sq, st_ = [], []
+        for p in range(2 * world + 3):
+            a, b, _ = synth.correlated(int(rng.integers(40, 400)), int(rng.integers(40, 500)), 500 + p)
+            sq.append(a)
+            st_.append(b)
+        gi, gd = ShardedMatcher(engine=eng).knn_pairs(sq, st_, k=2)
+        ok = True
+        for p in range(len(sq)):
+            ii, dd = eng.knn(sq[p], st_[p], 2)
+            ok = ok and np.array_equal(gi[p], ii) and np.array_equal(gd[p], dd)
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        verify["sharded_matcher_verified"] = bool(flag.item())
+        if not verify["sharded_matcher_verified"]:
+            raise SystemExit("ShardedMatcher.knn_pairs (CUDA engine) differs from the unsharded engine result")
 
-    # -- roofline pass: per-launch scan-kernel time from CUDA events on the launching stream --
+    # -- roofline: the step IS one launch of the scan kernel, so its average duration over the timed region is
+    #    ms_per_step (CUDA events on the launching stream, launch gaps included: an upper bound on the kernel time);
+    #    a second loop with the library's own per-launch events gives the isolated figure --
     eng.set_tuning(timing=1)
     scan_ms = []
     for i in range(args.steps):
-        q, t = dev_sets[i % N_SETS]
+        q, t = dev_sets[i % n_sets]
         eng.match_batched_device(q, t, tab, k=2, ratio=RATIO, out=out)
         scan_ms.append(eng.launch_info()["scan_ms"])
     eng.set_tuning(timing=0)
-    scan_avg = float(np.mean(scan_ms))
-    achieved_popc = pairs_per_step * 8 / (scan_avg * 1e-3)
-    hbm_bytes = 32 * 2 * N_PAIRS * N_DESC + 8 * n_out  # descriptors in + packed row state out
+    scan_iso = max_over_ranks(float(np.mean(scan_ms)))
+    kernel_ms = ms / args.steps if world == 1 else scan_iso
+    pairs_per_launch = P_loc * N_DESC * N_DESC
+    achieved_popc = pairs_per_launch * 8 / (kernel_ms * 1e-3)
+    hbm_bytes = 32 * 2 * n_out + 8 * n_out  # descriptors in + packed row state out
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("loop_closing_scan_bytes")
+    from_file = {}
+    try:   # figures that need a profiler (ncu --set full of this command) are READ FROM A FILE and labelled as such
+        from_file = json.load(open(os.path.join(ROOT, "profiles", "ncu_scan_summary.json")))
     except Exception:
         pass
     popc_issued = 4 if info["popc_mode"] in (4, 40) else (5 if info["popc_mode"] in (5, 50) else info["popc_mode"])
     roofline = {
         "bound": "int_popc", "kernel": "bfm_scan_kernel", "achieved": achieved_popc / 1e9, "peak": popc["ops_per_s"] / 1e9,
-        "unit": "GPOPC/s", "frac": achieved_popc / popc["ops_per_s"], "traffic": traffic,
-        "algorithmic": "8 POPC per descriptor pair x 1.024e9 pairs per launch",
+        "unit": "GPOPC/s", "frac": achieved_popc / popc["ops_per_s"],
+        "traffic": from_file.get("dram_bytes_per_launch") if world == 1 else None,
+        "traffic_source": from_file.get("source") if world == 1 else None,
+        "algorithmic": f"8 POPC per descriptor pair x {pairs_per_launch:.4g} pairs per launch",
         "popc_issued_per_pair": popc_issued,
         # the same launch against what the kernel really issues (carry-save tree: 4 POPC per pair, not 8):
-        # how close the XU pipe is to saturation, measured live; ncu's pipe-busy figure is in issue_bound
+        # how close the XU pipe is to saturation, measured live
         "frac_issued": achieved_popc * popc_issued / 8 / popc["ops_per_s"],
         "popc_mode": info["popc_mode"],
-        "issue_bound": {"pipe": "xu (POPC)", "busy_pct": 89.3, "alu_busy_pct": 83.6,
-                        "source": "profiles/r01e_ncu_scan_final.md (ncu --set full of this command)"},
-        "scan_ms": scan_avg, "scan_share_of_step": scan_avg / (ms / args.steps),
+        "kernel_ms": kernel_ms, "kernel_ms_how": ("ms_per_step of the timed region (one launch per step)" if world == 1 else
+                                                    "library events around each launch, separate loop (the step also holds the exchange)"),
+        "kernel_ms_isolated": scan_iso,
+        "from_file": from_file or None,
         "peak_source": "measured in this run: bfm_microbench POPC probe (16 POPC/clk/SM x 148 SMs x SM clock)",
         "popc_per_clk_per_sm": popc["ops_per_clk_per_sm"],
-        "hbm": {"achieved": hbm_bytes / (scan_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": hbm_bytes / (scan_avg * 1e-3) / 1e9 / hbm_peak,
+        "hbm": {"achieved": hbm_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": hbm_bytes,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
     }
 
-    # -- e2e: numpy in -> numpy out through the public API, pinned host inputs ---------------------
-    host_out = bb.HostBatchBuffers(n_out, N_PAIRS, k=2)  # pinned result arrays, reused every step
-    plan = eng.plan_batch(tab, k=2, ratio=RATIO)         # the table and options are validated once, outside the loop
+    # -- e2e: numpy in -> numpy out through the public API, pinned host inputs.  At N > 1 the same call also delivers
+    #    the exchange: its epilogue writes this rank's lists into every rank's table, then the barrier --
+    host_out = bb.HostBatchBuffers(n_out, P_loc, k=2)  # pinned result arrays, reused every step
+    plan = eng.plan_batch(tab, k=2, ratio=RATIO)       # the table and options are validated once, outside the loop
+    fe = None
+    if fused is not None:
+        from boslam_b200.distributed import FusedGather
+        fe = FusedGather(n_out, P_loc, k=2)
 
     def host_step(i):
-        pq, pt = pinned[i % N_SETS]
+        pq, pt = pinned[i % n_sets]
+        if fe is not None:
+            r = fe.run_host(plan, pq.array, pt.array, host_out)
+            fe.barrier()
+            return r
         return plan.run(pq.array, pt.array, host_out)
 
     e2e_steps = 0 if args.no_e2e else args.steps
     res = None
     for i in range(args.warmup if e2e_steps else 0):
         res = host_step(i)
+    if fe is not None:
+        fe.wait()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         res = host_step(i)
+    if fe is not None and e2e_steps:
+        fe.wait()
+        torch.cuda.synchronize()
     e2e_s = max(time.perf_counter() - t0, 1e-9)
     barrier()
-    if dist:
-        tms = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e_s = float(tms.item())
-    e2e = {"value": pairs_per_step * world * e2e_steps / e2e_s, "unit": "pairs/s",
-           "h2d_bytes_per_step": int(2 * n_out * 32 + tab.nbytes), "d2h_bytes_per_step": (int(res.counts.sum()) * 12 + N_PAIRS * 4) if res is not None else 0,
-           "ms_per_step": e2e_s / max(e2e_steps, 1) * 1e3, "matches_last_step": int(res.counts.sum()) if res is not None else None,
-           "copy_chunks": eng.launch_info().get("copy_chunks"),
-           "how": "numpy (pinned) in -> numpy (pinned) out through Engine.match_batched: ONE kernel launch per step whose first CTAs "
-                  "stream the step's inputs from pinned host memory into HBM (copy_chunks = feed rounds) while the others match; "
-                  "results written by the kernel into pinned host memory; one stream sync"} if e2e_steps else None
+    e2e_s = max_over_ranks(e2e_s)
+    e2e = None
+    if e2e_steps:
+        n_match = int(res.counts.sum())
+        e2e_ok = None
+        if fe is not None:   # the e2e leg's exchange delivered the same tables (last step used input set (steps-1) % n_sets)
+            fe.wait()
+            torch.cuda.synchronize()
+            q_, t_ = dev_sets[(e2e_steps - 1) % n_sets]
+            l2 = eng.match_batched_device(q_, t_, tab, k=2, ratio=RATIO)
+            lm = _masked_lists(torch, l2["m"][:, :n_out], l2["count"][:P_loc], N_DESC).contiguous()
+            am = torch.empty((world, 3, n_out), dtype=torch.int32, device=dev)
+            ac = torch.empty((world, P_loc), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(am, lm)
+            dist.all_gather_into_tensor(ac, l2["count"][:P_loc].contiguous())
+            tb = fe.tables()
+            ok = torch.equal(tb["count"], ac) and torch.equal(_masked_lists(torch, tb["m"], tb["count"], N_DESC), am)
+            ok = ok and np.array_equal(host_out.count[:P_loc], ac[rank].cpu().numpy())
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            e2e_ok = bool(flag.item())
+            if not e2e_ok:
+                raise SystemExit("e2e leg: the tables gathered by the host-path kernel differ from the NCCL gather")
+        e2e = {"value": pairs_per_step * e2e_steps / e2e_s, "unit": "pairs/s",
+               "h2d_bytes_per_step": int(2 * n_out * 32 + tab.nbytes), "d2h_bytes_per_step": n_match * 12 + P_loc * 4,
+               "bytes_are": "per rank", "ms_per_step": e2e_s / e2e_steps * 1e3, "matches_last_step_this_rank": n_match,
+               "copy_chunks": eng.launch_info().get("copy_chunks"), "exchange_in_timed_region": fe is not None,
+               "exchange_verified": e2e_ok,
+               "how": "numpy (pinned) in -> numpy (pinned) out through Engine.plan_batch(...).run: ONE kernel launch per step whose "
+                      "first CTAs stream the step's inputs from pinned host memory into HBM (copy_chunks = feed rounds) while the "
+                      "others match; results written by the kernel into pinned host memory" +
+                      (" AND, by the same epilogue, into every rank's symmetric table (NVSwitch multicast / peer stores), then "
+                       "the symmetric-memory barrier (overlapping the next step's kernel; the last one is waited for inside the "
+                       "timed region)" if fe is not None else "") + "; one stream sync per step"}
 
     line = {
         "metric": "hamming_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "loop_closing", "pairs_per_gpu": N_PAIRS, "desc_per_keyframe": N_DESC, "k": 2,
-                   "ratio": RATIO, "pairs_per_step_per_gpu": pairs_per_step,
-                   "l2": f"{N_SETS} rotating input sets, {N_SETS * 2 * n_out * 32 / 1e6:.0f} MB > 126 MB L2",
-                   "parallelism": (f"pair-sharded x{world}, match tables gathered by the kernel epilogue over NVLink "
-                                   f"({'NVSwitch multicast stores' if fused.multicast_ptr else 'peer stores'}) + overlapped barrier"
-                                   if fused is not None else f"pair-sharded x{world}, NCCL all_gather of match tables"
-                                   if gather_mode == "nccl" else f"DIAGNOSTIC: pair-sharded x{world} with NO exchange")
-                   if world > 1 else "single GPU"},
+        "config": bench_config(),
+        "run": {"pairs_this_rank": P_loc, "input_sets": n_sets, "input_mb_per_rank": n_sets * set_bytes / 1e6,
+                "parallelism": (f"pair list split x{world}, match tables gathered by the kernel epilogue over NVLink "
+                                f"({'NVSwitch multicast stores' if fused.multicast_ptr else 'peer stores'}) + symmetric-memory barrier "
+                                "per step (side stream, overlapping the next step's kernel; all inside the timed region)"
+                                if fused is not None else f"pair list split x{world}, NCCL all_gather of match tables"
+                                if gather_mode == "nccl" else f"DIAGNOSTIC: pair list split x{world} with NO exchange")
+                if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "launch": {k: info[k] for k in ("scan_grid", "scan_block", "queries_per_thread", "popc_mode",
                                         "train_rows_per_segment")},
-        "frames_per_s": N_PAIRS * world * args.steps / (ms * 1e-3),
+        "frames_per_s": N_PAIRS * args.steps / (ms * 1e-3),
+        "verify": verify,
     }
-    if gather_verified is not None:
-        line["gather_verified"] = gather_verified
+    if sync_ms is not None:
+        line["step_latency_ms_exchange_completed"] = sync_ms
+    line.update({k: v for k, v in verify.items() if k.startswith("gather_verified")})
+
+    # -- weak-scaling extra (round 1's headline form): every rank its own 256 pairs, exchange fused ----------------
+    if dist and fused is not None and not args.no_weak:
+        from boslam_b200.distributed import FusedGather
+        wq, wt = synth.keyframe_pair_batch(N_PAIRS, N_DESC, seed=5000 + rank)
+        wsets = [(torch.from_numpy(wq).to(dev), torch.from_numpy(wt).to(dev))]
+        for s_ in range(1, 4):   # 4 x 32.8 MB = 131 MB > L2
+            a, b = synth.keyframe_pair_batch(N_PAIRS, N_DESC, seed=5000 + 97 * s_ + rank)
+            wsets.append((torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)))
+        wtab = make_problems([N_DESC] * N_PAIRS, [N_DESC] * N_PAIRS)
+        fw = FusedGather(N_PAIRS * N_DESC, N_PAIRS, k=2)
+
+        def weak_step(i):
+            a, b = wsets[i % len(wsets)]
+            fw.run(eng, a, b, wtab, k=2, ratio=RATIO)
+            fw.barrier()
+        for i in range(args.warmup):
+            weak_step(i)
+        fw.wait()
+        wms = max_over_ranks(time_device_loop(torch, weak_step, args.steps, barrier, finish=fw.wait))
+        line["weak"] = {"value": pairs_per_step * world * args.steps / (wms * 1e-3), "unit": "pairs/s", "ms_per_step": wms / args.steps,
+                        "pairs_per_gpu": N_PAIRS, "note": "every rank matches its own 256 pairs; exchange fused, barrier in the timed region"}
+
+    if rank == 0 and world == 1 and not args.no_sustained:
+        # >= 2 s of back-to-back steps with the clock sampler running, beside the short burst above
+        n_sus = max(200, int(2200.0 / max(ms / args.steps, 1e-3)))
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        sms = time_device_loop(torch, device_step, n_sus, barrier)
+        line["sustained"] = {"value": pairs_per_step * n_sus / (sms * 1e-3), "unit": "pairs/s", "ms_per_step": sms / n_sus,
+                             "steps": n_sus, "seconds": sms * 1e-3, "clocks": s2.stop()}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cv2_reference as ref
@@ -594,7 +791,19 @@ def main():
                                     "sample": f"the full {N_PAIRS}-pair batch x {reps} reps, cv2 {ref.version()} knnMatch(k=2) + Python "
                                               f"ratio test incl. DMatch construction, os.cpu_count()={os.cpu_count()}",
                                     "ms_per_step": dt * 1e3, "matches": int(n_good)}
-            assert n_good == int(eng.match_batched(q, t, tab, k=2, ratio=RATIO).counts.sum()), "cv2 and engine disagree"
+            # the checker (outside every timed region): the engine's FULL tables of this batch against cv2's, entry by entry
+            ci, cd = cv2_tables(m, q, t, tab)
+            keep = (ci[:, 1] >= 0) & (cd[:, 0].astype(np.float64) < RATIO * cd[:, 1].astype(np.float64))
+            gi, gd, gres = eng.match_batched(q, t, tab, k=2, ratio=RATIO, want_knn=True)
+            same = np.array_equal(gi, ci) and np.array_equal(gd, cd) and int(gres.counts.sum()) == int(keep.sum()) == int(n_good)
+            for p in range(N_PAIRS):
+                rows = np.nonzero(keep[p * N_DESC:(p + 1) * N_DESC])[0]
+                a, b, c = gres[p]
+                same = same and np.array_equal(a, rows) and np.array_equal(b, ci[p * N_DESC + rows, 0]) and \
+                    np.array_equal(c.astype(np.int32), cd[p * N_DESC + rows, 0])
+            same = same and np.array_equal(all_ki[0].cpu().numpy(), ci) and np.array_equal(all_kd[0].cpu().numpy(), cd)
+            line["cpu_baseline"]["tables_equal_cv2"] = bool(same)
+            assert same, "cv2 and engine disagree on the headline batch (full knn tables + match lists)"
             try:  # also a 1-thread figure (8 of the 256 pairs)
                 import cv2
                 nthreads = cv2.getNumThreads()

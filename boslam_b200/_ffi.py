@@ -18,12 +18,12 @@ MASK_NONE, MASK_DENSE, MASK_WINDOW = 0, 1, 2
 MAX_TRAIN_ROWS = 1 << 22
 MAX_QUERY_ROWS = 1 << 22
 MAX_K = 16
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # every symbol include/bfm.h declares; tests/test_abi.py checks the library exports all of them
 EXPORTED_SYMBOLS = (
     "bfm_abi_version", "bfm_create", "bfm_destroy", "bfm_last_error", "bfm_match_batched", "bfm_knn",
-    "bfm_match", "bfm_match_batched_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
+    "bfm_match", "bfm_match_batched_multi", "bfm_match_batched_host_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
     "bfm_device_info", "bfm_host_alloc", "bfm_host_free", "bfm_map_create", "bfm_map_destroy", "bfm_map_update",
     "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview",
 )
@@ -93,6 +93,9 @@ def lib():
                                         ctypes.POINTER(Options), vp, vp, vp, vp, vp, vp, vp]
         L.bfm_match_batched_multi.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(Problem), i32, i32,
                                               ctypes.POINTER(Options), ctypes.POINTER(Outputs), i32, vp]
+        L.bfm_match_batched_host_multi.argtypes = [vp, vp, i32, vp, i32, ctypes.POINTER(Problem), i32, i32,
+                                                   ctypes.POINTER(Options), ctypes.POINTER(Outputs),
+                                                   ctypes.POINTER(Outputs), i32]
         L.bfm_map_create.argtypes = [vp, i32, ctypes.POINTER(vp)]
         L.bfm_map_destroy.argtypes = [vp]
         L.bfm_map_update.argtypes = [vp, i32, vp, vp, vp, vp]

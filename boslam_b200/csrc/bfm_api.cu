@@ -143,6 +143,11 @@ struct bfm_handle_s {
     uint32_t *h_ready = nullptr;  // pinned: staged rounds published by the host (read by the feeder CTAs)
     int host_threads = 0;         // tuning: 0 auto, -1 off
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // stream hand-over: every call leaves an event on its stream; a call that arrives on a DIFFERENT stream waits
+    // for it before it touches the shared workspace / tables (device calls are asynchronous)
+    cudaEvent_t last_ev = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool last_pending = false;
 
     bfm_launch_info_t info{};
     int64_t launches = 0;
@@ -347,7 +352,15 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
                const bfm_options_t *o, const bfm_outputs_t *dests, int n_dests, cudaStream_t st,
                const Gate *gate = nullptr, const int32_t *t_limit = nullptr, int32_t t_plan_rows = 0) {
     h->info = bfm_launch_info_t{};
-    if (n_problems <= 0 || n_out_rows <= 0) return BFM_OK;
+    if (n_problems <= 0) return BFM_OK;
+    if (n_out_rows <= 0) {
+        // every query set is empty: no kernel runs, but m_count is an output per problem and must read 0
+        for (int d = 0; d < n_dests && dests; ++d)
+            if (dests[d].m_count && !dests[d].multicast) CU_TRY(h, cudaMemsetAsync(dests[d].m_count, 0, (size_t)n_problems * 4, st));
+        return BFM_OK;
+    }
+    // stream hand-over: the workspace and the device tables are shared by all calls on this handle
+    if (h->last_pending && h->last_stream != st) CU_TRY(h, cudaStreamWaitEvent(st, h->last_ev, 0));
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(t)) & 15)
         return fail(h, BFM_ERR_INVALID, "descriptor arrays must be 16-byte aligned");
     if (n_dests < 1 || n_dests > bfm::MAX_DEST || !dests)
@@ -646,6 +659,9 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
     h->state_clean = true;  // every slot touched is restored by the CTA that finalizes its problem
+    CU_TRY(h, cudaEventRecord(h->last_ev, st));
+    h->last_stream = st;
+    h->last_pending = true;
 
     h->launches += binned ? 3 : passes * (defer ? 3 : 1);
     h->info.kernels_launched = binned ? 3 : passes * (defer ? 3 : 1);
@@ -721,6 +737,7 @@ int bfm_create(int device, bfm_handle_t *out) {
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_prog, 256) == cudaSuccess && cudaMemset(h->d_prog, 0, 256) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_ready, 256) == cudaSuccess && cudaMemset(h->d_ready, 0, 256) == cudaSuccess &&
          cudaMallocHost(&h->h_marks, sizeof(unsigned long long) * 2 * MAX_COPY_CHUNKS) == cudaSuccess &&
@@ -759,6 +776,7 @@ int bfm_destroy(bfm_handle_t h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     for (int i = 0; i < 2; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->last_ev) cudaEventDestroy(h->last_ev);
     if (h->in_stream) cudaStreamDestroy(h->in_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -774,6 +792,8 @@ static int check_call(bfm_handle_t h, const uint8_t *q, int32_t n_query_rows, co
     if (n_problems > 0 && !problems) return fail(h, BFM_ERR_INVALID, "problems is NULL");
     int rc = check_opts(h, opts, n_problems);
     if (rc) return rc;
+    if (opts->mask_kind == BFM_MASK_DENSE && opts->mask_row_stride < (int64_t)problems[0].t_count)
+        return fail(h, BFM_ERR_INVALID, "mask_row_stride must be >= t_count");
     if ((n_query_rows > 0 && !q) || (n_train_rows > 0 && !t)) return fail(h, BFM_ERR_INVALID, "descriptor pointer is NULL");
     CU_TRY(h, cudaSetDevice(h->device));
     return BFM_OK;
@@ -806,6 +826,21 @@ int bfm_match_batched_multi(bfm_handle_t h, const uint8_t *q, int32_t n_query_ro
     if (rc) return rc;
     return run_device(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, dests, n_dests,
                       stream == BFM_STREAM_OWN ? h->stream : static_cast<cudaStream_t>(stream));
+}
+
+int bfm_match_batched_host_multi(bfm_handle_t h, const uint8_t *q, int32_t n_query_rows, const uint8_t *t,
+                                 int32_t n_train_rows, const bfm_problem_t *problems, int32_t n_problems,
+                                 int32_t n_out_rows, const bfm_options_t *opts, const bfm_outputs_t *host_out,
+                                 const bfm_outputs_t *device_dests, int32_t n_device_dests) {
+    if (!h) return BFM_ERR_INVALID;
+    h->err.clear();
+    if (!host_out) return fail(h, BFM_ERR_INVALID, "host_out is NULL");
+    int rc = check_call(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts);
+    if (rc) return rc;
+    bfm_outputs_t user = *host_out;
+    user.multicast = 0;
+    return run_host(h, q, n_query_rows, t, n_train_rows, problems, n_problems, n_out_rows, opts, user, device_dests,
+                    n_device_dests);
 }
 
 int bfm_knn(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8_t *t, int32_t nt,

@@ -432,7 +432,7 @@ __device__ __noinline__ void feed_rows(const ScanParams &p) {
             for (int s = 0; s < 2; ++s) {
                 const int a = 2 * pair + s;
                 const unsigned long long rows = s ? (unsigned long long)p.feed_t_rows : (unsigned long long)p.feed_q_rows;
-                // rows per round is a multiple of 16; the first FEED_HEAD rounds are eighths of a round, so the
+                // rows per round is a multiple of 128; the first FEED_HEAD rounds are eighths of a round, so the
                 // matching CTAs of the first problems start after a few microseconds of upload
                 const unsigned long long per_round = rows * (pair == 0 ? 32ull : 8ull);
                 const unsigned long long b0 = r < FEED_HEAD ? (unsigned long long)r * (per_round / FEED_HEAD)
@@ -613,15 +613,17 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         const int lr = r * NT + tid;
         valid[r] = lr < sg.q_valid;
         const int row = sg.q_row0 + (valid[r] ? lr : 0);
-        const uint4 a = __ldg(p.q + 2 * (size_t)row);
-        const uint4 b = __ldg(p.q + 2 * (size_t)row + 1);
+        // .cg (L2) loads: on the SM-fed host path these arrays are written by feeder CTAs of this very launch, and
+        // ld.global.nc is only defined for memory that is read-only for the kernel's lifetime
+        const uint4 a = __ldcg(p.q + 2 * (size_t)row);
+        const uint4 b = __ldcg(p.q + 2 * (size_t)row + 1);
         qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
         qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
         if (XF) transform_desc(qw[r]);
         ibias[r] = (uint32_t)(sg.q_local0 + lr);
         if (MASK == 0 && !valid[r]) ibias[r] = KEY_DEAD;
         if (MASK == 2) {
-            const float2 xy = __ldg(p.q_xy + row);
+            const float2 xy = __ldcg(p.q_xy + row);
             // an absent row gets NaN coordinates: every window compare is false
             qx[r] = valid[r] ? xy.x : __int_as_float(0x7fc00000);
             qy[r] = xy.y;
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         bulk_g2s(&s_t[c & 1][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[c & 1]);
     };
     auto stage_xy = [&](int c) {
-        if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldg(p.t_xy + t_row0 + c * TT + tid);
+        if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldcg(p.t_xy + t_row0 + c * TT + tid);
     };
     auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
         mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));

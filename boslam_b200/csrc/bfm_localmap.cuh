@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(LM_NT) lm_compact_kernel(const MapView map, co
     if (blockIdx.x == gridDim.x - 1 && tid == 0) {
         int before = 0;
         for (int w = 0; w < LM_NT / 32; ++w) before += s_red[w];
-        *n_visible = before + mine;
+        n_visible[0] = before + mine;
+        n_visible[1] = 0;   // match count: stays 0 unless the matcher runs (it writes hdr[1] in its finalize)
     }
     if (!vis) return;
     pos += __popc(bal & ((1u << lane) - 1u));

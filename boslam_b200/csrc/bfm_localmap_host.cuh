@@ -129,7 +129,10 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
         return fail(h, BFM_ERR_INVALID, "bad sizes or NULL inputs");
     if (n_edges >= BFM_MAX_TRAIN_ROWS || nq >= BFM_MAX_QUERY_ROWS) return fail(h, BFM_ERR_INVALID, "more than 2^22 - 1 rows");
     if (opts->mask_kind == BFM_MASK_DENSE) return fail(h, BFM_ERR_INVALID, "a dense mask is not meaningful here: use the window");
-    if (opts->k > 2) return fail(h, BFM_ERR_INVALID, "k <= 2 on the tracking path");
+    if (opts->k < 1 || opts->k > 2) return fail(h, BFM_ERR_INVALID, "k must be 1 or 2 on the tracking path");
+    if (opts->cross_check && opts->k != 1) return fail(h, BFM_ERR_INVALID, "cross_check requires k == 1 (cv2 asserts the same)");
+    if (opts->cross_check && opts->ratio >= 0) return fail(h, BFM_ERR_INVALID, "cross_check and ratio are exclusive");
+    if (opts->mask_kind != BFM_MASK_NONE && opts->mask_kind != BFM_MASK_WINDOW) return fail(h, BFM_ERR_INVALID, "bad mask_kind");
     *n_visible = 0;
     *n_matches = 0;
     if (n_edges == 0) return BFM_OK;

@@ -48,9 +48,19 @@ bool host_ptr_is_pinned(const void *p) {
 
 int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t, int32_t nt_rows,
              const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows, const bfm_options_t *o,
-             const bfm_outputs_t &user) {
-    if (n_problems <= 0 || n_out_rows <= 0) return BFM_OK;
+             const bfm_outputs_t &user, const bfm_outputs_t *extra = nullptr, int n_extra = 0) {
+    // `extra`: up to 7 more destination sets in DEVICE memory (this GPU's or NVLink peers' / a multicast address):
+    // the same epilogue that writes the caller's host arrays also delivers the multi-GPU gather (bfm_match_batched_host_multi)
+    if (n_extra < 0 || n_extra > bfm::MAX_DEST - 1 || (n_extra > 0 && !extra))
+        return fail(h, BFM_ERR_INVALID, "between 0 and 7 extra device destinations are supported");
+    if (n_problems <= 0) return BFM_OK;
+    if (n_out_rows <= 0) {   // every query set is empty: m_count is still an output per problem
+        if (user.m_count) std::memset(user.m_count, 0, (size_t)n_problems * 4);
+        return BFM_OK;
+    }
     cudaStream_t st = h->stream, sin = h->in_stream;
+    // (a device call may still be running on a caller stream: run_device orders `st` behind it before the shared
+    // workspace is touched; d_in and the staging blocks are only ever used by these synchronous host calls)
     const bool window = o->mask_kind == BFM_MASK_WINDOW;
     const bool dense = o->mask_kind == BFM_MASK_DENSE && o->mask;
     const size_t qb = (size_t)nq_rows * 32, tb = (size_t)nt_rows * 32;
@@ -88,7 +98,11 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
                                        ((reinterpret_cast<uintptr_t>(user.knn_idx) | reinterpret_cast<uintptr_t>(user.knn_dist)) & 7) == 0)) &&
                         (!want_m || (host_ptr_is_pinned(user.m_query) && host_ptr_is_pinned(user.m_train) &&
                                      host_ptr_is_pinned(user.m_dist) && host_ptr_is_pinned(user.m_count)));
-    bfm_outputs_t dst = user;
+    bfm_outputs_t dests[bfm::MAX_DEST];
+    bfm_outputs_t &dst = dests[0];
+    dst = user;
+    for (int d = 0; d < n_extra; ++d) dests[1 + d] = extra[d];
+    const int n_dests = 1 + n_extra;
     if (!direct) {
         if (h->h_out_cap < out_total) {
             if (h->h_out) CU_TRY(h, cudaFreeHost(h->h_out));
@@ -133,8 +147,10 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         const int rows_per_round = std::max(h->feed_rows > 0 ? h->feed_rows : 8192, std::max(nq_rows, nt_rows) / 60000 + 1);  // rounds fit 16 bits
         const int S = std::max(1, (std::max(nq_rows, nt_rows) + rows_per_round - 1) / rows_per_round);
         gate.rounds = S + bfm::FEED_HEAD - 1;   // the first round is delivered as FEED_HEAD short ones
-        gate.q_rows = std::max(16, (((nq_rows + S - 1) / S) + 15) & ~15);
-        gate.t_rows = std::max(16, (((nt_rows + S - 1) / S) + 15) & ~15);
+        // rows per round are multiples of 128, so even the eighth-rounds of the head end on 128-byte boundaries of
+        // every array (16 rows x 8 B of pixel coordinates): no 32-byte sector is shared by two rounds
+        gate.q_rows = std::max(128, (((nq_rows + S - 1) / S) + 127) & ~127);
+        gate.t_rows = std::max(128, (((nt_rows + S - 1) / S) + 127) & ~127);
         gate.src[0] = q; gate.dst[0] = din + o_q; gate.bytes[0] = qb;
         gate.src[1] = t; gate.dst[1] = din + o_t; gate.bytes[1] = tb;
         if (window) {
@@ -145,7 +161,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         gate.epoch = next_feed_epoch(h, st);
         const double t_prep = cpu_ms();
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
-                        nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st, &gate);
+                        nt_rows, problems, n_problems, n_out_rows, &od, dests, n_dests, st, &gate);
         const double t_launched = cpu_ms();
         if (rc) {
             cudaDeviceSynchronize();
@@ -179,8 +195,10 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         const int rows_per_round = std::max(h->feed_rows > 0 ? h->feed_rows : 8192, std::max(nq_rows, nt_rows) / 60000 + 1);  // rounds fit 16 bits
         const int S = std::max(1, (std::max(nq_rows, nt_rows) + rows_per_round - 1) / rows_per_round);
         gate.rounds = S + bfm::FEED_HEAD - 1;
-        gate.q_rows = std::max(16, (((nq_rows + S - 1) / S) + 15) & ~15);
-        gate.t_rows = std::max(16, (((nt_rows + S - 1) / S) + 15) & ~15);
+        // rows per round are multiples of 128, so even the eighth-rounds of the head end on 128-byte boundaries of
+        // every array (16 rows x 8 B of pixel coordinates): no 32-byte sector is shared by two rounds
+        gate.q_rows = std::max(128, (((nq_rows + S - 1) / S) + 127) & ~127);
+        gate.t_rows = std::max(128, (((nt_rows + S - 1) / S) + 127) & ~127);
         const void *user[4] = {q, t, window ? (const void *)o->q_xy : nullptr, window ? (const void *)o->t_xy : nullptr};
         const size_t offs[4] = {o_q, o_t, o_qxy, o_txy}, bytes[4] = {qb, tb, qxy_b, txy_b};
         for (int a = 0; a < 4; ++a) {
@@ -235,7 +253,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         const double t_submitted = cpu_ms();
         gate.epoch = next_feed_epoch(h, st);
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
-                        nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st, &gate);
+                        nt_rows, problems, n_problems, n_out_rows, &od, dests, n_dests, st, &gate);
         const double t_launched = cpu_ms();
         h->pool->help_and_wait();   // also after a failed launch: the jobs reference this call's buffers
         advance();
@@ -264,7 +282,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         }
         const double t_copies = cpu_ms();
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
-                        nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st);
+                        nt_rows, problems, n_problems, n_out_rows, &od, dests, n_dests, st);
         if (rc) return rc;
         const double t_launch = cpu_ms();
         CU_TRY(h, cudaStreamSynchronize(st));
@@ -340,7 +358,7 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         gate.status = h->h_status;
         const double t_launch0 = cpu_ms();
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),
-                        nt_rows, problems, n_problems, n_out_rows, &od, &dst, 1, st, &gate);
+                        nt_rows, problems, n_problems, n_out_rows, &od, dests, n_dests, st, &gate);
         const double t_launch1 = cpu_ms();
         // the remaining chunks MUST be queued even if the launch failed half-way: CTAs may be waiting
         int rc2 = BFM_OK;

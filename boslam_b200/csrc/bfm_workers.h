@@ -14,12 +14,19 @@
 #include <thread>
 #include <vector>
 #include <cstring>
+#if defined(__SSE2__) || defined(_M_X64)
 #include <emmintrin.h>
+#define BFM_HAVE_SSE2 1
+#endif
 
 // memcpy into pinned staging memory with non-temporal stores: the data is about to be read by the GPU over
 // PCIe, not by this CPU, and lines left modified in the CPU caches make those device reads several times
 // slower (measured: 2.4 ms instead of 1.2 ms per 32.8 MB batch with a cache-allocating memcpy).
 inline void stream_copy(void *dst, const void *src, size_t n) {
+#ifndef BFM_HAVE_SSE2
+    std::memcpy(dst, src, n);   // non-x86 host: no portable non-temporal store; plain copy + full fence
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+#else
     char *d = static_cast<char *>(dst);
     const char *s = static_cast<const char *>(src);
     while (n && (reinterpret_cast<uintptr_t>(d) & 15)) { *d++ = *s++; --n; }
@@ -39,6 +46,7 @@ inline void stream_copy(void *dst, const void *src, size_t n) {
     n &= 63;
     if (n) std::memcpy(d, s, n);
     _mm_sfence();
+#endif
 }
 
 class WorkerPool {

@@ -74,6 +74,35 @@ def gather_ragged(local, group=None):
     return torch.cat(parts, dim=0) if parts else out, lens
 
 
+def _symmetric_memory():
+    """``torch.distributed._symmetric_memory`` is a private torch module (present in torch 2.5 ... 2.11, the
+    version this package was written against).  Import it here, check the three entry points the fused gather
+    needs, and fail with a message that names the torch version instead of an AttributeError deep inside a step."""
+    import torch
+    try:
+        import torch.distributed._symmetric_memory as symm
+    except Exception as e:  # pragma: no cover - depends on the torch build
+        raise RuntimeError(f"torch {torch.__version__} has no torch.distributed._symmetric_memory ({e}); the fused gather "
+                           "needs it - use gather_fixed() / BFM_GATHER=nccl (plain NCCL all_gather) instead") from e
+    missing = [n for n in ("empty", "rendezvous") if not hasattr(symm, n)]
+    if missing:
+        raise RuntimeError(f"torch {torch.__version__}: torch.distributed._symmetric_memory lacks {missing}; the fused "
+                           "gather was written against torch 2.11 - use gather_fixed() / BFM_GATHER=nccl instead")
+    return symm
+
+
+def _multicast_ptr(hdl) -> int:
+    """NVSwitch multicast address of a symmetric-memory handle, 0 when this torch build / box does not provide one
+    (the epilogue then stores to every peer separately: measured 96.8 % instead of 99.9 % weak-scaling efficiency)."""
+    import os
+    import sys
+    if not hasattr(hdl, "multicast_ptr"):
+        print("[boslam_b200] symmetric-memory handle has no multicast_ptr in this torch build: per-peer stores", file=sys.stderr)
+        return 0
+    mc = int(hdl.multicast_ptr or 0)
+    return mc if (mc and os.environ.get("BFM_MULTICAST", "1") != "0") else 0
+
+
 class FusedGather:
     """Result tables of a sharded batch, gathered by the matching kernel itself.
 
@@ -95,7 +124,7 @@ class FusedGather:
     def __init__(self, n_out: int, n_problems: int, k: int = 1, want_knn: bool = False, group=None, device=None):
         import torch
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
+        symm = _symmetric_memory()
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         if self.world > 8:
@@ -112,9 +141,7 @@ class FusedGather:
         self.hdl = symm.rendezvous(self.buf, self.group)
         self._ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         # NVSwitch multicast (NVLS): one multimem.st from the kernel epilogue lands in every rank's buffer
-        import os
-        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
-        self.multicast_ptr = mc if (mc and os.environ.get("BFM_MULTICAST", "1") != "0") else 0
+        self.multicast_ptr = _multicast_ptr(self.hdl)
         self.step = 0
         self._torch = torch
         self._side = torch.cuda.Stream(device=dev)
@@ -148,6 +175,17 @@ class FusedGather:
             self._torch.cuda.current_stream().wait_event(self._barrier_done[n - self.SLOTS + 1])
         own, peers = self.destinations()
         engine.match_batched_device(q, t, problems, out=own, replicas=peers, want_knn=self.want_knn, **kw)
+
+    def run_host(self, plan, q, t, host_out):
+        """The same step from HOST arrays (``plan`` = :meth:`Engine.plan_batch` of this rank's block; ``q`` / ``t``
+        numpy, ideally pinned; ``host_out`` a :class:`HostBatchBuffers`): one kernel launch reads the inputs from host
+        memory, matches, writes this rank's match lists into ``host_out`` AND into slice ``rank`` of every rank's
+        table.  Synchronous (the host path always is); follow with :meth:`barrier`."""
+        n = self.step
+        if n >= self.SLOTS:   # the slot's last readers: the barrier that released them must have completed
+            self._barrier_done[n - self.SLOTS + 1].synchronize()
+        own, peers = self.destinations()
+        return plan.run(q, t, host_out, replicas=[own] + list(peers))
 
     def barrier(self):
         """All ranks' kernels of this step have finished (and their NVLink writes with them): the slot is

@@ -447,7 +447,9 @@ class Engine:
     def match_batched_device(self, q, t, problems: np.ndarray, k=1, ratio=None, cross_check=False,
                              max_distance=None, strict=False, window=None, want_knn=False, out=None,
                              replicas=None):
-        """Fully asynchronous device form: returns padded CUDA tensors, no host sync.
+        """Fully asynchronous device form: returns padded CUDA tensors, no host sync.  Queued on torch's current
+        stream; calls on one engine run in issue order even across streams (the library chains them with events,
+        include/bfm.h "streams"), because they share the engine's workspace.
 
         out = dict(m=int32[3, n_out], count=int32[P], knn_idx=..., knn_dist=...) may be passed to
         reuse buffers.  Matches of problem p sit at m[:, out_begin[p] : out_begin[p] + count[p]].
@@ -544,7 +546,10 @@ class BatchPlan:
         self._opts_ref = ctypes.byref(self.opts)
         self._offsets = probs[:, 4].copy()
 
-    def run(self, q: np.ndarray, t: np.ndarray, out: HostBatchBuffers) -> BatchResult:
+    def run(self, q: np.ndarray, t: np.ndarray, out: HostBatchBuffers, replicas=None) -> BatchResult:
+        """``replicas``: up to 7 dicts of raw DEVICE pointers (``m_query, m_train, m_dist, count`` [+ ``multicast``], as
+        :meth:`boslam_b200.distributed.FusedGather.destinations` builds them): the epilogue that writes ``out`` (host)
+        also writes every result there - host copies, match and the multi-GPU exchange in one call."""
         if (q.dtype != np.uint8 or t.dtype != np.uint8 or not q.flags.c_contiguous or not t.flags.c_contiguous or
                 q.ndim != 2 or t.ndim != 2 or q.shape[1] != DESC_BYTES or t.shape[1] != DESC_BYTES or
                 q.shape[0] < self.nq_min or t.shape[0] < self.nt_min or (q.ctypes.data | t.ctypes.data) & 15):
@@ -554,11 +559,24 @@ class BatchPlan:
         eng = self.engine
         if self.P and self.n_out:
             m = out.m
-            with eng._lock:
-                rc = eng._lib.bfm_match_batched(eng._h, _ffi.MEM_HOST, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
-                                                self._pp, self.P, self.n_out, self._opts_ref, None, None, m[0].ctypes.data,
-                                                m[1].ctypes.data, m[2].ctypes.data, out.count.ctypes.data, None)
-                _ffi.check(eng._h, rc)
+            if replicas:
+                host = _ffi.Outputs()
+                host.m_query, host.m_train, host.m_dist = m[0].ctypes.data, m[1].ctypes.data, m[2].ctypes.data
+                host.m_count = out.count.ctypes.data
+                dests = (_ffi.Outputs * len(replicas))()
+                for d, o in zip(dests, replicas):
+                    Engine._fill_outputs(d, o, False)
+                with eng._lock:
+                    rc = eng._lib.bfm_match_batched_host_multi(eng._h, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
+                                                               self._pp, self.P, self.n_out, self._opts_ref,
+                                                               ctypes.byref(host), dests, len(replicas))
+                    _ffi.check(eng._h, rc)
+            else:
+                with eng._lock:
+                    rc = eng._lib.bfm_match_batched(eng._h, _ffi.MEM_HOST, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
+                                                    self._pp, self.P, self.n_out, self._opts_ref, None, None, m[0].ctypes.data,
+                                                    m[1].ctypes.data, m[2].ctypes.data, out.count.ctypes.data, None)
+                    _ffi.check(eng._h, rc)
         cnt = out.count[:self.P]
         if self.none_pass:
             cnt[:] = 0
@@ -570,10 +588,17 @@ _default_lock = threading.Lock()
 
 
 def default_engine(device: int = 0) -> Engine:
-    """Per-(thread, device) engine so concurrent callers never share a handle."""
+    """Per-(thread, device) engine so concurrent callers never share a handle.  Engines of threads that have
+    exited are closed (stream, pinned buffers, worker threads) the next time a new one is created."""
     key = (threading.get_ident(), int(device))
     with _default_lock:
-        e = _default_engines.get(key)
-        if e is None:
-            e = _default_engines[key] = Engine(device)
+        hit = _default_engines.get(key)
+        if hit is not None and hit[1].is_alive():
+            return hit[0]
+        for k, (eng, th) in list(_default_engines.items()):
+            if not th.is_alive() or k == key:   # thread idents are reused: a dead thread's entry must go first
+                del _default_engines[k]
+                eng.close()
+        e = Engine(device)
+        _default_engines[key] = (e, threading.current_thread())
         return e

@@ -157,8 +157,13 @@ class BFMatcher:
             queryDescriptors = queryDescriptors_in
             nq = len(queryDescriptors)
             rows = [()] * nq
-            for a, b, c in zip(qi.tolist(), ti.tolist(), d.tolist()):
-                rows[a] = (DMatch(a, b, 0, c),)
+            if bounds is None:
+                img_l, loc_l = repeat(0), ti.tolist()
+            else:   # add()/train() collection: per-image trainIdx + imgIdx, as match() and the plain knn path
+                img, loc = self._img_index(ti, bounds)
+                img_l, loc_l = img.tolist(), loc.tolist()
+            for a, b, im, c in zip(qi.tolist(), loc_l, img_l, d.tolist()):
+                rows[a] = (DMatch(a, b, im, c),)
             if compactResult:
                 rows = [r for r in rows if r]
             return tuple(rows)

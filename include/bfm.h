@@ -27,6 +27,10 @@
  *                       caller's buffers (this is the e2e path bench.py times).
  *     The `problems` table and the options struct are always host memory.
  *   - the caller owns every input and output buffer; the handle owns only its workspace.
+ *   - streams: calls on one handle may use different streams (BFM_MEM_DEVICE with caller streams, the
+ *     handle's own stream for BFM_MEM_HOST / bfm_track_local_map).  The handle's workspace is shared, so
+ *     every call leaves an event behind and a call arriving on another stream first waits for it
+ *     (cudaStreamWaitEvent): calls on one handle execute in the order they were issued, whatever their streams.
  *   - a handle is NOT re-entrant: one thread at a time per handle.  Different handles are
  *     independent (own stream, own workspace), which is how boslam's two threads
  *     (tracking in main, local mapping in a daemon thread, reference slam/main.py:37-47) use it.
@@ -44,7 +48,7 @@
 extern "C" {
 #endif
 
-#define BFM_ABI_VERSION 4
+#define BFM_ABI_VERSION 5
 #define BFM_DESC_BYTES 32
 /* per-problem limits of the packed (distance, index) keys the kernels reduce over;
  * cv2 itself refuses train sets of 2^18 rows or more (matchers.cpp:860, rule R7). */
@@ -153,6 +157,20 @@ int bfm_match_batched_multi(bfm_handle_t h,
                             const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
                             const bfm_options_t *opts,
                             const bfm_outputs_t *dests, int32_t n_dests, void *stream);
+
+/*
+ * The same with HOST caller arrays (the BFM_MEM_HOST path of bfm_match_batched: upload overlapped with the one
+ * kernel launch, results written into `host_out`, host pointers) plus n_device_dests (0..7) destination sets in
+ * DEVICE memory - this GPU's, NVLink peers' or an NVSwitch multicast address - written by the same epilogue.
+ * One call = host copies + match + multi-GPU exchange of a rank's pair block; the caller only
+ * needs a barrier afterwards.  Synchronous like every BFM_MEM_HOST call.
+ */
+int bfm_match_batched_host_multi(bfm_handle_t h,
+                                 const uint8_t *q, int32_t n_query_rows,
+                                 const uint8_t *t, int32_t n_train_rows,
+                                 const bfm_problem_t *problems, int32_t n_problems, int32_t n_out_rows,
+                                 const bfm_options_t *opts, const bfm_outputs_t *host_out,
+                                 const bfm_outputs_t *device_dests, int32_t n_device_dests);
 
 /* Single-problem conveniences (what slam/tracking.py:56,121 bind to). */
 int bfm_knn(bfm_handle_t h, int mem, const uint8_t *q, int32_t nq, const uint8_t *t, int32_t nt,

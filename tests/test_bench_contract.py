@@ -22,6 +22,9 @@ def test_reference_arm_prints_one_json_line():
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert k in d, k
     assert d["vs_baseline"] is None and d["higher_is_better"] is True and d["value"] > 0 and "workload" in d["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.bench_config() and d["scaling"] == "strong"   # both arms print the same config dict
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     e = d["e2e"]
@@ -55,13 +58,16 @@ def test_b200_arm_line_has_every_contract_key():
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert "impl" not in d and d["metric"] == "hamming_pairs_per_s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3
-    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "u32" and d["data"] == "synthetic"
-    assert d["config"]["workload"] == "loop_closing" and "l2" in d["config"]
+    assert d["scaling"] == "strong" and d["vs_baseline"] is None and d["dtype"] == "u32" and d["data"] == "synthetic"
+    assert d["config"]["workload"] == "loop_closing" and "l2" in d["config"] and d["config"]["pairs"] == 256
     assert d["gpu_launches"] == 3                                    # one kernel per step
     r = d["roofline"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in r, k
-    assert r["frac"] > 0.5 and r["traffic"] and r["hbm"]["peak"] > 0
+    assert r["frac"] > 0.5 and r["hbm"]["peak"] > 0
+    assert abs(r["kernel_ms"] - d["ms_per_step"]) < 1e-9             # measured live, over the timed region
+    assert d["verify"]["tables_crc32"] > 0 and d["cpu_baseline"]["tables_equal_cv2"] is True
+    assert d["sustained"]["seconds"] >= 2.0 and d["sustained"]["value"] > 0
     assert 0.5 < r["frac_issued"] <= 1.0 and r["popc_issued_per_pair"] == 4     # against the POPCs really issued
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 30e6 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]

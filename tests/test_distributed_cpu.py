@@ -83,3 +83,32 @@ def test_sharded_gather_world2_gloo(ragged):
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert ret.get(0) is True and ret.get(1) is True
+
+
+def test_symmetric_memory_guard_and_multicast_fallback(monkeypatch, capsys):
+    """The fused gather rests on the private torch.distributed._symmetric_memory: a torch build without the entry
+    points it needs must fail with a message that says so, and a handle without multicast_ptr must select the
+    per-peer-store fallback (multicast_ptr == 0) instead of raising."""
+    import sys
+    import types
+    from boslam_b200 import distributed as D
+    symm = D._symmetric_memory()                       # this image's torch has it
+    assert hasattr(symm, "empty") and hasattr(symm, "rendezvous")
+    fake = types.ModuleType("torch.distributed._symmetric_memory")
+    fake.empty = lambda *a, **k: None                  # rendezvous is gone
+    monkeypatch.setitem(sys.modules, "torch.distributed._symmetric_memory", fake)
+    import torch.distributed as td
+    monkeypatch.setattr(td, "_symmetric_memory", fake, raising=False)
+    with pytest.raises(RuntimeError, match="rendezvous"):
+        D._symmetric_memory()
+
+    class NoMulticast:
+        pass
+
+    class WithMulticast:
+        multicast_ptr = 0x7F0000000000
+    assert D._multicast_ptr(NoMulticast()) == 0 and "per-peer stores" in capsys.readouterr().err
+    monkeypatch.delenv("BFM_MULTICAST", raising=False)
+    assert D._multicast_ptr(WithMulticast()) == 0x7F0000000000
+    monkeypatch.setenv("BFM_MULTICAST", "0")
+    assert D._multicast_ptr(WithMulticast()) == 0
