@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "bfm_abi_version", "bfm_create", "bfm_destroy", "bfm_last_error", "bfm_match_batched", "bfm_knn",
     "bfm_match", "bfm_match_batched_multi", "bfm_match_batched_host_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
     "bfm_device_info", "bfm_host_alloc", "bfm_host_free", "bfm_map_create", "bfm_map_destroy", "bfm_map_update",
-    "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview",
+    "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview", "bfm_debug_timeline",
 )
 
 
@@ -108,6 +108,7 @@ def lib():
         L.bfm_set_tuning.argtypes = [vp, ctypes.c_char_p, i32]
         L.bfm_kernel_launch_count.argtypes = [vp]
         L.bfm_kernel_launch_count.restype = i64
+        L.bfm_debug_timeline.argtypes = [vp, vp, i32]
         L.bfm_microbench.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.bfm_device_info.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),

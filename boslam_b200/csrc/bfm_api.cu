@@ -48,52 +48,21 @@ constexpr int MAX_COPY_CHUNKS = 64;  // input chunks of the pipelined host path
 std::string g_create_error;
 std::mutex g_create_mutex;
 
-typedef void (*ScanFn)(const ScanParams);
+using bfm::ScanFn;
 
-template <int R, int MODE, int MASK, int PM>
-ScanFn scan_fn() {
-    // MODE 0: k=1, 1: k=1 + cross-check, 2: k=2
-    return bfm::bfm_scan_kernel<R, (MODE == 2 ? 2 : 1), (MODE == 1), MASK, PM, NT>;
-}
-template <int R, int MODE, int MASK>
-ScanFn pick_pm(int pm) {
-    switch (pm) {
-        case 4: return scan_fn<R, MODE, MASK, 4>();
-        case 5: return scan_fn<R, MODE, MASK, 5>();
-        case 6: return scan_fn<R, MODE, MASK, 6>();
-        case 40: return scan_fn<R, MODE, MASK, 40>();
-        case 50: return scan_fn<R, MODE, MASK, 50>();
-        default: return scan_fn<R, MODE, MASK, 8>();
-    }
-}
-template <int R, int MODE>
-ScanFn pick_mask(int mask, int pm) {
-    switch (mask) {
-        case 1: return pick_pm<R, MODE, 1>(pm);
-        case 2: return pick_pm<R, MODE, 2>(pm);
-        default: return pick_pm<R, MODE, 0>(pm);
-    }
-}
-template <int R>
-ScanFn pick_mode(int mode, int mask, int pm) {
-    switch (mode) {
-        case 1: return pick_mask<R, 1>(mask, pm);
-        case 2: return pick_mask<R, 2>(mask, pm);
-        default: return pick_mask<R, 0>(mask, pm);
-    }
-}
+// the kernel variants are instantiated in bfm_scan_inst.cu, one object per (register tile, mode)
 ScanFn pick_scan(int r, int mode, int mask, int pm, bool bound = false) {
-    if (bound) {  // k > 2 passes: R = 1, K = 2, transformed carry-save popcount
-        switch (mask) {
-            case 1: return bfm::bfm_scan_kernel<1, 2, false, 1, 40, NT, true>;
-            case 2: return bfm::bfm_scan_kernel<1, 2, false, 2, 40, NT, true>;
-            default: return bfm::bfm_scan_kernel<1, 2, false, 0, 40, NT, true>;
-        }
-    }
-    switch (r) {
-        case 1: return pick_mode<1>(mode, mask, pm);
-        case 2: return pick_mode<2>(mode, mask, pm);
-        default: return pick_mode<4>(mode, mask, pm);
+    if (bound) return bfm::pick_scan_r1_m2(mask, pm, true);   // k > 2 passes: R = 1, K = 2, transformed carry-save popcount
+    switch (r * 10 + mode) {
+        case 10: return bfm::pick_scan_r1_m0(mask, pm, false);
+        case 11: return bfm::pick_scan_r1_m1(mask, pm, false);
+        case 12: return bfm::pick_scan_r1_m2(mask, pm, false);
+        case 20: return bfm::pick_scan_r2_m0(mask, pm, false);
+        case 21: return bfm::pick_scan_r2_m1(mask, pm, false);
+        case 22: return bfm::pick_scan_r2_m2(mask, pm, false);
+        case 40: return bfm::pick_scan_r4_m0(mask, pm, false);
+        case 41: return bfm::pick_scan_r4_m1(mask, pm, false);
+        default: return bfm::pick_scan_r4_m2(mask, pm, false);
     }
 }
 
@@ -149,6 +118,8 @@ struct bfm_handle_s {
     cudaStream_t last_stream = nullptr;
     bool last_pending = false;
 
+    unsigned long long *trace = nullptr;   // bfm_debug_timeline
+    int trace_cap = 0;
     bfm_launch_info_t info{};
     int64_t launches = 0;
     std::vector<Segment> segs_host;
@@ -648,11 +619,16 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         const ScanFn fn = pick_scan(r, mode, mask, pm, pass > 0);
         sp.defer_finalize = defer ? 1 : 0;
         if (pass > 0) sp.n_feed = 0;   // the inputs are resident after the first pass
+        sp.trace = pass == 0 ? h->trace : nullptr;
+        sp.trace_cap = h->trace_cap;
+        sp.trace_base = 0;
         fn<<<(unsigned)(n_segs + (pass == 0 ? n_feed : 0)), NT, 0, st>>>(sp);
         CU_TRY(h, cudaGetLastError());
         if (defer) {
+            sp.trace_base = (int)n_segs + n_feed;
             bfm::fin_count_kernel<<<fin_tiles, bfm::FT_NT, 0, st>>>(sp, d_keep, d_tile);
             CU_TRY(h, cudaGetLastError());
+            sp.trace_base += fin_tiles;
             bfm::fin_write_kernel<<<fin_tiles, bfm::FT_NT, 0, st>>>(sp, d_keep, d_tile);
             CU_TRY(h, cudaGetLastError());
         }
@@ -919,6 +895,13 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
 }
 
 int64_t bfm_kernel_launch_count(bfm_handle_t h) { return h ? h->launches : 0; }
+
+int bfm_debug_timeline(bfm_handle_t h, uint64_t *device_buf, int32_t capacity_ctas) {
+    if (!h || capacity_ctas < 0) return BFM_ERR_INVALID;
+    h->trace = capacity_ctas > 0 ? reinterpret_cast<unsigned long long *>(device_buf) : nullptr;
+    h->trace_cap = h->trace ? capacity_ctas : 0;
+    return BFM_OK;
+}
 
 // Host-only: the work-item plan a batch would get.  No device is touched, so the planner's invariants are
 // testable on a box without a GPU (tests/test_planner_cpu.py).

@@ -118,6 +118,10 @@ struct ScanParams {
     // Result destinations.  dest[0] is the caller's buffers (device memory, or pinned host memory
     // written over PCIe on the host path); dest[1..] are the same buffers of NVLink peers
     // (multi-GPU gather fused into the epilogue).  Each pointer may be NULL.
+    // debug timeline (bfm_debug_timeline): CTA b of the launch stores %globaltimer at up to 8 points of its life into
+    // trace[(trace_base + b) * 8 ..]; NULL (the normal case) costs one uniform predicate per point
+    unsigned long long *trace;
+    int32_t trace_base, trace_cap;
     int32_t n_dest;
     uint32_t dest_multicast;   // bit d set: dest[d] holds NVSwitch multicast addresses (one multimem.st reaches every GPU)
     struct Dest {
@@ -164,6 +168,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+// debug timeline: one thread per CTA stamps point `slot` (0..7); see ScanParams::trace
+__device__ __forceinline__ void trace_mark(const ScanParams &p, int slot) {
+    if (p.trace != nullptr && threadIdx.x == 0 && (int)blockIdx.x + p.trace_base < p.trace_cap)
+        p.trace[(size_t)(p.trace_base + (int)blockIdx.x) * 8 + slot] = global_timer_ns();
 }
 
 // ---- 256-bit Hamming distance ------------------------------------------------------------------
@@ -502,6 +511,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         if (!p.feed_stall) feed_rows<NT>(p);
         return;
     }
+    trace_mark(p, 0);   // CTA entry
     const Segment sg = p.segs[blockIdx.x - p.n_feed];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -660,6 +670,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         }
     };
 
+    trace_mark(p, 1);   // gates passed, TMA issued, queries loaded
     __syncthreads();   // barrier init (thread 0, above) visible to every waiter
     if (nchunks > 0) {
         stage_xy(0);
@@ -667,6 +678,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         land(0);
     }
     __syncthreads();
+    trace_mark(p, 2);   // first chunk landed
 
     for (int c = 0; c < nchunks; ++c) {
         const int b = c & 1;
@@ -778,6 +790,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         }
     }
 
+    trace_mark(p, 3);   // scan done
     // -- commit: associative min-merge into the global row state ---------------------------------
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -800,6 +813,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
 
     // -- problem completion: the CTA whose segment is the last of its problem finalizes it -------------
     // (threadfence + counter: every CTA's state updates are visible before its count is)
+    trace_mark(p, 4);   // commit atomics issued
     if (p.defer_finalize) return;   // one very large problem: finalized by the tile-parallel kernels below
     __threadfence();
     __syncthreads();
@@ -810,9 +824,12 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         if (s_flag) p.done[sg.problem] = 0xFFFFFFFFu;              // self-cleaning, like the rest of the workspace
     }
     __syncthreads();
+    trace_mark(p, 5);   // done counter bumped
     if (s_flag) {
         __threadfence();
         finalize_problem<NT>(p, sg.problem, s_cnt);
+        __syncthreads();
+        trace_mark(p, 6);   // finalized (only the CTA that completed its problem)
     }
 }
 
@@ -825,7 +842,10 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
 // rows of all earlier tiles (ascending queryIdx is preserved) and restores the workspace.
 constexpr int FT_NT = 256, FT_RPT = 4, FT_ROWS = FT_NT * FT_RPT;
 
+#ifndef BFM_SCAN_INST_ONLY   // non-template kernels: defined once, in bfm_api.cu
+
 __global__ void __launch_bounds__(FT_NT) fin_count_kernel(const __grid_constant__ ScanParams p, uint8_t *keep_flag, int32_t *tile_count) {
+    trace_mark(p, 0);
     const Problem pr = p.problems[0];
     const int k = p.k;
     int kept = 0;
@@ -872,12 +892,14 @@ __global__ void __launch_bounds__(FT_NT) fin_count_kernel(const __grid_constant_
         for (int i = 0; i < FT_NT / 32; ++i) t += s_sum[i];
         tile_count[blockIdx.x] = t;
     }
+    trace_mark(p, 6);
 }
 
 __global__ void __launch_bounds__(FT_NT) fin_write_kernel(const __grid_constant__ ScanParams p, const uint8_t *keep_flag,
                                                           const int32_t *tile_count) {
     __shared__ int s_red[FT_NT / 32];
     __shared__ int s_cnt[FT_RPT][FT_NT / 32];
+    trace_mark(p, 0);
     const Problem pr = p.problems[0];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int part = 0;
@@ -929,6 +951,21 @@ __global__ void __launch_bounds__(FT_NT) fin_write_kernel(const __grid_constant_
             if (p.dest[d].m_count) put_i32(p.dest[d].m_count, before + tile_total, (p.dest_multicast >> d) & 1u);
     if (p.cross_check)   // every column-key read happened in fin_count; all tiles share the reset
         for (int j = blockIdx.x * FT_NT + tid; j < pr.t_count; j += gridDim.x * FT_NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
+    trace_mark(p, 6);
 }
+
+#endif  // BFM_SCAN_INST_ONLY
+
+typedef void (*ScanFn)(const ScanParams);
+// defined in bfm_scan_inst.cu (compiled once per register tile R and mode: 0 k = 1, 1 cross-check, 2 k = 2)
+ScanFn pick_scan_r1_m0(int mask, int pm, bool bound);
+ScanFn pick_scan_r1_m1(int mask, int pm, bool bound);
+ScanFn pick_scan_r1_m2(int mask, int pm, bool bound);
+ScanFn pick_scan_r2_m0(int mask, int pm, bool bound);
+ScanFn pick_scan_r2_m1(int mask, int pm, bool bound);
+ScanFn pick_scan_r2_m2(int mask, int pm, bool bound);
+ScanFn pick_scan_r4_m0(int mask, int pm, bool bound);
+ScanFn pick_scan_r4_m1(int mask, int pm, bool bound);
+ScanFn pick_scan_r4_m2(int mask, int pm, bool bound);
 
 }  // namespace bfm

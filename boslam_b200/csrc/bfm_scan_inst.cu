@@ -1,0 +1,54 @@
+// bfm_scan_inst.cu - instantiates the matching kernel (bfm_kernels.cuh) for ONE register tile and mode.
+// Compiled nine times (INST_R in {1, 2, 4} x INST_MODE in {0: k = 1, 1: cross-check, 2: k = 2}) so the variants
+// build in parallel; bfm_api.cu picks one through bfm_pick_scan_r<R>_m<MODE>().
+#define BFM_SCAN_INST_ONLY
+#include "bfm_kernels.cuh"
+
+#ifndef INST_R
+#error "compile with -DINST_R=1|2|4 -DINST_MODE=0|1|2"
+#endif
+
+namespace bfm {
+
+constexpr int INST_NT = 128;
+
+template <int MASK, int PM>
+static ScanFn inst_fn() {
+    return bfm_scan_kernel<INST_R, (INST_MODE == 2 ? 2 : 1), (INST_MODE == 1), MASK, PM, INST_NT>;
+}
+template <int MASK>
+static ScanFn inst_pm(int pm) {
+    switch (pm) {
+        case 4: return inst_fn<MASK, 4>();
+        case 5: return inst_fn<MASK, 5>();
+        case 6: return inst_fn<MASK, 6>();
+        case 40: return inst_fn<MASK, 40>();
+        case 50: return inst_fn<MASK, 50>();
+        default: return inst_fn<MASK, 8>();
+    }
+}
+
+#define BFM_CAT2(a, b, c, d) a##b##c##d
+#define BFM_CAT(a, b, c, d) BFM_CAT2(a, b, c, d)
+
+// mask: 0 none, 1 dense, 2 window; bound: the k > 2 pass variant (only R = 1, MODE = 2 has it)
+ScanFn BFM_CAT(pick_scan_r, INST_R, _m, INST_MODE)(int mask, int pm, bool bound) {
+#if INST_R == 1 && INST_MODE == 2
+    if (bound) {
+        switch (mask) {
+            case 1: return bfm_scan_kernel<1, 2, false, 1, 40, INST_NT, true>;
+            case 2: return bfm_scan_kernel<1, 2, false, 2, 40, INST_NT, true>;
+            default: return bfm_scan_kernel<1, 2, false, 0, 40, INST_NT, true>;
+        }
+    }
+#else
+    (void)bound;
+#endif
+    switch (mask) {
+        case 1: return inst_pm<1>(pm);
+        case 2: return inst_pm<2>(pm);
+        default: return inst_pm<0>(pm);
+    }
+}
+
+}  // namespace bfm

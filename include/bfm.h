@@ -261,6 +261,12 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t bfm_kernel_launch_count(bfm_handle_t h);
+/* Debug timeline of the matching kernel (tools/timeline_probe.py): with a device buffer uint64[capacity_ctas][8],
+ * CTA b of every following call's launch stores the GPU's %globaltimer (ns) at points of its life -
+ * [0] entry, [1] inputs requested, [2] first train chunk in shared memory, [3] scan done, [4] row keys committed,
+ * [5] completion counted, [6] problem finalized (only the CTA that did it) - into row b (the tile-parallel finalize
+ * kernels of a large single problem append their CTAs: [0] entry, [6] exit).  NULL / 0 switches it off (the default). */
+int bfm_debug_timeline(bfm_handle_t h, uint64_t *device_buf, int32_t capacity_ctas);
 
 /* Host-only preview of the work-item plan of a batch (no device needed; the CPU tests of the planner use it).
  * A work item is one CTA's share: a block of 128 x queries_per_thread query rows against a contiguous train
