@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "bfm_abi_version", "bfm_create", "bfm_destroy", "bfm_last_error", "bfm_match_batched", "bfm_knn",
     "bfm_match", "bfm_match_batched_multi", "bfm_match_batched_host_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
     "bfm_device_info", "bfm_host_alloc", "bfm_host_free", "bfm_map_create", "bfm_map_destroy", "bfm_map_update",
-    "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview", "bfm_debug_timeline",
+    "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview", "bfm_debug_timeline", "bfm_plan_preview_tiles",
 )
 
 
@@ -109,6 +109,7 @@ def lib():
         L.bfm_kernel_launch_count.argtypes = [vp]
         L.bfm_kernel_launch_count.restype = i64
         L.bfm_debug_timeline.argtypes = [vp, vp, i32]
+        L.bfm_plan_preview_tiles.argtypes = [ctypes.POINTER(Problem), i32, i32, vp, vp, i32, vp]
         L.bfm_microbench.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                      ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.bfm_device_info.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
@@ -180,3 +181,21 @@ def plan_preview(problems, queries_per_thread: int = 4, slots: int = 148 * 8, se
     if rc != BFM_OK:
         raise BfmError(rc, "bfm_plan_preview failed")
     return items, rows.value
+
+
+def plan_preview_tiles(problems, n_ctas: int = 148 * 8):
+    """Finalize tiles of the persistent form - host only.  Returns (tiles int32[m, 5] = {problem, row0, tile number,
+    tiles of the problem, look-back slot of tile 0}, tile_cta int32[m])."""
+    import numpy as np
+    L = lib()
+    tab = np.ascontiguousarray(problems, dtype=np.int32).reshape(-1, 6)
+    pp = tab.ctypes.data_as(ctypes.POINTER(Problem))
+    m = ctypes.c_int32()
+    rc = L.bfm_plan_preview_tiles(pp, len(tab), n_ctas, None, None, 0, ctypes.byref(m))
+    if rc != BFM_OK:
+        raise BfmError(rc, "bfm_plan_preview_tiles: invalid arguments")
+    tiles, tile_cta = np.empty((m.value, 5), np.int32), np.empty(m.value, np.int32)
+    rc = L.bfm_plan_preview_tiles(pp, len(tab), n_ctas, tiles.ctypes.data, tile_cta.ctypes.data, m.value, ctypes.byref(m))
+    if rc != BFM_OK:
+        raise BfmError(rc, "bfm_plan_preview_tiles failed")
+    return tiles, tile_cta

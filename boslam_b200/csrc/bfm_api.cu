@@ -36,13 +36,10 @@ constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
 // tapered tail of a batch (>= 8 problems): the last 10 % of the work is cut into segments of 1/2, then 1/4 of the
 // length - 256-pair batch 1046 -> 1026 us (980 -> 998 G pairs/s), pinned host path 1120 -> 1104 us
 // (tools/taper_probe.py, profiles/r01f_taper_probe.log)
+constexpr int GSS_MAX_ROWS = 512;
 constexpr int TAPER_AUTO = 4;
 constexpr int TAPER_PCT_AUTO = 10;
 constexpr int N_TABLE_SLOTS = 4;
-// a call that is ONE problem with this many query rows is finalized by the tile-parallel kernels: the single
-// finalizing CTA costs ~2.5 us per 1024 rows, two more launches ~3.5 us (tools/finalize_probe.py: 1000 rows
-// 18.6 vs 22.0 us, 2000 x 20000 cross-check 73.8 vs 66.7 us, 4096 x 4096 52 vs 42 us)
-constexpr int BIG_FINALIZE_ROWS = 1792;
 constexpr int MAX_COPY_CHUNKS = 64;  // input chunks of the pipelined host path
 
 std::string g_create_error;
@@ -83,7 +80,15 @@ struct bfm_handle_s {
     DevBuf state;    // rowstate (u64 per out row) followed by colkeys (u32 per problem-train row)
     DevBuf tables;   // device copy of [problems | segments]
     DevBuf lower;    // k > 2: per-row lower bound handed from one pass to the next
-    DevBuf fin;      // tile-parallel finalize of one very large problem: keep flags + tile counts
+    DevBuf finc;     // persistent form: look-back words of the finalize tiles (epoch-tagged, zeroed on allocation)
+    uint32_t fin_epoch = 0;
+    int persistent = 0;  // tuning: 0 auto (resident inputs take the persistent form), 1 off
+    int gss_div = 0, gss_min = 0;   // tuning: guided item lengths
+    std::vector<int2> cta_tiles_host;
+    std::vector<bfm::FinTile> fin_tiles_host;
+    int plan_ctas = 0;        // grid of the persistent form
+    uint32_t *d_queue = nullptr;   // two ticket counters used by alternate launches (each launch zeroes the other one)
+    int queue_phase = 0;
     DevBuf bins;     // binned window search: train rows in grid-cell order + cell table
     void *h_tables[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring
     size_t h_tables_cap[N_TABLE_SLOTS] = {0, 0, 0, 0};
@@ -102,7 +107,7 @@ struct bfm_handle_s {
     unsigned long long seq = 0;              // call sequence number (watermark epoch)
 
     // tuning knobs
-    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0, pipeline_min_kb = 0, finalize_rows = 0, taper = 0, taper_pct = 0;
+    int popc_mode = 0, qpt = 0, timing = 0, segment_rows = 0, waves = 0, pipeline_chunks = 0, window_bins = 0, feeders = 0, feed_rows = 0, test_stall = 0, pipeline_min_kb = 0, taper = 0, taper_pct = 0;
     uint32_t *d_prog = nullptr;   // SM-fed upload: progress words of the feeder CTAs
     uint32_t feed_epoch = 0;      // epoch of the last SM-fed call (1..65535)
     // pageable caller arrays: host threads stage them into pinned memory slice by slice for the feeders
@@ -127,7 +132,7 @@ struct bfm_handle_s {
     std::vector<Problem> probs_host, plan_probs;
     // plan cache + workspace hygiene
     bool plan_valid = false, state_clean = false;
-    int plan_sig[7] = {0, 0, 0, 0, 0, 0, 0};
+    int plan_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int plan_seg_rows = 0;
     std::vector<bfm_problem_t> plan_problems;
     // pipelined host path: the copy-in stream
@@ -186,7 +191,7 @@ int occupancy(bfm_handle_t h, int r, int mode, int mask, int pm, int *out) {
 // Cut every problem into (query block, train range) segments of near-equal cost so that the grid
 // is a few balanced waves over all SMs, whatever the batch shape.
 void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems, int r, int slots,
-                   std::vector<Segment> &segs, std::vector<int> &seg_begin, int *seg_rows_out) {
+                   std::vector<Segment> &segs, std::vector<int> &seg_begin, int *seg_rows_out, bool guided = false) {
     const int bq = NT * r;
     long long steps = 0;  // sum over query blocks of their train rows
     for (int p = 0; p < n_problems; ++p) {
@@ -227,9 +232,17 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
             }
         }
     }
+    // Guided item lengths (the persistent form draws items from a ticket counter): an item is 1/3 of an even share
+    // of the work that is LEFT when it starts - long items while the queue is full (few commits, few prologues), short
+    // ones at the end, so that even the CTAs the warp schedulers serve last (equal CTAs of one SM progress at rates
+    // up to 3x apart: profiles/r02_timeline.md) finish their last item with everybody else.
+    const bool gss = (guided && h->taper == 0 && h->segment_rows == 0) || h->taper == 16;
+    const int gss_min = h->gss_min > 0 ? h->gss_min : (r == 1 ? 32 : 16);
+    const long long gss_div = (long long)(h->gss_div > 0 ? h->gss_div : 3) * slots;
+    if (gss) L = (int)std::max<long long>(gss_min, std::min<long long>(GSS_MAX_ROWS, steps / gss_div + 1));
     *seg_rows_out = L;
-    // taper knob: 0 = auto, 1 = off, 2 / 4 / 8 = finest divisor of the segment length in the tail
-    const int taper_div = (h->segment_rows > 0 || n_problems < 8) ? 1 : (h->taper > 0 ? h->taper : TAPER_AUTO);
+    // taper knob: 0 = auto, 1 = off, 2 / 4 / 8 = finest divisor of the segment length in the tail, 16 = guided
+    const int taper_div = (gss || h->segment_rows > 0 || n_problems < 8) ? 1 : (h->taper > 0 ? h->taper : TAPER_AUTO);
     int taper_levels = 0;
     while ((1 << (taper_levels + 1)) <= taper_div) ++taper_levels;
     const double taper_frac = (h->taper_pct > 0 ? h->taper_pct : TAPER_PCT_AUTO) / 100.0;
@@ -261,6 +274,30 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
                 Lp = std::max(MIN_SEG_ROWS, L >> std::min(level, taper_levels));
             }
         }
+        if (gss) {
+            for (int qb = 0; qb * bq < pr.q_count; ++qb) {
+                int t0 = 0;
+                while (t0 < pr.t_count) {
+                    int cnt = (int)std::max<long long>(gss_min, std::min<long long>(GSS_MAX_ROWS, (steps - cum) / gss_div + 1));
+                    if (pr.t_count - t0 - cnt < gss_min) cnt = pr.t_count - t0;   // no slivers
+                    cnt = std::min(cnt, pr.t_count - t0);
+                    Segment sg;
+                    sg.q_row0 = pr.q_begin + qb * bq;
+                    sg.q_valid = std::min(bq, pr.q_count - qb * bq);
+                    sg.q_local0 = qb * bq;
+                    sg.out_row0 = pr.out_begin + qb * bq;
+                    sg.t_row0 = pr.t_begin + t0;
+                    sg.t_count = cnt;
+                    sg.t_local0 = t0;
+                    sg.problem = p;
+                    segs.push_back(sg);
+                    t0 += cnt;
+                    cum += cnt;
+                }
+            }
+            seg_begin[p + 1] = (int)segs.size();
+            continue;
+        }
         cum += (long long)((pr.q_count + bq - 1) / bq) * pr.t_count;
         const int nsp = (pr.t_count + Lp - 1) / Lp;
         const int base = pr.t_count / nsp, rem = pr.t_count % nsp;
@@ -282,6 +319,44 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
             }
         }
         seg_begin[p + 1] = (int)segs.size();
+    }
+}
+
+// The persistent form (resident inputs): at most ONE wave of CTAs drawing the work items of plan_segments from a ticket
+// counter; when the queue is empty the problems are finalized tile by tile (FT rows of one problem per tile).  Tile
+// (p, j) belongs to CTA owner(p, j), non-decreasing in j: a tile only waits for the tiles before it, i.e. for CTAs with
+// a lower or equal index, which the hardware dispatched no later than its own (the rule the feeder CTAs of the host
+// path rely on as well).  Owners rotate over the grid so the tiles of a batch spread evenly.
+constexpr int FT_ROWS_TILE = NT * bfm::FT_RPT;
+
+void plan_tiles(const bfm_problem_t *problems, int n_problems, int n_ctas, std::vector<bfm::FinTile> &tiles,
+                std::vector<int2> &cta_tiles) {
+    struct Owned { bfm::FinTile t; int owner; };
+    std::vector<Owned> own;
+    int slot = 0;
+    for (int p = 0; p < n_problems; ++p) {
+        const int rows = std::max(0, problems[p].q_count);
+        const int nt = std::max(1, (rows + FT_ROWS_TILE - 1) / FT_ROWS_TILE);
+        int base = slot % n_ctas;
+        if (nt <= n_ctas && base + nt > n_ctas) base = 0;
+        for (int j = 0; j < nt; ++j) {
+            Owned o;
+            o.t.problem = p; o.t.row0 = j * FT_ROWS_TILE; o.t.index = j; o.t.n_tiles = nt; o.t.slot0 = slot;
+            o.t.pad[0] = o.t.pad[1] = o.t.pad[2] = 0;
+            o.owner = nt <= n_ctas ? base + j : (int)((long long)j * n_ctas / nt);
+            own.push_back(o);
+        }
+        slot += nt;
+    }
+    std::stable_sort(own.begin(), own.end(), [](const Owned &a, const Owned &b) { return a.owner < b.owner; });
+    cta_tiles.assign((size_t)n_ctas, make_int2(0, 0));
+    tiles.clear();
+    tiles.reserve(own.size());
+    for (size_t i = 0; i < own.size(); ++i) {
+        int2 &w = cta_tiles[own[i].owner];
+        if (w.y == 0) w.x = (int)i;
+        ++w.y;
+        tiles.push_back(own[i].t);
     }
 }
 
@@ -414,8 +489,10 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
-    const int plan_sig[7] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots,
-                             h->taper * 1000 + h->taper_pct};
+    // resident inputs take the persistent form (at most one wave, tile-parallel finalize inside the same launch)
+    const bool persistent = !gate && !binned && h->persistent != 1;
+    const int plan_sig[8] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots,
+                             h->taper * 1000 + h->taper_pct + 100000 * h->gss_div + 10000000 * h->gss_min, persistent ? 1 : 0};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
                           h->plan_problems.size() == (size_t)n_problems &&
                           std::memcmp(h->plan_problems.data(), problems, sizeof(bfm_problem_t) * (size_t)n_problems) == 0;
@@ -437,20 +514,29 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         h->plan_probs = h->probs_host;
         h->plan_probs[0].n_segs = bin_grid;   // the search kernel's CTAs play the role of segments
     } else if (!plan_hit) {
-        plan_segments(h, plan_problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows);
+        // (a device-side train count re-cuts the rows that exist over equal items per query block: no guided lengths)
+        plan_segments(h, plan_problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows, persistent && t_limit == nullptr);
         h->plan_seg_rows = seg_rows;
         h->plan_probs = h->probs_host;
         for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = h->seg_begin[p + 1] - h->seg_begin[p];
+        if (persistent) {
+            long long n_tiles = 0;
+            for (int p = 0; p < n_problems; ++p) n_tiles += std::max(1, (std::max(0, problems[p].q_count) + FT_ROWS_TILE - 1) / FT_ROWS_TILE);
+            h->plan_ctas = (int)std::min<long long>(slots, std::max<long long>((long long)h->segs_host.size(), std::min<long long>(n_tiles, slots)));
+            h->plan_ctas = std::max(h->plan_ctas, 1);
+            plan_tiles(problems, n_problems, h->plan_ctas, h->fin_tiles_host, h->cta_tiles_host);
+        }
     }
     seg_rows = h->plan_seg_rows;
     const size_t n_segs = h->segs_host.size();
+    const size_t n_ctas_p = persistent ? h->cta_tiles_host.size() : 0, n_tiles_p = persistent ? h->fin_tiles_host.size() : 0;
 
     // -- workspace: [row state u64 | column keys u32 | done counters u32], all-ones when idle.  It is
     //    self-cleaning (the finalizing CTA restores every slot it read), so a memset is only queued
     //    after (re)allocation or after a call that failed half-way --------------------------------------
     const size_t state_bytes = (size_t)n_out_rows * 8;
     const size_t col_bytes = (size_t)col_rows * 4;
-    const size_t done_bytes = (size_t)n_problems * 4;
+    const size_t done_bytes = (size_t)n_problems * 4 * 2;   // done counters + finalized-tile counters (persistent form)
     const unsigned state_gen = h->state.generation;
     int rc = ensure(h, h->state, state_bytes + col_bytes + done_bytes);
     if (rc) return rc;
@@ -458,25 +544,23 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     unsigned long long *rowstate = static_cast<unsigned long long *>(h->state.p);
     uint32_t *colkeys = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes);
     uint32_t *done = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes + col_bytes);
+    uint32_t *fin_done = done + n_problems;
+    if (persistent) {
+        const unsigned finc_gen = h->finc.generation;
+        rc = ensure(h, h->finc, n_tiles_p * 4);
+        if (rc) return rc;
+        if (h->finc.generation != finc_gen || h->fin_epoch + (uint32_t)passes >= (1u << 20)) {
+            CU_TRY(h, cudaMemsetAsync(h->finc.p, 0, h->finc.cap, st));
+            h->fin_epoch = 0;
+        }
+    }
     if (passes > 1) {
         rc = ensure(h, h->lower, (size_t)n_out_rows * 4);
         if (rc) return rc;
     }
-    // one very large problem: tile-parallel finalize kernels instead of the single finalizing CTA
-    const bool defer = !binned && n_problems == 1 && problems[0].q_count >= (h->finalize_rows > 0 ? h->finalize_rows : BIG_FINALIZE_ROWS) && problems[0].t_count > 0 && n_dests >= 1;
-    const int fin_tiles = defer ? (problems[0].q_count + bfm::FT_ROWS - 1) / bfm::FT_ROWS : 0;
-    uint8_t *d_keep = nullptr;
-    int32_t *d_tile = nullptr;
-    if (defer) {
-        const size_t o_tile = align256((size_t)problems[0].q_count);
-        rc = ensure(h, h->fin, o_tile + (size_t)fin_tiles * 4);
-        if (rc) return rc;
-        d_keep = static_cast<uint8_t *>(h->fin.p);
-        d_tile = reinterpret_cast<int32_t *>(static_cast<char *>(h->fin.p) + o_tile);
-    }
-
     const size_t prob_bytes = (size_t)n_problems * sizeof(Problem);
-    const size_t table_bytes = prob_bytes + n_segs * sizeof(Segment);
+    const size_t seg_bytes = n_segs * sizeof(Segment), work_bytes = (n_ctas_p * sizeof(int2) + 15) & ~(size_t)15;
+    const size_t table_bytes = prob_bytes + seg_bytes + work_bytes + n_tiles_p * sizeof(bfm::FinTile);
     const unsigned tables_gen = h->tables.generation;
     rc = ensure(h, h->tables, table_bytes);
     if (rc) return rc;
@@ -497,7 +581,12 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             CU_TRY(h, cudaEventSynchronize(h->table_ev[slot]));  // previous upload from this slot is done
         }
         std::memcpy(h->h_tables[slot], h->plan_probs.data(), prob_bytes);
-        std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes, h->segs_host.data(), n_segs * sizeof(Segment));
+        std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes, h->segs_host.data(), seg_bytes);
+        if (persistent) {
+            std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes + seg_bytes, h->cta_tiles_host.data(), n_ctas_p * sizeof(int2));
+            std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes + seg_bytes + work_bytes, h->fin_tiles_host.data(),
+                        n_tiles_p * sizeof(bfm::FinTile));
+        }
         // NOTE: the device table is shared by consecutive calls on one handle; stream order keeps the
         // upload of call n+1 behind the kernel of call n when both use the same stream (the contract).
         CU_TRY(h, cudaMemcpyAsync(h->tables.p, h->h_tables[slot], table_bytes, cudaMemcpyHostToDevice, st));
@@ -509,7 +598,10 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     const Problem *d_probs = static_cast<const Problem *>(h->tables.p);
     const Segment *d_segs = reinterpret_cast<const Segment *>(static_cast<char *>(h->tables.p) + prob_bytes);
 
-    if (!h->state_clean) CU_TRY(h, cudaMemsetAsync(h->state.p, 0xFF, h->state.cap, st));
+    if (!h->state_clean) {
+        CU_TRY(h, cudaMemsetAsync(h->state.p, 0xFF, h->state.cap, st));
+        CU_TRY(h, cudaMemsetAsync(h->d_queue, 0, 256, st));
+    }
     h->state_clean = false;  // set again once the kernel (which restores the state) is queued
 
     ScanParams sp;
@@ -521,6 +613,14 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     sp.rowstate = rowstate;
     sp.colkeys = colkeys;
     sp.done = done;
+    if (persistent) {
+        sp.cta_tiles = reinterpret_cast<const int2 *>(static_cast<char *>(h->tables.p) + prob_bytes + seg_bytes);
+        sp.n_items = (int32_t)n_segs;
+        sp.n_ctas = (int32_t)n_ctas_p;
+        sp.fin_tiles = reinterpret_cast<const bfm::FinTile *>(static_cast<char *>(h->tables.p) + prob_bytes + seg_bytes + work_bytes);
+        sp.fin_done = fin_done;
+        sp.fin_count = static_cast<uint32_t *>(h->finc.p);
+    }
     sp.t_limit = t_limit;
     if (t_limit != nullptr && !binned) {
         const int nqb = (problems[0].q_count + NT * r - 1) / (NT * r);
@@ -617,21 +717,19 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         if (pass > 0)  // the match list (gate on the nearest neighbour) was produced by the first pass
             for (int d = 0; d < n_dests; ++d) sp.dest[d].m_count = nullptr;
         const ScanFn fn = pick_scan(r, mode, mask, pm, pass > 0);
-        sp.defer_finalize = defer ? 1 : 0;
         if (pass > 0) sp.n_feed = 0;   // the inputs are resident after the first pass
         sp.trace = pass == 0 ? h->trace : nullptr;
         sp.trace_cap = h->trace_cap;
         sp.trace_base = 0;
-        fn<<<(unsigned)(n_segs + (pass == 0 ? n_feed : 0)), NT, 0, st>>>(sp);
-        CU_TRY(h, cudaGetLastError());
-        if (defer) {
-            sp.trace_base = (int)n_segs + n_feed;
-            bfm::fin_count_kernel<<<fin_tiles, bfm::FT_NT, 0, st>>>(sp, d_keep, d_tile);
-            CU_TRY(h, cudaGetLastError());
-            sp.trace_base += fin_tiles;
-            bfm::fin_write_kernel<<<fin_tiles, bfm::FT_NT, 0, st>>>(sp, d_keep, d_tile);
-            CU_TRY(h, cudaGetLastError());
+        if (persistent) {
+            sp.fin_epoch = ++h->fin_epoch;
+            sp.queue = h->d_queue + 32 * h->queue_phase;          // (separate 128-byte lines)
+            sp.queue_other = h->d_queue + 32 * (h->queue_phase ^ 1);
+            h->queue_phase ^= 1;
         }
+        const unsigned grid = persistent ? (unsigned)n_ctas_p : (unsigned)(n_segs + (pass == 0 ? n_feed : 0));
+        fn<<<grid, NT, 0, st>>>(sp);
+        CU_TRY(h, cudaGetLastError());
     }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
     h->state_clean = true;  // every slot touched is restored by the CTA that finalizes its problem
@@ -639,9 +737,9 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     h->last_stream = st;
     h->last_pending = true;
 
-    h->launches += binned ? 3 : passes * (defer ? 3 : 1);
-    h->info.kernels_launched = binned ? 3 : passes * (defer ? 3 : 1);
-    h->info.scan_grid = binned ? bin_grid : (int32_t)n_segs;
+    h->launches += binned ? 3 : passes;
+    h->info.kernels_launched = binned ? 3 : passes;
+    h->info.scan_grid = binned ? bin_grid : (persistent ? (int32_t)n_ctas_p : (int32_t)n_segs);
     h->info.scan_block = NT;
     h->info.queries_per_thread = r;
     h->info.popc_mode = pm;
@@ -715,6 +813,7 @@ int bfm_create(int device, bfm_handle_t *out) {
     for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_prog, 256) == cudaSuccess && cudaMemset(h->d_prog, 0, 256) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_queue, 256) == cudaSuccess && cudaMemset(h->d_queue, 0, 256) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_ready, 256) == cudaSuccess && cudaMemset(h->d_ready, 0, 256) == cudaSuccess &&
          cudaMallocHost(&h->h_marks, sizeof(unsigned long long) * 2 * MAX_COPY_CHUNKS) == cudaSuccess &&
          cudaMallocHost(&h->h_status, 64) == cudaSuccess && cudaMallocHost(&h->h_ready, 64) == cudaSuccess;
@@ -736,10 +835,11 @@ int bfm_destroy(bfm_handle_t h) {
     if (!h) return BFM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins, &h->fin})
+    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins, &h->finc})
         if (b->p) cudaFree(b->p);
     if (h->d_ready) cudaFree(h->d_ready);
     if (h->d_prog) cudaFree(h->d_prog);
+    if (h->d_queue) cudaFree(h->d_queue);
     if (h->h_marks) cudaFreeHost(h->h_marks);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_ready) cudaFreeHost(h->h_ready);
@@ -876,15 +976,19 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "window_bins") {
         if (value != 0 && value != 1) return fail(h, BFM_ERR_INVALID, "window_bins must be 0 (auto) or 1 (brute force)");
         h->window_bins = value;
-    } else if (k == "finalize_rows") {
-        if (value < 0) return fail(h, BFM_ERR_INVALID, "finalize_rows must be >= 0");
-        h->finalize_rows = value;
     } else if (k == "taper") {
-        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(h, BFM_ERR_INVALID, "taper must be 0 (auto), 1 (off), 2, 4 or 8");
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16)
+            return fail(h, BFM_ERR_INVALID, "taper must be 0 (auto), 1 (off), 2, 4, 8 or 16 (guided)");
         h->taper = value;
     } else if (k == "taper_pct") {
         if (value < 0 || value > 90) return fail(h, BFM_ERR_INVALID, "taper_pct must be 0 (auto) .. 90");
         h->taper_pct = value;
+    } else if (k == "gss_div" || k == "gss_min") {
+        if (value < 0) return fail(h, BFM_ERR_INVALID, k + " must be >= 0");
+        (k == "gss_div" ? h->gss_div : h->gss_min) = value;
+    } else if (k == "persistent") {
+        if (value != 0 && value != 1) return fail(h, BFM_ERR_INVALID, "persistent must be 0 (auto: resident inputs take the persistent form) or 1 (off)");
+        h->persistent = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");
         h->waves = value;
@@ -911,7 +1015,7 @@ int bfm_plan_preview(const bfm_problem_t *problems, int32_t n_problems, int32_t 
     if (!problems || n_problems <= 0 || !n_items || slots <= 0 || capacity < 0 || (capacity > 0 && !items_out)) return BFM_ERR_INVALID;
     if (queries_per_thread != 1 && queries_per_thread != 2 && queries_per_thread != 4) return BFM_ERR_INVALID;
     if (segment_rows < 0 || waves < 0 || taper_pct < 0 || taper_pct > 90 ||
-        (taper != 0 && taper != 1 && taper != 2 && taper != 4 && taper != 8))
+        (taper != 0 && taper != 1 && taper != 2 && taper != 4 && taper != 8 && taper != 16))
         return BFM_ERR_INVALID;
     for (int p = 0; p < n_problems; ++p)
         if (problems[p].q_count < 0 || problems[p].t_count < 0 || problems[p].q_begin < 0 || problems[p].t_begin < 0 ||
@@ -931,6 +1035,27 @@ int bfm_plan_preview(const bfm_problem_t *problems, int32_t n_problems, int32_t 
     const size_t n = std::min(segs.size(), (size_t)capacity);
     static_assert(sizeof(Segment) == 8 * sizeof(int32_t), "a work item is eight int32");
     if (n) std::memcpy(items_out, segs.data(), n * sizeof(Segment));
+    return BFM_OK;
+}
+
+int bfm_plan_preview_tiles(const bfm_problem_t *problems, int32_t n_problems, int32_t n_ctas, int32_t *tiles_out,
+                           int32_t *tile_cta_out, int32_t tile_capacity, int32_t *n_tiles) {
+    if (!problems || n_problems <= 0 || !n_tiles || n_ctas <= 0 || tile_capacity < 0) return BFM_ERR_INVALID;
+    for (int p = 0; p < n_problems; ++p)
+        if (problems[p].q_count < 0 || problems[p].q_count >= BFM_MAX_QUERY_ROWS) return BFM_ERR_INVALID;
+    std::vector<int2> work;
+    std::vector<bfm::FinTile> tiles;
+    plan_tiles(problems, n_problems, n_ctas, tiles, work);
+    *n_tiles = (int32_t)tiles.size();
+    for (size_t c = 0; c < work.size(); ++c)
+        for (int f = work[c].x; f < work[c].x + work[c].y; ++f) {
+            if (f >= tile_capacity) break;
+            if (tiles_out) {
+                const int32_t row[5] = {tiles[f].problem, tiles[f].row0, tiles[f].index, tiles[f].n_tiles, tiles[f].slot0};
+                std::memcpy(tiles_out + 5 * (size_t)f, row, sizeof(row));
+            }
+            if (tile_cta_out) tile_cta_out[f] = (int32_t)c;
+        }
     return BFM_OK;
 }
 

@@ -50,6 +50,16 @@ struct __align__(16) Segment {
     int32_t problem;   // index into the problem table
 };
 
+// One finalize tile of the persistent form: FT_TILE_ROWS query rows of one problem.
+struct __align__(16) FinTile {
+    int32_t problem;
+    int32_t row0;        // first row of the tile inside its problem
+    int32_t index;       // tile number inside its problem (0 .. n_tiles - 1)
+    int32_t n_tiles;     // tiles of the problem
+    int32_t slot0;       // fin_count slot of the problem's tile 0
+    int32_t pad[3];
+};
+
 struct __align__(16) Problem {   // device view of bfm_problem_t
     int32_t q_begin, q_count, t_begin, t_count, out_begin;
     int32_t col0;      // first column-key slot of this problem (cross-check)
@@ -90,6 +100,19 @@ struct ScanParams {
     int32_t feed_stall;                      // test hook: feeders deliver nothing, so the gate's time-out path runs
     const uint32_t *feed_host_ready;         // pinned host word: rounds staged by the host's worker threads so far
                                              // (pageable caller arrays); NULL = the sources are complete
+    // Persistent form (resident inputs): the grid is at most one wave; CTA c starts with work item c and draws
+    // further items from the ticket counter `queue`; when the queue is empty it finalizes tiles
+    // [cta_tiles[c].x, +.y) of fin_tiles.  A tile waits for its problem's items (all drawn by then, each by a
+    // running CTA) and for the tiles before it, which belong to CTAs with a lower or equal index - dispatched
+    // no later than this one.  queue == NULL: one work item per CTA, the CTA that completes a problem finalizes
+    // it (the gated host path).
+    uint32_t *queue, *queue_other;   // this launch's ticket counter (zero on entry) and the next launch's (zeroed here)
+    int32_t n_items, n_ctas;
+    const int2 *cta_tiles;
+    const struct FinTile *fin_tiles;
+    uint32_t *fin_done;              // [problems] finalized-tile counters, all-ones when idle
+    uint32_t *fin_count;             // [tiles] (epoch << 12 | rows kept by the tile): look-back of the ordered compaction
+    uint32_t fin_epoch;              // this call's epoch (1 .. 2^20 - 1); words of earlier calls never match
     const int32_t *t_limit;          // optional device scalar: train rows that exist (single problem), else NULL
     int32_t limit_segs;              // with t_limit: work items per query block (the rows that exist are re-cut over them)
     const uint8_t *mask;             // dense mask (single problem): [q_local][mask_stride]
@@ -108,7 +131,6 @@ struct ScanParams {
     const uint32_t *lower;           // [out rows] or NULL (first pass)
     uint32_t *lower_out;             // [out rows] or NULL: finalize stores the row's second key of this pass
     int32_t knn_col0, knn_cols;      // this pass fills columns [knn_col0, knn_col0 + knn_cols) of the knn table
-    int32_t defer_finalize;          // 1: the scan kernel only reduces; fin_count / fin_write kernels finalize
     // ---- finalize (run by the CTA that completes a problem's last segment) ----------------------
     int32_t k;             // columns (row stride) of the knn table
     int32_t cross_check;
@@ -284,116 +306,158 @@ __device__ __forceinline__ void put_i32(int32_t *p, int v, bool multicast) {
 // matches in ascending queryIdx order.  Every workspace slot it reads is reset to all-ones, so the
 // workspace is self-cleaning and a steady-state call needs no memset.  Results go to every
 // destination in p.dest (plain stores: device memory, pinned host memory or NVLink peer memory).
-constexpr int FIN_RPT = 8;  // rows per thread and tile
+constexpr int FIN_RPT = 8;   // rows per thread and tile: the CTA that completes a problem walks it in tiles of NT * 8 rows
+constexpr int FT_RPT = 4;    // persistent form: tiles of NT * 4 rows, each finalized by the CTA the plan names
 
-template <int NT>
-__device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi, int (*s_cnt)[NT / 32]) {
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t *p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Rows [base, base + NT * RPT) of problem `pi`: decode, knn table, keep decisions, ordered compaction, row-state reset.
+// `running` = matches kept by the rows before `base`.  LOOKBACK: the rows before `base` belong to other tiles (other
+// CTAs): this tile publishes its own count in fin_count[slot0 + index] and sums the counts of the tiles before it
+// (they are finalized by CTAs dispatched no later than this one, so the wait cannot deadlock).  Returns the tile's count.
+template <int NT, int RPT, bool LOOKBACK>
+__device__ __forceinline__ int finalize_rows(const ScanParams &p, const Problem &pr, const int pi, const int base, int running,
+                                             int (*s_cnt)[NT / 32], const FinTile *ft) {
     constexpr int NW = NT / 32;
-    const Problem pr = p.problems[pi];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const int k = p.k;
-    int running = 0;
-    for (int base = 0; base < pr.q_count; base += NT * FIN_RPT) {
-        int idx1[FIN_RPT], d1[FIN_RPT];
-        bool keep[FIN_RPT];
-        uint32_t bal[FIN_RPT];
-        // phase 1: all row-state loads of the tile in flight together, then the resets
-        unsigned long long st[FIN_RPT];
+    int idx1[RPT], d1[RPT];
+    bool keep[RPT];
+    uint32_t bal[RPT];
+    // phase 1: all row-state loads of the tile in flight together, then the resets
+    unsigned long long st[RPT];
 #pragma unroll
-        for (int j = 0; j < FIN_RPT; ++j) {
-            const int i = base + j * NT + tid;
-            st[j] = i < pr.q_count ? __ldcg(p.rowstate + (size_t)pr.out_begin + i) : ~0ull;
-        }
+    for (int j = 0; j < RPT; ++j) {
+        const int i = base + j * NT + tid;
+        st[j] = i < pr.q_count ? __ldcg(p.rowstate + (size_t)pr.out_begin + i) : ~0ull;
+    }
 #pragma unroll
-        for (int j = 0; j < FIN_RPT; ++j) {
-            const int i = base + j * NT + tid;
-            if (i < pr.q_count) p.rowstate[(size_t)pr.out_begin + i] = ~0ull;
-        }
-        // phase 2: all column-key loads (cross-check) in flight together
-        uint32_t ck[FIN_RPT];
+    for (int j = 0; j < RPT; ++j) {
+        const int i = base + j * NT + tid;
+        if (i < pr.q_count) p.rowstate[(size_t)pr.out_begin + i] = ~0ull;
+    }
+    // phase 2: all column-key loads (cross-check) in flight together
+    uint32_t ck[RPT];
 #pragma unroll
-        for (int j = 0; j < FIN_RPT; ++j) {
-            const uint32_t k1 = (uint32_t)(st[j] >> 32);
-            ck[j] = KEY_NONE;
-            if (p.cross_check && k1 < KEY_DEAD) ck[j] = __ldcg(p.colkeys + (size_t)pr.col0 + (k1 & IDX_MASK));
-        }
-        // phase 3: decode, knn table, keep decisions
+    for (int j = 0; j < RPT; ++j) {
+        const uint32_t k1 = (uint32_t)(st[j] >> 32);
+        ck[j] = KEY_NONE;
+        if (p.cross_check && k1 < KEY_DEAD) ck[j] = __ldcg(p.colkeys + (size_t)pr.col0 + (k1 & IDX_MASK));
+    }
+    // phase 3: decode, knn table, keep decisions
 #pragma unroll
-        for (int j = 0; j < FIN_RPT; ++j) {
-            const int i = base + j * NT + tid;
-            const bool in = i < pr.q_count;
-            const uint32_t k1 = (uint32_t)(st[j] >> 32), k2 = (uint32_t)st[j];
-            const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
-            idx1[j] = has1 ? (int)(k1 & IDX_MASK) : -1;
-            d1[j] = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
-            const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
-            if (in) {
-                const size_t o = ((size_t)pr.out_begin + i) * (size_t)k + (size_t)p.knn_col0;
-                for (int d = 0; d < p.n_dest; ++d) {
-                    int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
-                    if (!ki) continue;
-                    const bool mc = (p.dest_multicast >> d) & 1u;
-                    if (k == 2 && !mc) {   // 8-byte aligned: o is even
-                        *reinterpret_cast<int2 *>(ki + o) = make_int2(idx1[j], idx2);
-                        *reinterpret_cast<int2 *>(kd + o) = make_int2(d1[j], d2);
-                    } else {
-                        put_i32(ki + o, idx1[j], mc);
-                        put_i32(kd + o, d1[j], mc);
-                        if (p.knn_cols > 1) { put_i32(ki + o + 1, idx2, mc); put_i32(kd + o + 1, d2, mc); }
-                    }
+    for (int j = 0; j < RPT; ++j) {
+        const int i = base + j * NT + tid;
+        const bool in = i < pr.q_count;
+        const uint32_t k1 = (uint32_t)(st[j] >> 32), k2 = (uint32_t)st[j];
+        const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
+        idx1[j] = has1 ? (int)(k1 & IDX_MASK) : -1;
+        d1[j] = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
+        const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
+        if (in) {
+            const size_t o = ((size_t)pr.out_begin + i) * (size_t)k + (size_t)p.knn_col0;
+            for (int d = 0; d < p.n_dest; ++d) {
+                int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
+                if (!ki) continue;
+                const bool mc = (p.dest_multicast >> d) & 1u;
+                if (k == 2 && !mc) {   // 8-byte aligned: o is even
+                    *reinterpret_cast<int2 *>(ki + o) = make_int2(idx1[j], idx2);
+                    *reinterpret_cast<int2 *>(kd + o) = make_int2(d1[j], d2);
+                } else {
+                    put_i32(ki + o, idx1[j], mc);
+                    put_i32(kd + o, d1[j], mc);
+                    if (p.knn_cols > 1) { put_i32(ki + o + 1, idx2, mc); put_i32(kd + o + 1, d2, mc); }
                 }
-                if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
             }
-            bool kp = in && has1;
-            if (kp && p.cross_check) kp = ck[j] == (((uint32_t)d1[j] << DIST_SHIFT) | (uint32_t)i);
-            if (kp && p.use_ratio) kp = has2 && ((double)d1[j] < p.ratio * (double)d2);
-            if (kp && p.max_distance >= 0) kp = d1[j] <= p.max_distance;
-            keep[j] = kp;
-            bal[j] = __ballot_sync(0xffffffffu, kp);
-            if (lane == 0) s_cnt[j][warp] = __popc(bal[j]);
+            if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
         }
-        __syncthreads();
-        // ordered compaction: rows ascend with (j, warp, lane)
-        int before = running, tile_total = 0;
+        bool kp = in && has1;
+        if (kp && p.cross_check) kp = ck[j] == (((uint32_t)d1[j] << DIST_SHIFT) | (uint32_t)i);
+        if (kp && p.use_ratio) kp = has2 && ((double)d1[j] < p.ratio * (double)d2);
+        if (kp && p.max_distance >= 0) kp = d1[j] <= p.max_distance;
+        keep[j] = kp;
+        bal[j] = __ballot_sync(0xffffffffu, kp);
+        if (lane == 0) s_cnt[j][warp] = __popc(bal[j]);
+    }
+    __syncthreads();
+    // ordered compaction: rows ascend with (j, warp, lane)
+    int before = 0, tile_total = 0;
 #pragma unroll
-        for (int j = 0; j < FIN_RPT; ++j) {
+    for (int j = 0; j < RPT; ++j) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int c = s_cnt[j][w];
+            tile_total += c;
+            if (j == 0 && w < warp) before += c;
+        }
+    }
+    if (LOOKBACK) {
+        // publish this tile's count, then add up the tiles before it (every thread sums them all: index <= a few dozen
+        // for any real frame; the words sit in L2)
+        if (tid == 0) *(volatile uint32_t *)(p.fin_count + ft->slot0 + ft->index) = (p.fin_epoch << 12) | (uint32_t)tile_total;
+        const uint32_t tag = p.fin_epoch << 12;
+        for (int t = lane; t < ft->index; t += 32) {
+            uint32_t v;
+            unsigned long long t0 = 0;
+            while (((v = *(volatile const uint32_t *)(p.fin_count + ft->slot0 + t)) & 0xFFFFF000u) != tag) {
+                __nanosleep(64);
+                if (t0 == 0) t0 = global_timer_ns();
+                else if (global_timer_ns() - t0 > 2000000000ull) { v = 0; break; }   // never hang the GPU
+            }
+            running += (int)(v & 0xFFFu);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) running += __shfl_xor_sync(0xffffffffu, running, o);
+    }
+    int pos_j = running + before;   // rank of this warp's first kept row of slot j = 0
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+        if (j > 0) {
+            // rows of slot j come after every row of slot j-1: add the rest of slot j-1 and the
+            // warps before this one in slot j
+            int add = 0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-                const int c = s_cnt[j][w];
-                tile_total += c;
-                if (j == 0 && w < warp) before += c;
+                if (w >= warp) add += s_cnt[j - 1][w];
+                if (w < warp) add += s_cnt[j][w];
+            }
+            pos_j += add;
+        }
+        if (keep[j]) {
+            const size_t o = (size_t)pr.out_begin + pos_j + __popc(bal[j] & lt);
+            const int i = base + j * NT + tid;
+            for (int d = 0; d < p.n_dest; ++d) {
+                if (!p.dest[d].m_count) continue;
+                const bool mc = (p.dest_multicast >> d) & 1u;
+                put_i32(p.dest[d].m_query + o, i, mc);
+                put_i32(p.dest[d].m_train + o, idx1[j], mc);
+                put_i32(p.dest[d].m_dist + o, d1[j], mc);
             }
         }
-        int pos_j = before;   // rank of this warp's first kept row of slot j = 0
-#pragma unroll
-        for (int j = 0; j < FIN_RPT; ++j) {
-            if (j > 0) {
-                // rows of slot j come after every row of slot j-1: add the rest of slot j-1 and the
-                // warps before this one in slot j
-                int add = 0;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    if (w >= warp) add += s_cnt[j - 1][w];
-                    if (w < warp) add += s_cnt[j][w];
-                }
-                pos_j += add;
-            }
-            if (keep[j]) {
-                const size_t o = (size_t)pr.out_begin + pos_j + __popc(bal[j] & lt);
-                const int i = base + j * NT + tid;
-                for (int d = 0; d < p.n_dest; ++d) {
-                    if (!p.dest[d].m_count) continue;
-                    const bool mc = (p.dest_multicast >> d) & 1u;
-                    put_i32(p.dest[d].m_query + o, i, mc);
-                    put_i32(p.dest[d].m_train + o, idx1[j], mc);
-                    put_i32(p.dest[d].m_dist + o, d1[j], mc);
-                }
-            }
-        }
-        running += tile_total;
-        __syncthreads();   // s_cnt is rewritten by the next tile
     }
+    if (LOOKBACK && ft->index == ft->n_tiles - 1 && tid == 0)
+        for (int d = 0; d < p.n_dest; ++d)
+            if (p.dest[d].m_count) put_i32(p.dest[d].m_count + pi, running + tile_total, (p.dest_multicast >> d) & 1u);
+    (void)pi;
+    __syncthreads();   // s_cnt is rewritten by the next tile
+    return tile_total;
+}
+
+template <int NT>
+__device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi, int (*s_cnt)[NT / 32]) {
+    const Problem pr = p.problems[pi];
+    const int tid = threadIdx.x;
+    int running = 0;
+    for (int base = 0; base < pr.q_count; base += NT * FIN_RPT)
+        running += finalize_rows<NT, FIN_RPT, false>(p, pr, pi, base, running, s_cnt, nullptr);
     if (tid == 0)
         for (int d = 0; d < p.n_dest; ++d)
             if (p.dest[d].m_count) put_i32(p.dest[d].m_count + pi, running, (p.dest_multicast >> d) & 1u);
@@ -401,6 +465,53 @@ __device__ __noinline__ void finalize_problem(const ScanParams &p, const int pi,
         // every column-key read of this problem happened above, in this CTA
         for (int j = tid; j < pr.t_count; j += NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
     }
+}
+
+// Persistent form: one tile of a problem.  Waits until every work item of the problem has been committed (the done
+// counter idles at all-ones, so n arrivals read n - 1), finalizes the tile's rows, and the tile that finishes last
+// restores the problem's column keys and counters - the workspace stays self-cleaning.
+template <int NT>
+__device__ __noinline__ void finalize_tile(const ScanParams &p, const FinTile *ftp, int (*s_cnt)[NT / 32], int *s_flag) {
+    const int tid = threadIdx.x;
+    const int pi = ftp->problem;
+    const Problem pr = p.problems[pi];
+    if (tid == 0) {
+        const uint32_t want = (uint32_t)pr.n_segs - 1u;
+        unsigned long long t0 = 0;
+        while (ld_acquire_gpu(p.done + pi) != want) {
+            __nanosleep(100);
+            if (t0 == 0) t0 = global_timer_ns();
+            else if (global_timer_ns() - t0 > 2000000000ull) break;   // never hang the GPU
+        }
+    }
+    __syncthreads();
+    finalize_rows<NT, FT_RPT, true>(p, pr, pi, ftp->row0, 0, s_cnt, ftp);
+    // the tile that finishes last restores what all tiles of the problem have read
+    if (tid == 0) {
+        // (this tile's reads of the column keys have returned - the keep decisions above consumed them - so the
+        // tile that resets them after seeing this count cannot overtake them: no fence)
+        const uint32_t old = atomicAdd(p.fin_done + pi, 1u);   // idles at all-ones
+        *s_flag = (old == (uint32_t)ftp->n_tiles - 2u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (*s_flag) {
+        if (tid == 0) {
+            p.done[pi] = 0xFFFFFFFFu;
+            p.fin_done[pi] = 0xFFFFFFFFu;
+        }
+        if (p.cross_check) {
+            uint32_t *ck = p.colkeys + (size_t)pr.col0;
+            int j = tid;
+            // 16-byte stores over the aligned middle
+            const int head = (int)(((16u - ((uint32_t)(uintptr_t)ck & 15u)) & 15u) >> 2);
+            for (; j < min(head, pr.t_count); j += NT) ck[j] = KEY_NONE;
+            const int n4 = (pr.t_count - min(head, pr.t_count)) >> 2;
+            uint4 *ck4 = reinterpret_cast<uint4 *>(ck + min(head, pr.t_count));
+            for (int q4 = tid; q4 < n4; q4 += NT) ck4[q4] = make_uint4(KEY_NONE, KEY_NONE, KEY_NONE, KEY_NONE);
+            for (int r = min(head, pr.t_count) + 4 * n4 + tid; r < pr.t_count; r += NT) ck[r] = KEY_NONE;
+        }
+    }
+    __syncthreads();   // s_flag is rewritten by the next tile
 }
 
 // ---- SM-fed upload ---------------------------------------------------------------------------------------
@@ -506,18 +617,89 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     __shared__ uint32_t s_col[CROSS ? 2 : 1][CROSS ? NW : 1][CROSS ? TT : 1];
     __shared__ int s_cnt[FIN_RPT][NW];
     __shared__ int s_flag;
+    // CTA-uniform state of the persistent form, kept out of the registers the inner loop needs:
+    // [0] current item, [1] problem / [2] first query row / [3] first output row / [5] valid rows of the query block held
+    // in registers, [4] items scanned for it since the last commit, [6] train chunks streamed so far
+    __shared__ int s_run[8];
 
     if ((int)blockIdx.x < p.n_feed) {   // the first CTAs of the grid feed the others (SM-fed upload)
         if (!p.feed_stall) feed_rows<NT>(p);
         return;
     }
     trace_mark(p, 0);   // CTA entry
-    const Segment sg = p.segs[blockIdx.x - p.n_feed];
+    if (p.trace != nullptr && threadIdx.x == 0 && (int)blockIdx.x + p.trace_base < p.trace_cap) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[(size_t)(p.trace_base + (int)blockIdx.x) * 8 + 7] = smid;
+    }
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    const int cta = (int)blockIdx.x - p.n_feed;
+    // Work items.  Static form (the gated host path): CTA b takes item b and the CTA that completes a problem finalizes
+    // it.  Persistent form (resident inputs, p.queue != NULL): the grid is at most one wave; a CTA starts with item
+    // `cta` and draws its next items from a device-wide ticket counter, so CTAs the warp schedulers favour simply take
+    // more of them and all SMs run dry together; consecutive items of one query block keep the queries and the running
+    // keys in registers (one commit per run); the problems are finalized tile by tile once the queue is empty.
+    const bool dyn = p.queue != nullptr;
+    uint32_t nxt = 0;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        s_run[0] = cta;
+        s_run[1] = -1;
+        s_run[2] = -1;
+        s_run[3] = 0;
+        s_run[4] = 0;
+        s_run[5] = 0;
+        s_run[6] = 0;
+        if (dyn) {
+            if (cta == 0) *p.queue_other = 0u;   // the counter of the NEXT launch (idle: the previous launch has drained)
+            nxt = (uint32_t)p.n_ctas + atomicAdd(p.queue, 1u);   // in flight while the first item is scanned
+        }
+    }
+    __syncthreads();
+
+    // the query block held in registers and its running keys
+    uint32_t qw[R][8];
+    uint32_t ibias[R];          // CROSS: low bits of the column key (query index), dead bit if row absent
+    bool valid[MASK == 1 ? R : 1];
+    float qx[R], qy[R];
+    const uint8_t *mrow[R];
+    uint32_t b1[R], b2[R], lb[R];
     int col0 = 0;
-    if (CROSS) col0 = p.problems[sg.problem].col0;
+
+    // commit: associative min-merge of the running keys into the global row state
+    // row state = (best << 32) | second, updated through its two 32-bit halves (little endian):
+    // one atomicMin on `best` returns the displaced key; whatever lost there, or this run's
+    // own runner-up, competes for `second` with a fire-and-forget atomic.  Every key except the
+    // final best is offered to `second` exactly when it stops being (or fails to become) the
+    // best, so `second` ends as the true runner-up for any arrival order.
+    auto commit = [&](const int out0, const int q_valid) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r * NT + tid >= q_valid || b1[r] >= KEY_DEAD) continue;
+            uint32_t *half = reinterpret_cast<uint32_t *>(p.rowstate + (size_t)(out0 + r * NT + tid));
+            if (K == 1) {
+                atomicMin(half + 1, b1[r]);
+            } else {
+                const uint32_t n2 = b2[r] >= KEY_DEAD ? KEY_NONE : b2[r];
+                const uint32_t displaced = atomicMin(half + 1, b1[r]);
+                const uint32_t cand = min(max(displaced, b1[r]), n2);
+                if (cand != KEY_NONE) atomicMin(half, cand);
+            }
+        }
+    };
+
+    for (;;) {
+    // (every value of s_run read here was written before the last barrier)
+    const int item = s_run[0];
+    if (dyn ? item >= p.n_items : item != cta) break;
+    const bool first_item = item == cta;
+    const uint32_t g0 = (uint32_t)s_run[6];   // chunk g lives in buffer g & 1, barrier phase (g >> 1) & 1
+    const int acc_problem = s_run[1], acc_q0 = s_run[2], acc_out0 = s_run[3], acc_items = s_run[4], acc_qvalid = s_run[5];
+    const Segment sg = p.segs[item];
 
     // -- input gate, SM-fed variant: wait until every feeder has finished the round that covers our rows
     if (p.n_feed > 0) {
@@ -585,11 +767,11 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     // train rows of this segment; with a device-side limit (a train set whose size was decided by an
     // earlier kernel on the same stream, e.g. the visible local-map points) the range is clamped here
     // (single problem).  The rows that exist are then re-cut evenly over this query block's `limit_segs` work
-    // items, so every CTA gets the same share whatever the host guessed when it planned.
+    // items, so every item gets the same share whatever the host guessed when it planned.
     int t_count = sg.t_count, t_row0 = sg.t_row0, t_local0 = sg.t_local0;
     if (p.t_limit != nullptr) {
         const int rows = max(0, __ldg(p.t_limit));
-        const int s_idx = ((int)blockIdx.x - p.n_feed) % p.limit_segs;
+        const int s_idx = item % p.limit_segs;
         const int per = (rows + p.limit_segs - 1) / p.limit_segs;
         t_row0 = sg.t_row0 - sg.t_local0 + s_idx * per;
         t_local0 = s_idx * per;
@@ -597,80 +779,90 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     }
 
     // -- start the train stream first: the TMA of chunks 0 and 1 flies while the queries are loaded ----
+    // (a persistent CTA arrives here after the closing barrier of its previous item: both buffers are free)
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
         const int n0 = min(TT, t_count), n1 = min(TT, t_count - TT);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes of the previous item (transform) before async writes
         if (n0 > 0) {
-            mbar_expect_tx(&s_bar[0], (uint32_t)n0 * 32u);
-            bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)t_row0, (uint32_t)n0 * 32u, &s_bar[0]);
+            mbar_expect_tx(&s_bar[g0 & 1], (uint32_t)n0 * 32u);
+            bulk_g2s(&s_t[g0 & 1][0], p.t + 2 * (size_t)t_row0, (uint32_t)n0 * 32u, &s_bar[g0 & 1]);
         }
         if (n1 > 0) {
-            mbar_expect_tx(&s_bar[1], (uint32_t)n1 * 32u);
-            bulk_g2s(&s_t[1][0], p.t + 2 * (size_t)(t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[1]);
+            mbar_expect_tx(&s_bar[(g0 + 1) & 1], (uint32_t)n1 * 32u);
+            bulk_g2s(&s_t[(g0 + 1) & 1][0], p.t + 2 * (size_t)(t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[(g0 + 1) & 1]);
         }
     }
 
-    // -- this thread's R query descriptors (two coalesced 16-byte loads each) ---------------------
-    uint32_t qw[R][8];
-    uint32_t ibias[R];          // CROSS: low bits of the column key (query index), dead bit if row absent
-    bool valid[R];
-    float qx[R], qy[R];
-    const uint8_t *mrow[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int lr = r * NT + tid;
-        valid[r] = lr < sg.q_valid;
-        const int row = sg.q_row0 + (valid[r] ? lr : 0);
-        // .cg (L2) loads: on the SM-fed host path these arrays are written by feeder CTAs of this very launch, and
-        // ld.global.nc is only defined for memory that is read-only for the kernel's lifetime
-        const uint4 a = __ldcg(p.q + 2 * (size_t)row);
-        const uint4 b = __ldcg(p.q + 2 * (size_t)row + 1);
-        qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
-        qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
-        if (XF) transform_desc(qw[r]);
-        ibias[r] = (uint32_t)(sg.q_local0 + lr);
-        if (MASK == 0 && !valid[r]) ibias[r] = KEY_DEAD;
-        if (MASK == 2) {
-            const float2 xy = __ldcg(p.q_xy + row);
-            // an absent row gets NaN coordinates: every window compare is false
-            qx[r] = valid[r] ? xy.x : __int_as_float(0x7fc00000);
-            qy[r] = xy.y;
+    // -- a new query block: commit the run that ends here, then this thread's R query descriptors (two coalesced
+    //    16-byte loads each) --------------------------------------------------------------------------
+    const bool new_block = sg.problem != acc_problem || sg.q_local0 != acc_q0;
+    if (new_block && acc_items > 0) commit(acc_out0, acc_qvalid);
+    __syncthreads();   // s_run has been read by every thread; release: the atomics above are visible to whoever acquires the counter
+    if (tid == 0) {
+        if (new_block) {
+            if (acc_items > 0) red_release_gpu_add(p.done + acc_problem, (uint32_t)acc_items);
+            s_run[1] = sg.problem;
+            s_run[2] = sg.q_local0;
+            s_run[3] = sg.out_row0;
+            s_run[5] = sg.q_valid;
         }
-        if (MASK == 1) mrow[r] = p.mask + (size_t)(sg.q_local0 + (valid[r] ? lr : 0)) * (size_t)p.mask_stride;
+        s_run[4] = new_block ? 1 : acc_items + 1;
     }
-
-    uint32_t b1[R], b2[R];
+    if (new_block) {
+        if (CROSS) col0 = p.problems[sg.problem].col0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { b1[r] = KEY_NONE; b2[r] = KEY_NONE; }
-    uint32_t lb[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) lb[r] = (BOUND && valid[r]) ? __ldg(p.lower + sg.out_row0 + r * NT + tid) : 0u;
+        for (int r = 0; r < R; ++r) {
+            const int lr = r * NT + tid;
+            const bool have = lr < sg.q_valid;
+            if (MASK == 1) valid[r] = have;
+            const int row = sg.q_row0 + (have ? lr : 0);
+            // .cg (L2) loads: on the SM-fed host path these arrays are written by feeder CTAs of this very launch, and
+            // ld.global.nc is only defined for memory that is read-only for the kernel's lifetime
+            const uint4 a = __ldcg(p.q + 2 * (size_t)row);
+            const uint4 b = __ldcg(p.q + 2 * (size_t)row + 1);
+            qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
+            qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
+            if (XF) transform_desc(qw[r]);
+            ibias[r] = (uint32_t)(sg.q_local0 + lr);
+            if (MASK == 0 && !have) ibias[r] = KEY_DEAD;
+            if (MASK == 2) {
+                const float2 xy = __ldcg(p.q_xy + row);
+                // an absent row gets NaN coordinates: every window compare is false
+                qx[r] = have ? xy.x : __int_as_float(0x7fc00000);
+                qy[r] = xy.y;
+            }
+            if (MASK == 1) mrow[r] = p.mask + (size_t)(sg.q_local0 + (have ? lr : 0)) * (size_t)p.mask_stride;
+            b1[r] = KEY_NONE;
+            b2[r] = KEY_NONE;
+            lb[r] = (BOUND && have) ? __ldg(p.lower + sg.out_row0 + r * NT + tid) : 0u;
+        }
+    }
 
     const int nchunks = (t_count + TT - 1) / TT;
     auto chunk_rows = [&](int c) { return min(TT, t_count - c * TT); };
-    auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer c&1
+    auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer (g0 + c) & 1
         const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
+        const uint32_t gb = (g0 + (uint32_t)c) & 1u;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes
-        mbar_expect_tx(&s_bar[c & 1], bytes);
-        bulk_g2s(&s_t[c & 1][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[c & 1]);
+        mbar_expect_tx(&s_bar[gb], bytes);
+        bulk_g2s(&s_t[gb][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[gb]);
     };
     auto stage_xy = [&](int c) {
-        if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldcg(p.t_xy + t_row0 + c * TT + tid);
+        if (MASK == 2 && tid < chunk_rows(c)) s_xy[(g0 + (uint32_t)c) & 1u][tid] = __ldcg(p.t_xy + t_row0 + c * TT + tid);
     };
     auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
-        mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
+        const uint32_t g = g0 + (uint32_t)c, gb = g & 1u;
+        mbar_wait(&s_bar[gb], (g >> 1) & 1u);
         if (XF && tid < chunk_rows(c)) {
-            const uint4 a = s_t[c & 1][2 * tid], b = s_t[c & 1][2 * tid + 1];
+            const uint4 a = s_t[gb][2 * tid], b = s_t[gb][2 * tid + 1];
             uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             transform_desc(w);
-            s_t[c & 1][2 * tid] = make_uint4(w[0], w[1], w[2], w[3]);
-            s_t[c & 1][2 * tid + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+            s_t[gb][2 * tid] = make_uint4(w[0], w[1], w[2], w[3]);
+            s_t[gb][2 * tid + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
     };
 
-    trace_mark(p, 1);   // gates passed, TMA issued, queries loaded
+    if (first_item) trace_mark(p, 1);   // gates passed, TMA issued, queries loaded
     __syncthreads();   // barrier init (thread 0, above) visible to every waiter
     if (nchunks > 0) {
         stage_xy(0);
@@ -678,10 +870,10 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         land(0);
     }
     __syncthreads();
-    trace_mark(p, 2);   // first chunk landed
+    if (first_item) trace_mark(p, 2);   // first chunk landed
 
     for (int c = 0; c < nchunks; ++c) {
-        const int b = c & 1;
+        const int b = (int)((g0 + (uint32_t)c) & 1u);
         const int n = chunk_rows(c);
         const uint32_t jbase = (uint32_t)(t_local0 + c * TT);
         if constexpr (R >= 2) {
@@ -780,7 +972,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
             stage_xy(c + 2);
         }
         if (CROSS) {
-            // s_col[b] is next written in iteration c+2, i.e. after the barrier of iteration c+1
+            // s_col[b] is next written two chunks later, i.e. after the next barrier
             for (int j = tid; j < n; j += NT) {
                 uint32_t m = s_col[b][0][j];
 #pragma unroll
@@ -789,32 +981,23 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
             }
         }
     }
+    if (first_item) trace_mark(p, 3);   // scan of the first item done
 
-    trace_mark(p, 3);   // scan done
-    // -- commit: associative min-merge into the global row state ---------------------------------
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        if (!valid[r] || b1[r] >= KEY_DEAD) continue;
-        // row state = (best << 32) | second, updated through its two 32-bit halves (little endian):
-        // one atomicMin on `best` returns the displaced key; whatever lost there, or this segment's
-        // own runner-up, competes for `second` with a fire-and-forget atomic.  Every key except the
-        // final best is offered to `second` exactly when it stops being (or fails to become) the
-        // best, so `second` ends as the true runner-up for any arrival order.
-        uint32_t *half = reinterpret_cast<uint32_t *>(p.rowstate + (size_t)(sg.out_row0 + r * NT + tid));
-        if (K == 1) {
-            atomicMin(half + 1, b1[r]);
-        } else {
-            const uint32_t n2 = b2[r] >= KEY_DEAD ? KEY_NONE : b2[r];
-            const uint32_t displaced = atomicMin(half + 1, b1[r]);
-            const uint32_t cand = min(max(displaced, b1[r]), n2);
-            if (cand != KEY_NONE) atomicMin(half, cand);
+    if (dyn) {
+        // the next ticket (drawn while this item was scanned); draw the one after it right away
+        if (tid == 0) {
+            s_run[6] = (int)(g0 + (uint32_t)nchunks);
+            s_run[0] = (int)min(nxt, 0x7FFFFFFFu);
+            if (nxt < (uint32_t)p.n_items) nxt = (uint32_t)p.n_ctas + atomicAdd(p.queue, 1u);
         }
+        __syncthreads();
+        continue;
     }
 
-    // -- problem completion: the CTA whose segment is the last of its problem finalizes it -------------
+    // -- static form: commit, then the CTA whose item is the last of its problem finalizes it -------------
     // (threadfence + counter: every CTA's state updates are visible before its count is)
+    commit(sg.out_row0, sg.q_valid);
     trace_mark(p, 4);   // commit atomics issued
-    if (p.defer_finalize) return;   // one very large problem: finalized by the tile-parallel kernels below
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -831,130 +1014,24 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         __syncthreads();
         trace_mark(p, 6);   // finalized (only the CTA that completed its problem)
     }
-}
+    break;
+    }   // work items of this CTA
 
-// ---- tile-parallel finalize for ONE problem on its own (Q >= 1792 rows: a tracking frame, the sweep) ------
-// The in-kernel finalize is one CTA per problem, which is right for a batch of keyframe pairs (one
-// finalizing CTA per pair, all in parallel) and serial when the call is a single problem: ~2.5 us per
-// 1024 rows (tools/finalize_probe.py), against ~3.5 us for two more launches.  Here tiles of FT_ROWS rows
-// run in parallel: fin_count decodes, writes the knn table, decides keep and counts per tile; fin_write
-// places the kept rows after the kept
-// rows of all earlier tiles (ascending queryIdx is preserved) and restores the workspace.
-constexpr int FT_NT = 256, FT_RPT = 4, FT_ROWS = FT_NT * FT_RPT;
-
-#ifndef BFM_SCAN_INST_ONLY   // non-template kernels: defined once, in bfm_api.cu
-
-__global__ void __launch_bounds__(FT_NT) fin_count_kernel(const __grid_constant__ ScanParams p, uint8_t *keep_flag, int32_t *tile_count) {
-    trace_mark(p, 0);
-    const Problem pr = p.problems[0];
-    const int k = p.k;
-    int kept = 0;
-#pragma unroll
-    for (int j = 0; j < FT_RPT; ++j) {
-        const int i = blockIdx.x * FT_ROWS + j * FT_NT + threadIdx.x;
-        if (i >= pr.q_count) continue;
-        const unsigned long long st = __ldcg(p.rowstate + (size_t)pr.out_begin + i);
-        const uint32_t k1 = (uint32_t)(st >> 32), k2 = (uint32_t)st;
-        const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
-        const int idx1 = has1 ? (int)(k1 & IDX_MASK) : -1, d1 = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
-        const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
-        const size_t o = ((size_t)pr.out_begin + i) * (size_t)k + (size_t)p.knn_col0;
-        for (int d = 0; d < p.n_dest; ++d) {
-            int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
-            if (!ki) continue;
-            const bool mc = (p.dest_multicast >> d) & 1u;
-            if (k == 2 && !mc) {   // 8-byte aligned: o is even
-                *reinterpret_cast<int2 *>(ki + o) = make_int2(idx1, idx2);
-                *reinterpret_cast<int2 *>(kd + o) = make_int2(d1, d2);
-            } else {
-                put_i32(ki + o, idx1, mc);
-                put_i32(kd + o, d1, mc);
-                if (p.knn_cols > 1) { put_i32(ki + o + 1, idx2, mc); put_i32(kd + o + 1, d2, mc); }
-            }
+    // -- persistent form: commit the last run, then the finalize tiles the plan gave this CTA ------------------
+    if (dyn) {
+        if (s_run[4] > 0) {
+            commit(s_run[3], s_run[5]);
+            __syncthreads();
+            if (tid == 0) red_release_gpu_add(p.done + s_run[1], (uint32_t)s_run[4]);
         }
-        if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
-        bool kp = has1;
-        if (kp && p.cross_check) kp = __ldcg(p.colkeys + (size_t)pr.col0 + idx1) == (((uint32_t)d1 << DIST_SHIFT) | (uint32_t)i);
-        if (kp && p.use_ratio) kp = has2 && ((double)d1 < p.ratio * (double)d2);
-        if (kp && p.max_distance >= 0) kp = d1 <= p.max_distance;
-        keep_flag[i] = kp ? 1 : 0;
-        kept += kp ? 1 : 0;
-    }
-    const int total = kept;
-    __shared__ int s_sum[FT_NT / 32];
-    int w = total;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = w;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int i = 0; i < FT_NT / 32; ++i) t += s_sum[i];
-        tile_count[blockIdx.x] = t;
-    }
-    trace_mark(p, 6);
-}
-
-__global__ void __launch_bounds__(FT_NT) fin_write_kernel(const __grid_constant__ ScanParams p, const uint8_t *keep_flag,
-                                                          const int32_t *tile_count) {
-    __shared__ int s_red[FT_NT / 32];
-    __shared__ int s_cnt[FT_RPT][FT_NT / 32];
-    trace_mark(p, 0);
-    const Problem pr = p.problems[0];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int part = 0;
-    for (int b = tid; b < (int)blockIdx.x; b += FT_NT) part += tile_count[b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) s_red[warp] = part;
-    bool keep[FT_RPT];
-    uint32_t bal[FT_RPT];
-    unsigned long long st[FT_RPT];
-#pragma unroll
-    for (int j = 0; j < FT_RPT; ++j) {
-        const int i = blockIdx.x * FT_ROWS + j * FT_NT + tid;
-        const bool in = i < pr.q_count;
-        keep[j] = in && keep_flag[i] != 0;
-        st[j] = in ? __ldcg(p.rowstate + (size_t)pr.out_begin + i) : ~0ull;
-        if (in) p.rowstate[(size_t)pr.out_begin + i] = ~0ull;
-        bal[j] = __ballot_sync(0xffffffffu, keep[j]);
-        if (lane == 0) s_cnt[j][warp] = __popc(bal[j]);
-    }
-    __syncthreads();
-    int before = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < FT_NT / 32; ++w) before += s_red[w];
-    const bool want_list = p.dest[0].m_count != nullptr;
-#pragma unroll
-    for (int j = 0; j < FT_RPT; ++j) {
-        int pos = before + tile_total;
-#pragma unroll
-        for (int w = 0; w < FT_NT / 32; ++w) {
-            if (w < warp) pos += s_cnt[j][w];
-            tile_total += s_cnt[j][w];
-        }
-        if (keep[j] && want_list) {
-            const size_t o = (size_t)pr.out_begin + pos + __popc(bal[j] & ((1u << lane) - 1u));
-            const uint32_t k1 = (uint32_t)(st[j] >> 32);
-            const int i = blockIdx.x * FT_ROWS + j * FT_NT + tid;
-            for (int d = 0; d < p.n_dest; ++d) {
-                if (!p.dest[d].m_count) continue;
-                const bool mc = (p.dest_multicast >> d) & 1u;
-                put_i32(p.dest[d].m_query + o, i, mc);
-                put_i32(p.dest[d].m_train + o, (int)(k1 & IDX_MASK), mc);
-                put_i32(p.dest[d].m_dist + o, (int)(k1 >> DIST_SHIFT), mc);
-            }
+        trace_mark(p, 5);   // all work items of this CTA committed
+        const int2 w = __ldg(p.cta_tiles + cta);
+        if (w.y > 0) {
+            for (int f = w.x; f < w.x + w.y; ++f) finalize_tile<NT>(p, p.fin_tiles + f, s_cnt, &s_flag);
+            trace_mark(p, 6);   // its finalize tiles done
         }
     }
-    if (blockIdx.x == gridDim.x - 1 && tid == 0)
-        for (int d = 0; d < p.n_dest; ++d)
-            if (p.dest[d].m_count) put_i32(p.dest[d].m_count, before + tile_total, (p.dest_multicast >> d) & 1u);
-    if (p.cross_check)   // every column-key read happened in fin_count; all tiles share the reset
-        for (int j = blockIdx.x * FT_NT + tid; j < pr.t_count; j += gridDim.x * FT_NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
-    trace_mark(p, 6);
 }
-
-#endif  // BFM_SCAN_INST_ONLY
 
 typedef void (*ScanFn)(const ScanParams);
 // defined in bfm_scan_inst.cu (compiled once per register tile R and mode: 0 k = 1, 1 cross-check, 2 k = 2)

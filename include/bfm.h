@@ -257,7 +257,12 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
  *       "window_bins" {0=auto, 1=brute-force window kernel},
  *       "taper" {0=auto (4), 1=off, 2, 4, 8: finest divisor of the segment length in the tail of a batch},
  *       "taper_pct" {0=auto (10): percent of the batch's work, at its end, that is cut finer},
- *       "finalize_rows" {0=auto (1792): query rows from which ONE problem is finalized by the tile-parallel kernels} */
+ *       "gss_div" {0=auto (3)}, "gss_min" {0=auto (16 rows; 32 with one query per thread)}: guided item lengths of the
+ *                     persistent form - an item is 1/gss_div of an even share of the work left when it starts, at least
+ *                     gss_min train rows; "taper" = 16 forces guided lengths, 1 switches them off,
+ *       "persistent" {0=auto: resident inputs take the persistent form of the kernel - at most one wave of CTAs, each
+ *                     walking a planned run of work items and then finalizing the tiles the plan gave it; 1=off: one work
+ *                     item per CTA and the CTA that completes a problem finalizes it, as on the gated host path} */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t bfm_kernel_launch_count(bfm_handle_t h);
@@ -276,6 +281,14 @@ int bfm_debug_timeline(bfm_handle_t h, uint64_t *device_buf, int32_t capacity_ct
 int bfm_plan_preview(const bfm_problem_t *problems, int32_t n_problems, int32_t queries_per_thread, int32_t slots,
                      int32_t segment_rows, int32_t waves, int32_t taper, int32_t taper_pct, int32_t *items_out,
                      int32_t capacity, int32_t *n_items, int32_t *segment_rows_out);
+
+/* Host-only preview of the finalize tiles of the persistent form (resident inputs: a grid of at most one wave draws the
+ * work items of bfm_plan_preview from a ticket counter, then finalizes the problems tile by tile, 512 query rows per
+ * tile).  tiles_out: int32[tile_capacity][5] = {problem, row0, tile number, tiles of the problem, look-back slot of the
+ * problem's tile 0}; tile_cta_out[f] = CTA (0 .. n_ctas - 1) that finalizes tile f.  A tile only waits for tiles of CTAs
+ * with a lower or equal index. */
+int bfm_plan_preview_tiles(const bfm_problem_t *problems, int32_t n_problems, int32_t n_ctas, int32_t *tiles_out,
+                           int32_t *tile_cta_out, int32_t tile_capacity, int32_t *n_tiles);
 
 /* Integer-pipe micro-benchmark: the roofline denominator.
  * test: 0 POPC, 1 LOP3, 2 IADD3, 3 POPC+LOP3 1:1, 4 POPC+2xLOP3, 5 REDUX.MIN, 6 IMAD, 7 VIMNMX,

@@ -511,10 +511,11 @@ def test_binned_window_search_equals_brute_force(eng, case):
 
 
 def test_finalize_paths_agree(eng):
-    """A call that is one problem of >= 1792 query rows is finalized by the tile-parallel kernels, a smaller
-    one by the CTA that completes it.  Forced both ways (finalize_rows knob) every mode must return the same
+    """Resident inputs take the persistent form of the matching kernel (at most one wave of CTAs, each walking a run
+    of work items, then finalizing the tiles the plan gave it); the gated host path keeps one work item per CTA and
+    the CTA that completes a problem finalizes it.  Forced both ways (persistent knob) every mode must return the same
     bits as the oracle: plain, ratio, gate, cross-check, dense mask, window, k = 3, device tensors, and the
-    local-map step (train count decided on the device)."""
+    local-map step (train count decided on the device) - always ONE launch per two neighbours."""
     import torch
     q, t, qxy, txy, _ = synth.window_scene(2100, 2600, 77)
     win = (qxy, txy, 15.0)
@@ -531,8 +532,8 @@ def test_finalize_paths_agree(eng):
     targs = (sc["des"], sc["kp"], sc["R"], sc["t"], sc["see_vector"], sc["edges"])
     tracks = []
     try:
-        for thr, kernels in ((1 << 30, 1), (1, 3)):
-            eng.set_tuning(finalize_rows=thr)
+        for thr, kernels in ((0, 1), (1, 1)):
+            eng.set_tuning(persistent=thr)
             _eq(eng.knn(q, t, 3), want["knn3"], thr)
             assert eng.launch_info()["kernels_launched"] == 2 * kernels
             _eq(eng.match(q, t, cross_check=True), want["cc"], thr)
@@ -556,18 +557,18 @@ def test_finalize_paths_agree(eng):
         _eq(tracks[0], tracks[1], "local-map step")
         assert len(tracks[0][1]) > 0 and len(tracks[0][6]) > 0
     finally:
-        eng.set_tuning(finalize_rows=0, window_bins=0)
+        eng.set_tuning(persistent=0, window_bins=0)
 
 
 def test_large_single_problem_tile_parallel_finalize(eng):
-    """A single problem with many query rows is finalized by the tile-parallel kernels (the in-kernel
-    finalize is one CTA per problem): same results, workspace left clean for the next call."""
+    """A single problem with many query rows is finalized tile by tile, in parallel, by the CTAs the plan names
+    (inside the one launch): same results, workspace left clean for the next call."""
     q, t, _ = synth.correlated(9001, 700, 123)
     oi, od = c_oracle.knn(q, t, 3)
     for k in (1, 2, 3):
         idx, dist = eng.knn(q, t, k)
         assert np.array_equal(idx, oi[:, :k]) and np.array_equal(dist, od[:, :k]), k
-        assert eng.launch_info()["kernels_launched"] == 3 * ((k + 1) // 2)
+        assert eng.launch_info()["kernels_launched"] == (k + 1) // 2
     _eq(eng.match(q, t, cross_check=True), c_oracle.cross_check(q, t))
     _eq(eng.match(q, t, k=2, ratio=0.8), orc.match(q, t, k=2, ratio=0.8))
     _eq(eng.match(q, t, cross_check=True, max_distance=25), orc.match(q, t, cross_check_=True, max_distance=25))

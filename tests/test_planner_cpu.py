@@ -100,3 +100,47 @@ def test_plan_preview_rejects_bad_arguments():
     bad[0, 1] = -1
     with pytest.raises(bb.BfmError):
         _ffi.plan_preview(bad)
+
+
+# ---- the persistent form (resident inputs): finalize tiles and their owners ---------------------------------------
+
+def _check_tiles(tab, tiles, tile_cta, n_ctas):
+    assert (np.diff(tile_cta) >= 0).all() and tile_cta.min() >= 0 and tile_cta.max() < n_ctas, "a CTA's tiles are one contiguous run"
+    slot = 0
+    for p, (_, q_count, _, _, _, _) in enumerate(tab.tolist()):
+        sel = tiles[:, 0] == p
+        mine, owners = tiles[sel], tile_cta[sel]
+        order = np.argsort(mine[:, 2], kind="stable")
+        mine, owners = mine[order], owners[order]
+        nt = max(1, -(-q_count // 512))
+        # every problem's rows exactly once, 512 rows per tile (an empty problem still gets the tile that writes its count)
+        assert len(mine) == nt and mine[:, 2].tolist() == list(range(nt)) and (mine[:, 3] == nt).all()
+        assert mine[:, 1].tolist() == [512 * j for j in range(nt)]
+        assert (mine[:, 4] == slot).all(), "look-back slots are dense and disjoint"
+        slot += nt
+        # no CTA waits for a CTA dispatched after it: owners do not decrease along the look-back chain
+        assert (np.diff(owners) >= 0).all()
+    # within one CTA the tiles come in (problem, tile) order, so a look-back never waits for a later tile of the same CTA
+    for c in np.unique(tile_cta):
+        mine = tiles[tile_cta == c]
+        key = mine[:, 0].astype(np.int64) * (1 << 20) + mine[:, 2]
+        assert (np.diff(key) > 0).all()
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(0, 9000), min_size=1, max_size=60), st.sampled_from([SLOTS, 148 * 6, 37, 3, 1]))
+def test_tile_owners_never_wait_for_a_later_cta(q_counts, n_ctas):
+    tab = bb.make_problems(q_counts, [100] * len(q_counts))
+    tiles, tile_cta = _ffi.plan_preview_tiles(tab, n_ctas)
+    _check_tiles(tab, tiles, tile_cta, n_ctas)
+
+
+def test_tiles_of_the_headline_batch_spread_over_the_grid():
+    tab = bb.make_problems([2000] * 256, [2000] * 256)
+    tiles, tile_cta = _ffi.plan_preview_tiles(tab, SLOTS)
+    _check_tiles(tab, tiles, tile_cta, SLOTS)
+    assert len(tiles) == 1024 and np.bincount(tile_cta, minlength=SLOTS).max() <= 2
+    one = bb.make_problems([70000], [70000])
+    tiles, tile_cta = _ffi.plan_preview_tiles(one, 64)      # more tiles than CTAs: consecutive tiles share a CTA, in order
+    _check_tiles(one, tiles, tile_cta, 64)
+    assert len(tiles) == 137 and np.bincount(tile_cta, minlength=64).max() <= 3
