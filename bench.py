@@ -33,6 +33,7 @@ sweep) is tools/size_sweep.py -> profiles/.
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -211,25 +212,62 @@ def extras(eng, torch, steps):
     from boslam_b200.engine import make_problems
     out = {}
 
-    def run(name, host_fn, dev_fn, frames_per_call, pairs_per_call, reps):
+    trace_buf = torch.zeros((16384, 8), dtype=torch.int64, device="cuda")
+
+    def gpu_span_us(plan):
+        """First CTA entry -> last CTA exit of ONE call on the GPU's own clock (bfm_debug_timeline: every CTA stamps
+        %globaltimer): the kernel time proper, free of launch and event latency.  Median of 5."""
+        spans = []
+        for _ in range(5):
+            trace_buf.zero_()
+            eng._lib.bfm_debug_timeline(eng._h, ctypes.c_void_p(trace_buf.data_ptr()), trace_buf.shape[0])
+            plan.run()
+            torch.cuda.synchronize()
+            eng._lib.bfm_debug_timeline(eng._h, None, 0)
+            a = trace_buf.cpu().numpy()[:, :7]
+            a = a[a[:, 0] > 0]
+            if len(a):
+                spans.append((a.max() - a[:, 0].min()) / 1e3)
+        return float(np.median(spans)) if spans else None
+
+    def run(name, host_fn, plan, frames_per_call, pairs_per_call, reps):
+        """e2e: the public host call (numpy in -> numpy out), wall clock.  device: the same problem resident in HBM
+        through a bound DevicePlan (the bare library call, ~4 us of host time): `ms_device` = back-to-back calls on one
+        stream between two CUDA events (what a loop of such calls costs per call, launch gaps included),
+        `ms_device_idle_stream` = one call between two events on an idle stream (adds the event / launch latency
+        of an empty stream, ~9 us on this pool), `us_gpu_span` = the kernel itself on the GPU clock."""
         for _ in range(3):
             host_fn()
-            dev_fn()
+            plan.run()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(reps):
             host_fn()
         e2e = (time.perf_counter() - t0) / reps
+        n_dev = max(reps, 50)
+        st = torch.cuda.current_stream().cuda_stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(reps):
-            dev_fn()
+        for _ in range(n_dev):
+            plan.run(st)
         e1.record()
         torch.cuda.synchronize()
-        dev = e0.elapsed_time(e1) / reps * 1e-3
+        dev = e0.elapsed_time(e1) / n_dev * 1e-3
+        idle = []
+        for _ in range(7):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            plan.run(st)
+            b.record()
+            torch.cuda.synchronize()
+            idle.append(a.elapsed_time(b))
+        li = eng.launch_info()
         out[name] = {"frames_per_s_e2e": frames_per_call / e2e, "frames_per_s_device": frames_per_call / dev,
                      "pairs_per_s_e2e": pairs_per_call / e2e, "pairs_per_s_device": pairs_per_call / dev,
-                     "ms_e2e": e2e * 1e3, "ms_device": dev * 1e3}
+                     "ms_e2e": e2e * 1e3, "ms_device": dev * 1e3, "ms_device_idle_stream": float(np.median(idle)),
+                     "us_gpu_span": gpu_span_us(plan), "kernels_per_call": li["kernels_launched"], "grid": li["scan_grid"],
+                     "work_items": li["segments"], "queries_per_thread": li["queries_per_thread"]}
 
     reps = max(steps, 10)
     # configs[0]: two frames, 1000 descriptors each, crossCheck + gate < 30 (slam/tracking.py:56-57)
@@ -238,7 +276,7 @@ def extras(eng, torch, steps):
     tab1 = make_problems([1000], [1000])
     run("frame_to_frame_1000x1000_crosscheck",
         lambda: eng.match(q, t, cross_check=True, max_distance=30, strict=True),
-        lambda: eng.match_batched_device(qd, td, tab1, cross_check=True, max_distance=30, strict=True),
+        eng.plan_device(qd, td, tab1, cross_check=True, max_distance=30, strict=True),
         1, 1000 * 1000, reps)
     # configs[1]: tracking, 2000 frame descriptors vs 20k local-map points, window + ratio 0.8
     q, t, qxy, txy, _ = synth.window_scene(2000, 20000, 12)
@@ -247,11 +285,11 @@ def extras(eng, torch, steps):
     tab2 = make_problems([2000], [20000])
     run("tracking_2000x20000_window_ratio",
         lambda: eng.match(q, t, k=2, ratio=RATIO, window=(qxy, txy, 15.0)),
-        lambda: eng.match_batched_device(qd, td, tab2, k=2, ratio=RATIO, window=(qxyd, txyd, 15.0)),
+        eng.plan_device(qd, td, tab2, k=2, ratio=RATIO, window=(qxyd, txyd, 15.0)),
         1, 2000 * 20000, reps)
     run("tracking_2000x20000_crosscheck_gate30",  # the reference-faithful variant (slam/tracking.py:121)
         lambda: eng.match(q, t, cross_check=True, max_distance=30),
-        lambda: eng.match_batched_device(qd, td, tab2, cross_check=True, max_distance=30),
+        eng.plan_device(qd, td, tab2, cross_check=True, max_distance=30),
         1, 2000 * 20000, reps)
     # configs[2]: local mapping, new keyframe vs 20 covisible keyframes, 2000 descriptors each
     qb, tb = synth.keyframe_pair_batch(20, 2000, 13)
@@ -259,11 +297,11 @@ def extras(eng, torch, steps):
     qbd, tbd = torch.from_numpy(qb).cuda(), torch.from_numpy(tb).cuda()
     run("local_mapping_20x2000x2000_k2_ratio",
         lambda: eng.match_batched(qb, tb, tab3, k=2, ratio=RATIO),
-        lambda: eng.match_batched_device(qbd, tbd, tab3, k=2, ratio=RATIO),
+        eng.plan_device(qbd, tbd, tab3, k=2, ratio=RATIO),
         1, 20 * 2000 * 2000, reps)
     run("local_mapping_20x2000x2000_crosscheck_gate30",   # the reference's local-mapping matcher is crossCheck=True (slam/local_mapping.py:21)
         lambda: eng.match_batched(qb, tb, tab3, cross_check=True, max_distance=30),
-        lambda: eng.match_batched_device(qbd, tbd, tab3, cross_check=True, max_distance=30),
+        eng.plan_device(qbd, tbd, tab3, cross_check=True, max_distance=30),
         1, 20 * 2000 * 2000, reps)
     # the headline batch from ordinary (pageable) numpy arrays into ordinary numpy arrays: what a caller who knows
     # nothing about pinned memory gets (worker threads stage the arrays for the kernel's feeder CTAs)

@@ -8,11 +8,11 @@ a CPU implementation.
 from . import synth  # noqa: F401
 from ._ffi import BfmError, LIB_PATH  # noqa: F401
 from .bank import KeyframeBank  # noqa: F401
-from .engine import BatchPlan, BatchResult, Engine, HostBatchBuffers, PinnedBuffer, default_engine, make_problems  # noqa: F401
+from .engine import BatchPlan, BatchResult, DevicePlan, Engine, HostBatchBuffers, PinnedBuffer, default_engine, make_problems  # noqa: F401
 from .localmap import CameraModel, MapStore, TrackResult, quaternion_from_rotation, select_representative  # noqa: F401
 from .matcher import NORM_HAMMING, BFMatcher, BFMatcher_create, DMatch, install, uninstall  # noqa: F401
 
-__all__ = ["BFMatcher", "BFMatcher_create", "DMatch", "NORM_HAMMING", "Engine", "BatchPlan", "BatchResult", "PinnedBuffer", "HostBatchBuffers",
+__all__ = ["BFMatcher", "BFMatcher_create", "DMatch", "NORM_HAMMING", "Engine", "BatchPlan", "DevicePlan", "BatchResult", "PinnedBuffer", "HostBatchBuffers",
            "make_problems", "default_engine", "KeyframeBank", "MapStore", "CameraModel", "TrackResult", "select_representative", "match", "knn_match", "match_pairs", "BfmError", "synth", "install", "uninstall"]
 
 

@@ -37,6 +37,7 @@ constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
 // length - 256-pair batch 1046 -> 1026 us (980 -> 998 G pairs/s), pinned host path 1120 -> 1104 us
 // (tools/taper_probe.py, profiles/r01f_taper_probe.log)
 constexpr int GSS_MAX_ROWS = 512;
+constexpr long long PERSISTENT_MAX_PAIRS = 600ll * 1000 * 1000;   // launches above this (~0.5 ms) take the static form
 constexpr int TAPER_AUTO = 4;
 constexpr int TAPER_PCT_AUTO = 10;
 constexpr int N_TABLE_SLOTS = 4;
@@ -48,18 +49,18 @@ std::mutex g_create_mutex;
 using bfm::ScanFn;
 
 // the kernel variants are instantiated in bfm_scan_inst.cu, one object per (register tile, mode)
-ScanFn pick_scan(int r, int mode, int mask, int pm, bool bound = false) {
-    if (bound) return bfm::pick_scan_r1_m2(mask, pm, true);   // k > 2 passes: R = 1, K = 2, transformed carry-save popcount
+ScanFn pick_scan(int r, int mode, int mask, int pm, bool bound, bool dyn) {
+    if (bound) return bfm::pick_scan_r1_m2(mask, pm, true, dyn);   // k > 2 passes: R = 1, K = 2, transformed carry-save popcount
     switch (r * 10 + mode) {
-        case 10: return bfm::pick_scan_r1_m0(mask, pm, false);
-        case 11: return bfm::pick_scan_r1_m1(mask, pm, false);
-        case 12: return bfm::pick_scan_r1_m2(mask, pm, false);
-        case 20: return bfm::pick_scan_r2_m0(mask, pm, false);
-        case 21: return bfm::pick_scan_r2_m1(mask, pm, false);
-        case 22: return bfm::pick_scan_r2_m2(mask, pm, false);
-        case 40: return bfm::pick_scan_r4_m0(mask, pm, false);
-        case 41: return bfm::pick_scan_r4_m1(mask, pm, false);
-        default: return bfm::pick_scan_r4_m2(mask, pm, false);
+        case 10: return bfm::pick_scan_r1_m0(mask, pm, false, dyn);
+        case 11: return bfm::pick_scan_r1_m1(mask, pm, false, dyn);
+        case 12: return bfm::pick_scan_r1_m2(mask, pm, false, dyn);
+        case 20: return bfm::pick_scan_r2_m0(mask, pm, false, dyn);
+        case 21: return bfm::pick_scan_r2_m1(mask, pm, false, dyn);
+        case 22: return bfm::pick_scan_r2_m2(mask, pm, false, dyn);
+        case 40: return bfm::pick_scan_r4_m0(mask, pm, false, dyn);
+        case 41: return bfm::pick_scan_r4_m1(mask, pm, false, dyn);
+        default: return bfm::pick_scan_r4_m2(mask, pm, false, dyn);
     }
 }
 
@@ -181,7 +182,7 @@ int occupancy(bfm_handle_t h, int r, int mode, int mask, int pm, int *out) {
     int &c = h->occ_cache[r_index(r)][mode][mask][pm_index(pm)];
     if (c == 0) {
         int n = 0;
-        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_scan(r, mode, mask, pm), NT, 0));
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_scan(r, mode, mask, pm, false, false), NT, 0));
         c = std::max(n, 1);
     }
     *out = c;
@@ -191,7 +192,7 @@ int occupancy(bfm_handle_t h, int r, int mode, int mask, int pm, int *out) {
 // Cut every problem into (query block, train range) segments of near-equal cost so that the grid
 // is a few balanced waves over all SMs, whatever the batch shape.
 void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems, int r, int slots,
-                   std::vector<Segment> &segs, std::vector<int> &seg_begin, int *seg_rows_out, bool guided = false) {
+                   std::vector<Segment> &segs, std::vector<int> &seg_begin, int *seg_rows_out, bool guided = false) {   // guided: the persistent form
     const int bq = NT * r;
     long long steps = 0;  // sum over query blocks of their train rows
     for (int p = 0; p < n_problems; ++p) {
@@ -202,8 +203,10 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
     int L;
     if (h->segment_rows > 0) {
         L = h->segment_rows;
-    } else if (h->waves > 0) {
-        const long long target = (long long)slots * h->waves;
+    } else if (h->waves > 0 || (guided && n_problems == 1)) {
+        // (persistent form, one problem: ONE wave - every CTA takes one item and the ticket counter hands the few
+        // that remain to whoever is done first; 2000 x 20000: 57.7 -> 56.6 us, 4096^2: 33.2 -> 31.0 us)
+        const long long target = (long long)slots * (h->waves > 0 ? h->waves : 1);
         L = (int)std::max<long long>(MIN_SEG_ROWS, (steps + target - 1) / target);
     } else {
         // All CTAs of a launch cost about the same, so a grid of n CTAs over `slots` resident ones runs
@@ -232,11 +235,10 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
             }
         }
     }
-    // Guided item lengths (the persistent form draws items from a ticket counter): an item is 1/3 of an even share
-    // of the work that is LEFT when it starts - long items while the queue is full (few commits, few prologues), short
-    // ones at the end, so that even the CTAs the warp schedulers serve last (equal CTAs of one SM progress at rates
-    // up to 3x apart: profiles/r02_timeline.md) finish their last item with everybody else.
-    const bool gss = (guided && h->taper == 0 && h->segment_rows == 0) || h->taper == 16;
+    // Guided item lengths (taper = 16; an experiment kept for profiles/r02_kernel_forms.md, never chosen automatically):
+    // an item is 1 / gss_div of an even share of the work that is LEFT when it starts.  With the persistent form it
+    // LOSES to equal lengths: the CTAs the warp schedulers serve last hold their first - longest - item to the end.
+    const bool gss = h->taper == 16;
     const int gss_min = h->gss_min > 0 ? h->gss_min : (r == 1 ? 32 : 16);
     const long long gss_div = (long long)(h->gss_div > 0 ? h->gss_div : 3) * slots;
     if (gss) L = (int)std::max<long long>(gss_min, std::min<long long>(GSS_MAX_ROWS, steps / gss_div + 1));
@@ -490,7 +492,12 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
     // resident inputs take the persistent form (at most one wave, tile-parallel finalize inside the same launch)
-    const bool persistent = !gate && !binned && h->persistent != 1;
+    // The static form wins on long launches (the hardware hands a freed CTA slot to the next work item, and a CTA that
+    // has waited longest is served first, so the items of a large batch drain in order), the persistent form on short
+    // ones (one wave, no second and third wave of CTA launches, tile-parallel finalize): profiles/r02_kernel_forms.md
+    long long total_pairs = 0;
+    for (int p = 0; p < n_problems; ++p) total_pairs += (long long)std::max(0, problems[p].q_count) * std::max(0, problems[p].t_count);
+    const bool persistent = !gate && !binned && (h->persistent == 2 || (h->persistent == 0 && total_pairs <= PERSISTENT_MAX_PAIRS));
     const int plan_sig[8] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots,
                              h->taper * 1000 + h->taper_pct + 100000 * h->gss_div + 10000000 * h->gss_min, persistent ? 1 : 0};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
@@ -515,7 +522,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         h->plan_probs[0].n_segs = bin_grid;   // the search kernel's CTAs play the role of segments
     } else if (!plan_hit) {
         // (a device-side train count re-cuts the rows that exist over equal items per query block: no guided lengths)
-        plan_segments(h, plan_problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows, persistent && t_limit == nullptr);
+        plan_segments(h, plan_problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows, persistent);
         h->plan_seg_rows = seg_rows;
         h->plan_probs = h->probs_host;
         for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = h->seg_begin[p + 1] - h->seg_begin[p];
@@ -716,7 +723,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         sp.lower_out = pass + 1 < passes ? static_cast<uint32_t *>(h->lower.p) : nullptr;
         if (pass > 0)  // the match list (gate on the nearest neighbour) was produced by the first pass
             for (int d = 0; d < n_dests; ++d) sp.dest[d].m_count = nullptr;
-        const ScanFn fn = pick_scan(r, mode, mask, pm, pass > 0);
+        const ScanFn fn = pick_scan(r, mode, mask, pm, pass > 0, persistent);
         if (pass > 0) sp.n_feed = 0;   // the inputs are resident after the first pass
         sp.trace = pass == 0 ? h->trace : nullptr;
         sp.trace_cap = h->trace_cap;
@@ -987,7 +994,7 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
         if (value < 0) return fail(h, BFM_ERR_INVALID, k + " must be >= 0");
         (k == "gss_div" ? h->gss_div : h->gss_min) = value;
     } else if (k == "persistent") {
-        if (value != 0 && value != 1) return fail(h, BFM_ERR_INVALID, "persistent must be 0 (auto: resident inputs take the persistent form) or 1 (off)");
+        if (value < 0 || value > 2) return fail(h, BFM_ERR_INVALID, "persistent must be 0 (auto), 1 (off) or 2 (always, for resident inputs)");
         h->persistent = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");

@@ -600,12 +600,22 @@ __device__ __noinline__ void feed_rows(const ScanParams &p) {
 // PM    popcount evaluation (see hamming256)
 // NT    threads per CTA (== TT: one thread transforms one staged train row)
 // BOUND only admit keys above a per-row lower bound (passes 2.. of knnMatch with k > 2; R == 1)
+// DYN   persistent form (resident inputs) / static form (the gated host path), see below
 //
-// Pipeline per CTA: chunk c+2 is fetched by TMA while chunk c is scanned; one __syncthreads per
-// chunk.  Shared memory: 2 x 4 KB train rows, 2 x 1 KB pixel coords (window), 2 x 2 KB column
-// keys (cross-check).  Roles inside one grid: CTAs [0, n_feed) are feeders (host path with pinned
-// inputs), the rest take work item blockIdx.x - n_feed.
-template <int R, int K, bool CROSS, int MASK, int PM, int NT, bool BOUND = false>
+// Static form: CTA b takes work item b (after the feeders): chunk c+2 of its train range is fetched by TMA while chunk
+// c is scanned, one __syncthreads per chunk; the CTA that completes a problem finalizes it.  CTAs [0, n_feed) are
+// feeders (host path with pinned inputs).
+//
+// Persistent form: the grid is at most one wave.  A CTA starts with item `cta` and draws its next items from a
+// device-wide ticket counter (the ticket is drawn one item ahead, so its latency hides behind the scan), which keeps
+// every SM supplied until the queue is empty whatever pace its CTAs run at; consecutive items of one query block keep
+// the queries and the running keys in registers (one commit per run); when the queue is empty the CTA finalizes the
+// tiles the plan gave it.  Measured against two alternatives (profiles/r02_kernel_forms.md): equal static shares per
+// CTA (stream-K) lose 10 % because the warp schedulers serve the CTAs of an SM at rates up to 3x apart and the slow
+// ones finish alone, and a fully overlapped chunk stream (tickets, descriptors and TMA several items ahead) loses to
+// this form because CTAs that never stall starve their neighbours - the per-item stall is what shares the pipe.
+// Shared memory: 2 x 4 KB train rows, 2 x 1 KB pixel coords (window), 2 x 2 KB column keys (cross-check).
+template <int R, int K, bool CROSS, int MASK, int PM, int NT, bool BOUND, bool DYN>
 __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const __grid_constant__ ScanParams p) {
     static_assert(!BOUND || R == 1, "the lower-bound variant (k > 2 passes) uses the plain 32-bit key path");
     constexpr int NW = NT / 32;
@@ -617,12 +627,9 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     __shared__ uint32_t s_col[CROSS ? 2 : 1][CROSS ? NW : 1][CROSS ? TT : 1];
     __shared__ int s_cnt[FIN_RPT][NW];
     __shared__ int s_flag;
-    // CTA-uniform state of the persistent form, kept out of the registers the inner loop needs:
-    // [0] current item, [1] problem / [2] first query row / [3] first output row / [5] valid rows of the query block held
-    // in registers, [4] items scanned for it since the last commit, [6] train chunks streamed so far
-    __shared__ int s_run[8];
+    __shared__ int s_run[DYN ? 8 : 1];   // persistent form: CTA-uniform state (see below)
 
-    if ((int)blockIdx.x < p.n_feed) {   // the first CTAs of the grid feed the others (SM-fed upload)
+    if (!DYN && (int)blockIdx.x < p.n_feed) {   // the first CTAs of the grid feed the others (SM-fed upload)
         if (!p.feed_stall) feed_rows<NT>(p);
         return;
     }
@@ -635,31 +642,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int cta = (int)blockIdx.x - p.n_feed;
-    // Work items.  Static form (the gated host path): CTA b takes item b and the CTA that completes a problem finalizes
-    // it.  Persistent form (resident inputs, p.queue != NULL): the grid is at most one wave; a CTA starts with item
-    // `cta` and draws its next items from a device-wide ticket counter, so CTAs the warp schedulers favour simply take
-    // more of them and all SMs run dry together; consecutive items of one query block keep the queries and the running
-    // keys in registers (one commit per run); the problems are finalized tile by tile once the queue is empty.
-    const bool dyn = p.queue != nullptr;
-    uint32_t nxt = 0;
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        mbar_fence_init();
-        s_run[0] = cta;
-        s_run[1] = -1;
-        s_run[2] = -1;
-        s_run[3] = 0;
-        s_run[4] = 0;
-        s_run[5] = 0;
-        s_run[6] = 0;
-        if (dyn) {
-            if (cta == 0) *p.queue_other = 0u;   // the counter of the NEXT launch (idle: the previous launch has drained)
-            nxt = (uint32_t)p.n_ctas + atomicAdd(p.queue, 1u);   // in flight while the first item is scanned
-        }
-    }
-    __syncthreads();
+    const int cta = (int)blockIdx.x - (DYN ? 0 : p.n_feed);
 
     // the query block held in registers and its running keys
     uint32_t qw[R][8];
@@ -669,6 +652,37 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     const uint8_t *mrow[R];
     uint32_t b1[R], b2[R], lb[R];
     int col0 = 0;
+
+    // this thread's R query descriptors of a block (two coalesced 16-byte loads each); the running keys start empty
+    auto load_queries = [&](const int q_row0, const int q_valid, const int q_local0, const int out_row0, const int problem) {
+        if (CROSS) col0 = p.problems[problem].col0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int lr = r * NT + tid;
+            const bool have = lr < q_valid;
+            if (MASK == 1) valid[r] = have;
+            const int row = q_row0 + (have ? lr : 0);
+            // .cg (L2) loads: on the SM-fed host path these arrays are written by feeder CTAs of this very launch, and
+            // ld.global.nc is only defined for memory that is read-only for the kernel's lifetime
+            const uint4 a = __ldcg(p.q + 2 * (size_t)row);
+            const uint4 b = __ldcg(p.q + 2 * (size_t)row + 1);
+            qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
+            qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
+            if (XF) transform_desc(qw[r]);
+            ibias[r] = (uint32_t)(q_local0 + lr);
+            if (MASK == 0 && !have) ibias[r] = KEY_DEAD;
+            if (MASK == 2) {
+                const float2 xy = __ldcg(p.q_xy + row);
+                // an absent row gets NaN coordinates: every window compare is false
+                qx[r] = have ? xy.x : __int_as_float(0x7fc00000);
+                qy[r] = xy.y;
+            }
+            if (MASK == 1) mrow[r] = p.mask + (size_t)(q_local0 + (have ? lr : 0)) * (size_t)p.mask_stride;
+            b1[r] = KEY_NONE;
+            b2[r] = KEY_NONE;
+            lb[r] = (BOUND && have) ? __ldg(p.lower + out_row0 + r * NT + tid) : 0u;
+        }
+    };
 
     // commit: associative min-merge of the running keys into the global row state
     // row state = (best << 32) | second, updated through its two 32-bit halves (little endian):
@@ -692,190 +706,8 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         }
     };
 
-    for (;;) {
-    // (every value of s_run read here was written before the last barrier)
-    const int item = s_run[0];
-    if (dyn ? item >= p.n_items : item != cta) break;
-    const bool first_item = item == cta;
-    const uint32_t g0 = (uint32_t)s_run[6];   // chunk g lives in buffer g & 1, barrier phase (g >> 1) & 1
-    const int acc_problem = s_run[1], acc_q0 = s_run[2], acc_out0 = s_run[3], acc_items = s_run[4], acc_qvalid = s_run[5];
-    const Segment sg = p.segs[item];
-
-    // -- input gate, SM-fed variant: wait until every feeder has finished the round that covers our rows
-    if (p.n_feed > 0) {
-        if (warp == 0) {
-            const int q_need = sg.q_row0 + sg.q_valid, t_need = sg.t_row0 + sg.t_count;
-            auto round_of = [](int rows, int per_round) {   // rounds that must be complete for rows [0, rows)
-                if (rows <= 0) return 0;
-                if (rows <= per_round) return (rows + per_round / FEED_HEAD - 1) / (per_round / FEED_HEAD);
-                return FEED_HEAD - 1 + (rows + per_round - 1) / per_round;
-            };
-            const uint32_t need = (p.feed_epoch << 16) |
-                                  (uint32_t)min(p.feed_rounds, max(round_of(q_need, p.feed_q_rows), round_of(t_need, p.feed_t_rows)));
-            const unsigned long long t0 = global_timer_ns();
-            int ok = 1;
-            uint32_t sleep_ns = 250u;
-            while (true) {
-                uint32_t v = 0xFFFFFFFFu;
-                if (lane < p.n_feed) v = *(volatile const uint32_t *)(p.feed_prog + lane);
-                v = __reduce_min_sync(0xffffffffu, v);
-                if (v >= need) break;
-                __nanosleep(sleep_ns);                      // back off: a thousand CTAs poll one cache line
-                sleep_ns = min(sleep_ns * 2u, 4000u);
-                if (global_timer_ns() - t0 > 4000000000ull) {
-                    ok = 0;
-                    if (lane == 0) *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
-                    break;
-                }
-            }
-            // feeders: data stores, __threadfence, progress store; here: progress load, fence, data loads
-            __threadfence();
-            asm volatile("fence.proxy.async;" ::: "memory");
-            if (lane == 0) s_flag = ok;
-        }
-        __syncthreads();
-        if (!s_flag) return;
-        __syncthreads();   // s_flag is reused by the kernel tail
-    }
-
-    // -- input gate (pipelined host path): wait until the copy engine has landed this segment's rows
-    if (p.ready != nullptr) {
-        if (tid == 0) {
-            const unsigned long long need_q = p.ready_base + (unsigned long long)(sg.q_row0 + sg.q_valid);
-            const unsigned long long need_t = p.ready_base + (unsigned long long)(sg.t_row0 + sg.t_count);
-            const unsigned long long t0 = global_timer_ns();
-            int ok = 1;
-            while (ld_relaxed_sys(p.ready) < need_q || ld_relaxed_sys(p.ready + 1) < need_t) {
-                __nanosleep(200);
-                if (global_timer_ns() - t0 > 4000000000ull) {   // 4 s: the copies were never queued
-                    ok = 0;
-                    *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
-                    break;
-                }
-            }
-            // the rows were written by the copy engine before the flag: order our reads (generic and
-            // async proxy) after the flag read
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
-            asm volatile("fence.proxy.async;" ::: "memory");
-            s_flag = ok;
-        }
-        __syncthreads();
-        if (!s_flag) return;
-        __syncthreads();   // s_flag is reused by the kernel tail
-    }
-
-    // train rows of this segment; with a device-side limit (a train set whose size was decided by an
-    // earlier kernel on the same stream, e.g. the visible local-map points) the range is clamped here
-    // (single problem).  The rows that exist are then re-cut evenly over this query block's `limit_segs` work
-    // items, so every item gets the same share whatever the host guessed when it planned.
-    int t_count = sg.t_count, t_row0 = sg.t_row0, t_local0 = sg.t_local0;
-    if (p.t_limit != nullptr) {
-        const int rows = max(0, __ldg(p.t_limit));
-        const int s_idx = item % p.limit_segs;
-        const int per = (rows + p.limit_segs - 1) / p.limit_segs;
-        t_row0 = sg.t_row0 - sg.t_local0 + s_idx * per;
-        t_local0 = s_idx * per;
-        t_count = max(0, min(per, rows - t_local0));
-    }
-
-    // -- start the train stream first: the TMA of chunks 0 and 1 flies while the queries are loaded ----
-    // (a persistent CTA arrives here after the closing barrier of its previous item: both buffers are free)
-    if (tid == 0) {
-        const int n0 = min(TT, t_count), n1 = min(TT, t_count - TT);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes of the previous item (transform) before async writes
-        if (n0 > 0) {
-            mbar_expect_tx(&s_bar[g0 & 1], (uint32_t)n0 * 32u);
-            bulk_g2s(&s_t[g0 & 1][0], p.t + 2 * (size_t)t_row0, (uint32_t)n0 * 32u, &s_bar[g0 & 1]);
-        }
-        if (n1 > 0) {
-            mbar_expect_tx(&s_bar[(g0 + 1) & 1], (uint32_t)n1 * 32u);
-            bulk_g2s(&s_t[(g0 + 1) & 1][0], p.t + 2 * (size_t)(t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[(g0 + 1) & 1]);
-        }
-    }
-
-    // -- a new query block: commit the run that ends here, then this thread's R query descriptors (two coalesced
-    //    16-byte loads each) --------------------------------------------------------------------------
-    const bool new_block = sg.problem != acc_problem || sg.q_local0 != acc_q0;
-    if (new_block && acc_items > 0) commit(acc_out0, acc_qvalid);
-    __syncthreads();   // s_run has been read by every thread; release: the atomics above are visible to whoever acquires the counter
-    if (tid == 0) {
-        if (new_block) {
-            if (acc_items > 0) red_release_gpu_add(p.done + acc_problem, (uint32_t)acc_items);
-            s_run[1] = sg.problem;
-            s_run[2] = sg.q_local0;
-            s_run[3] = sg.out_row0;
-            s_run[5] = sg.q_valid;
-        }
-        s_run[4] = new_block ? 1 : acc_items + 1;
-    }
-    if (new_block) {
-        if (CROSS) col0 = p.problems[sg.problem].col0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int lr = r * NT + tid;
-            const bool have = lr < sg.q_valid;
-            if (MASK == 1) valid[r] = have;
-            const int row = sg.q_row0 + (have ? lr : 0);
-            // .cg (L2) loads: on the SM-fed host path these arrays are written by feeder CTAs of this very launch, and
-            // ld.global.nc is only defined for memory that is read-only for the kernel's lifetime
-            const uint4 a = __ldcg(p.q + 2 * (size_t)row);
-            const uint4 b = __ldcg(p.q + 2 * (size_t)row + 1);
-            qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
-            qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
-            if (XF) transform_desc(qw[r]);
-            ibias[r] = (uint32_t)(sg.q_local0 + lr);
-            if (MASK == 0 && !have) ibias[r] = KEY_DEAD;
-            if (MASK == 2) {
-                const float2 xy = __ldcg(p.q_xy + row);
-                // an absent row gets NaN coordinates: every window compare is false
-                qx[r] = have ? xy.x : __int_as_float(0x7fc00000);
-                qy[r] = xy.y;
-            }
-            if (MASK == 1) mrow[r] = p.mask + (size_t)(sg.q_local0 + (have ? lr : 0)) * (size_t)p.mask_stride;
-            b1[r] = KEY_NONE;
-            b2[r] = KEY_NONE;
-            lb[r] = (BOUND && have) ? __ldg(p.lower + sg.out_row0 + r * NT + tid) : 0u;
-        }
-    }
-
-    const int nchunks = (t_count + TT - 1) / TT;
-    auto chunk_rows = [&](int c) { return min(TT, t_count - c * TT); };
-    auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer (g0 + c) & 1
-        const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
-        const uint32_t gb = (g0 + (uint32_t)c) & 1u;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes
-        mbar_expect_tx(&s_bar[gb], bytes);
-        bulk_g2s(&s_t[gb][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[gb]);
-    };
-    auto stage_xy = [&](int c) {
-        if (MASK == 2 && tid < chunk_rows(c)) s_xy[(g0 + (uint32_t)c) & 1u][tid] = __ldcg(p.t_xy + t_row0 + c * TT + tid);
-    };
-    auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
-        const uint32_t g = g0 + (uint32_t)c, gb = g & 1u;
-        mbar_wait(&s_bar[gb], (g >> 1) & 1u);
-        if (XF && tid < chunk_rows(c)) {
-            const uint4 a = s_t[gb][2 * tid], b = s_t[gb][2 * tid + 1];
-            uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            transform_desc(w);
-            s_t[gb][2 * tid] = make_uint4(w[0], w[1], w[2], w[3]);
-            s_t[gb][2 * tid + 1] = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-    };
-
-    if (first_item) trace_mark(p, 1);   // gates passed, TMA issued, queries loaded
-    __syncthreads();   // barrier init (thread 0, above) visible to every waiter
-    if (nchunks > 0) {
-        stage_xy(0);
-        if (nchunks > 1) stage_xy(1);
-        land(0);
-    }
-    __syncthreads();
-    if (first_item) trace_mark(p, 2);   // first chunk landed
-
-    for (int c = 0; c < nchunks; ++c) {
-        const int b = (int)((g0 + (uint32_t)c) & 1u);
-        const int n = chunk_rows(c);
-        const uint32_t jbase = (uint32_t)(t_local0 + c * TT);
+    // the n train rows staged in buffer b (train indices jbase ..) against the R queries of every thread
+    auto scan_chunk = [&](const int b, const int n, const uint32_t jbase) {
         if constexpr (R >= 2) {
             // ---- packed path: two queries share one register of chunk-local 16-bit keys ----------
             // key16 = d << 7 | j (j < 128), so one VIMNMX.U16x2 updates two queries at once; the
@@ -965,60 +797,144 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
                 }
             }
         }
-        if (c + 1 < nchunks) land(c + 1);
-        __syncthreads();   // chunk c fully consumed: s_t[b] / s_xy[b] free, s_col[b] complete, chunk c+1 ready
-        if (c + 2 < nchunks) {
-            if (tid == 0) fetch(c + 2);
-            stage_xy(c + 2);
-        }
-        if (CROSS) {
-            // s_col[b] is next written two chunks later, i.e. after the next barrier
-            for (int j = tid; j < n; j += NT) {
-                uint32_t m = s_col[b][0][j];
+    };
+    // cross-check: the per-warp column minima of a scanned chunk (complete after a barrier) into the global column keys
+    auto flush_cols = [&](const int b, const int n, const int col_first) {
+        for (int j = tid; j < n; j += NT) {
+            uint32_t m = s_col[b][0][j];
 #pragma unroll
-                for (int w = 1; w < NW; ++w) m = min(m, s_col[b][w][j]);
-                if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)col0 + t_local0 + c * TT + j, m);
-            }
+            for (int w = 1; w < NW; ++w) m = min(m, s_col[b][w][j]);
+            if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)col0 + col_first + j, m);
         }
-    }
-    if (first_item) trace_mark(p, 3);   // scan of the first item done
-
-    if (dyn) {
-        // the next ticket (drawn while this item was scanned); draw the one after it right away
-        if (tid == 0) {
-            s_run[6] = (int)(g0 + (uint32_t)nchunks);
-            s_run[0] = (int)min(nxt, 0x7FFFFFFFu);
-            if (nxt < (uint32_t)p.n_items) nxt = (uint32_t)p.n_ctas + atomicAdd(p.queue, 1u);
+    };
+    // a landed chunk is rewritten in place (XF), one row per thread
+    auto transform_rows = [&](const int b, const int n) {
+        if (XF && tid < n) {
+            const uint4 a = s_t[b][2 * tid], bb = s_t[b][2 * tid + 1];
+            uint32_t w[8] = {a.x, a.y, a.z, a.w, bb.x, bb.y, bb.z, bb.w};
+            transform_desc(w);
+            s_t[b][2 * tid] = make_uint4(w[0], w[1], w[2], w[3]);
+            s_t[b][2 * tid + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
-        __syncthreads();
-        continue;
-    }
+    };
 
-    // -- static form: commit, then the CTA whose item is the last of its problem finalizes it -------------
-    // (threadfence + counter: every CTA's state updates are visible before its count is)
-    commit(sg.out_row0, sg.q_valid);
-    trace_mark(p, 4);   // commit atomics issued
-    __threadfence();
-    __syncthreads();
     if (tid == 0) {
-        const uint32_t n_segs = (uint32_t)p.problems[sg.problem].n_segs;
-        const uint32_t old = atomicAdd(p.done + sg.problem, 1u);   // idles at 0xFFFFFFFF: first arrival wraps to 0
-        s_flag = (old == n_segs - 2u) ? 1 : 0;
-        if (s_flag) p.done[sg.problem] = 0xFFFFFFFFu;              // self-cleaning, like the rest of the workspace
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
     }
-    __syncthreads();
-    trace_mark(p, 5);   // done counter bumped
-    if (s_flag) {
-        __threadfence();
-        finalize_problem<NT>(p, sg.problem, s_cnt);
-        __syncthreads();
-        trace_mark(p, 6);   // finalized (only the CTA that completed its problem)
-    }
-    break;
-    }   // work items of this CTA
 
-    // -- persistent form: commit the last run, then the finalize tiles the plan gave this CTA ------------------
-    if (dyn) {
+    if constexpr (DYN) {
+        // ============================== persistent form ================================================
+        // CTA-uniform state, kept in shared memory so that it costs the inner loop no registers: s_run[0] current item,
+        // [1] problem / [2] first query row / [3] first output row / [5] valid rows of the query block held in
+        // registers, [4] items scanned for it since the last commit, [6] train chunks streamed so far
+        uint32_t nxt = 0;   // (thread 0) the next ticket, in flight while the current item is scanned
+        if (tid == 0) {
+            s_run[0] = cta;
+            s_run[1] = -1;
+            s_run[2] = -1;
+            s_run[3] = 0;
+            s_run[4] = 0;
+            s_run[5] = 0;
+            s_run[6] = 0;
+            if (cta == 0) *p.queue_other = 0u;   // the counter of the NEXT launch (idle: the previous launch has drained)
+            nxt = (uint32_t)p.n_ctas + atomicAdd(p.queue, 1u);
+        }
+        __syncthreads();
+        for (;;) {
+            // (every value of s_run read here was written before the last barrier)
+            const int item = s_run[0];
+            if (item >= p.n_items) break;
+            const bool first_item = item == cta;
+            const uint32_t g0 = (uint32_t)s_run[6];   // chunk g lives in buffer g & 1, barrier phase (g >> 1) & 1
+            const int acc_problem = s_run[1], acc_q0 = s_run[2], acc_out0 = s_run[3], acc_items = s_run[4], acc_qvalid = s_run[5];
+            const Segment sg = p.segs[item];
+            int t_count = sg.t_count, t_row0 = sg.t_row0, t_local0 = sg.t_local0;
+            if (p.t_limit != nullptr) {   // a device-side train count: the rows that exist, re-cut over the planned items
+                const int rows = max(0, __ldg(p.t_limit));
+                const int s_idx = item % p.limit_segs;
+                const int per = (rows + p.limit_segs - 1) / p.limit_segs;
+                t_row0 = sg.t_row0 - sg.t_local0 + s_idx * per;
+                t_local0 = s_idx * per;
+                t_count = max(0, min(per, rows - t_local0));
+            }
+            // start the train stream first (the closing barrier of the previous item freed both buffers)
+            if (tid == 0) {
+                const int n0 = min(TT, t_count), n1 = min(TT, t_count - TT);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes of the previous item (transform) before async writes
+                if (n0 > 0) {
+                    mbar_expect_tx(&s_bar[g0 & 1], (uint32_t)n0 * 32u);
+                    bulk_g2s(&s_t[g0 & 1][0], p.t + 2 * (size_t)t_row0, (uint32_t)n0 * 32u, &s_bar[g0 & 1]);
+                }
+                if (n1 > 0) {
+                    mbar_expect_tx(&s_bar[(g0 + 1) & 1], (uint32_t)n1 * 32u);
+                    bulk_g2s(&s_t[(g0 + 1) & 1][0], p.t + 2 * (size_t)(t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[(g0 + 1) & 1]);
+                }
+            }
+            // a new query block: commit the run that ends here, then load the block
+            const bool new_block = sg.problem != acc_problem || sg.q_local0 != acc_q0;
+            if (new_block && acc_items > 0) commit(acc_out0, acc_qvalid);
+            __syncthreads();   // s_run has been read by every thread; release: the atomics above are visible to whoever acquires the counter
+            if (tid == 0) {
+                if (new_block) {
+                    if (acc_items > 0) red_release_gpu_add(p.done + acc_problem, (uint32_t)acc_items);
+                    s_run[1] = sg.problem;
+                    s_run[2] = sg.q_local0;
+                    s_run[3] = sg.out_row0;
+                    s_run[5] = sg.q_valid;
+                }
+                s_run[4] = new_block ? 1 : acc_items + 1;
+            }
+            if (new_block) load_queries(sg.q_row0, sg.q_valid, sg.q_local0, sg.out_row0, sg.problem);
+
+            const int nchunks = (t_count + TT - 1) / TT;
+            auto chunk_rows = [&](int c) { return min(TT, t_count - c * TT); };
+            auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer (g0 + c) & 1
+                const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
+                const uint32_t gb = (g0 + (uint32_t)c) & 1u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes
+                mbar_expect_tx(&s_bar[gb], bytes);
+                bulk_g2s(&s_t[gb][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[gb]);
+            };
+            auto stage_xy = [&](int c) {
+                if (MASK == 2 && tid < chunk_rows(c)) s_xy[(g0 + (uint32_t)c) & 1u][tid] = __ldcg(p.t_xy + t_row0 + c * TT + tid);
+            };
+            auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
+                const uint32_t g = g0 + (uint32_t)c;
+                mbar_wait(&s_bar[g & 1u], (g >> 1) & 1u);
+                transform_rows((int)(g & 1u), chunk_rows(c));
+            };
+            if (first_item) trace_mark(p, 1);   // TMA issued, queries loaded
+            if (nchunks > 0) {
+                stage_xy(0);
+                if (nchunks > 1) stage_xy(1);
+                land(0);
+            }
+            __syncthreads();
+            if (first_item) trace_mark(p, 2);   // first chunk landed
+            for (int c = 0; c < nchunks; ++c) {
+                const int b = (int)((g0 + (uint32_t)c) & 1u);
+                const int n = chunk_rows(c);
+                scan_chunk(b, n, (uint32_t)(t_local0 + c * TT));
+                if (c + 1 < nchunks) land(c + 1);
+                __syncthreads();   // chunk c fully consumed: s_t[b] / s_xy[b] free, s_col[b] complete, chunk c+1 ready
+                if (c + 2 < nchunks) {
+                    if (tid == 0) fetch(c + 2);
+                    stage_xy(c + 2);
+                }
+                if (CROSS) flush_cols(b, n, t_local0 + c * TT);   // s_col[b] is next written two chunks later, after the next barrier
+            }
+            if (first_item) trace_mark(p, 3);   // scan of the first item done
+            // the next ticket (drawn while this item was scanned); draw the one after it right away
+            if (tid == 0) {
+                s_run[6] = (int)(g0 + (uint32_t)nchunks);
+                s_run[0] = (int)min(nxt, 0x7FFFFFFFu);
+                if (nxt < (uint32_t)p.n_items) nxt = (uint32_t)p.n_ctas + atomicAdd(p.queue, 1u);
+            }
+            __syncthreads();
+        }
+        // -- the queue is empty: commit the last run, then the finalize tiles the plan gave this CTA -----------------
         if (s_run[4] > 0) {
             commit(s_run[3], s_run[5]);
             __syncthreads();
@@ -1030,19 +946,174 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
             for (int f = w.x; f < w.x + w.y; ++f) finalize_tile<NT>(p, p.fin_tiles + f, s_cnt, &s_flag);
             trace_mark(p, 6);   // its finalize tiles done
         }
+    } else {
+        // ============================== static form: one work item =====================================
+        const Segment sg = p.segs[cta];
+
+        // -- input gate, SM-fed variant: wait until every feeder has finished the round that covers our rows
+        if (p.n_feed > 0) {
+            if (warp == 0) {
+                const int q_need = sg.q_row0 + sg.q_valid, t_need = sg.t_row0 + sg.t_count;
+                auto round_of = [](int rows, int per_round) {   // rounds that must be complete for rows [0, rows)
+                    if (rows <= 0) return 0;
+                    if (rows <= per_round) return (rows + per_round / FEED_HEAD - 1) / (per_round / FEED_HEAD);
+                    return FEED_HEAD - 1 + (rows + per_round - 1) / per_round;
+                };
+                const uint32_t need = (p.feed_epoch << 16) |
+                                      (uint32_t)min(p.feed_rounds, max(round_of(q_need, p.feed_q_rows), round_of(t_need, p.feed_t_rows)));
+                const unsigned long long t0 = global_timer_ns();
+                int ok = 1;
+                uint32_t sleep_ns = 250u;
+                while (true) {
+                    uint32_t v = 0xFFFFFFFFu;
+                    if (lane < p.n_feed) v = *(volatile const uint32_t *)(p.feed_prog + lane);
+                    v = __reduce_min_sync(0xffffffffu, v);
+                    if (v >= need) break;
+                    __nanosleep(sleep_ns);                      // back off: a thousand CTAs poll one cache line
+                    sleep_ns = min(sleep_ns * 2u, 4000u);
+                    if (global_timer_ns() - t0 > 4000000000ull) {
+                        ok = 0;
+                        if (lane == 0) *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
+                        break;
+                    }
+                }
+                // feeders: data stores, __threadfence, progress store; here: progress load, fence, data loads
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                if (lane == 0) s_flag = ok;
+            }
+            __syncthreads();
+            if (!s_flag) return;
+            __syncthreads();   // s_flag is reused by the kernel tail
+        }
+
+        // -- input gate (pipelined host path): wait until the copy engine has landed this segment's rows
+        if (p.ready != nullptr) {
+            if (tid == 0) {
+                const unsigned long long need_q = p.ready_base + (unsigned long long)(sg.q_row0 + sg.q_valid);
+                const unsigned long long need_t = p.ready_base + (unsigned long long)(sg.t_row0 + sg.t_count);
+                const unsigned long long t0 = global_timer_ns();
+                int ok = 1;
+                while (ld_relaxed_sys(p.ready) < need_q || ld_relaxed_sys(p.ready + 1) < need_t) {
+                    __nanosleep(200);
+                    if (global_timer_ns() - t0 > 4000000000ull) {   // 4 s: the copies were never queued
+                        ok = 0;
+                        *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
+                        break;
+                    }
+                }
+                // the rows were written by the copy engine before the flag: order our reads (generic and
+                // async proxy) after the flag read
+                asm volatile("fence.acq_rel.sys;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+                s_flag = ok;
+            }
+            __syncthreads();
+            if (!s_flag) return;
+            __syncthreads();   // s_flag is reused by the kernel tail
+        }
+
+        // train rows of this segment; with a device-side limit (a train set whose size was decided by an
+        // earlier kernel on the same stream, e.g. the visible local-map points) the range is clamped here
+        // (single problem).  The rows that exist are then re-cut evenly over this query block's `limit_segs` work
+        // items, so every item gets the same share whatever the host guessed when it planned.
+        int t_count = sg.t_count, t_row0 = sg.t_row0, t_local0 = sg.t_local0;
+        if (p.t_limit != nullptr) {
+            const int rows = max(0, __ldg(p.t_limit));
+            const int s_idx = cta % p.limit_segs;
+            const int per = (rows + p.limit_segs - 1) / p.limit_segs;
+            t_row0 = sg.t_row0 - sg.t_local0 + s_idx * per;
+            t_local0 = s_idx * per;
+            t_count = max(0, min(per, rows - t_local0));
+        }
+
+        // -- start the train stream first: the TMA of chunks 0 and 1 flies while the queries are loaded ----
+        if (tid == 0) {
+            const int n0 = min(TT, t_count), n1 = min(TT, t_count - TT);
+            if (n0 > 0) {
+                mbar_expect_tx(&s_bar[0], (uint32_t)n0 * 32u);
+                bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)t_row0, (uint32_t)n0 * 32u, &s_bar[0]);
+            }
+            if (n1 > 0) {
+                mbar_expect_tx(&s_bar[1], (uint32_t)n1 * 32u);
+                bulk_g2s(&s_t[1][0], p.t + 2 * (size_t)(t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[1]);
+            }
+        }
+        load_queries(sg.q_row0, sg.q_valid, sg.q_local0, sg.out_row0, sg.problem);
+
+        const int nchunks = (t_count + TT - 1) / TT;
+        auto chunk_rows = [&](int c) { return min(TT, t_count - c * TT); };
+        auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer c & 1
+            const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes
+            mbar_expect_tx(&s_bar[c & 1], bytes);
+            bulk_g2s(&s_t[c & 1][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[c & 1]);
+        };
+        auto stage_xy = [&](int c) {
+            if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldcg(p.t_xy + t_row0 + c * TT + tid);
+        };
+        auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
+            mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
+            transform_rows(c & 1, chunk_rows(c));
+        };
+
+        trace_mark(p, 1);   // gates passed, TMA issued, queries loaded
+        __syncthreads();   // barrier init (thread 0, above) visible to every waiter
+        if (nchunks > 0) {
+            stage_xy(0);
+            if (nchunks > 1) stage_xy(1);
+            land(0);
+        }
+        __syncthreads();
+        trace_mark(p, 2);   // first chunk landed
+
+        for (int c = 0; c < nchunks; ++c) {
+            const int n = chunk_rows(c);
+            scan_chunk(c & 1, n, (uint32_t)(t_local0 + c * TT));
+            if (c + 1 < nchunks) land(c + 1);
+            __syncthreads();   // chunk c fully consumed: s_t[b] / s_xy[b] free, s_col[b] complete, chunk c+1 ready
+            if (c + 2 < nchunks) {
+                if (tid == 0) fetch(c + 2);
+                stage_xy(c + 2);
+            }
+            if (CROSS) flush_cols(c & 1, n, t_local0 + c * TT);   // s_col[b] is next written two chunks later, after the next barrier
+        }
+        trace_mark(p, 3);   // scan done
+
+        // -- commit, then the CTA whose item is the last of its problem finalizes it -------------
+        // (threadfence + counter: every CTA's state updates are visible before its count is)
+        commit(sg.out_row0, sg.q_valid);
+        trace_mark(p, 4);   // commit atomics issued
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t n_segs = (uint32_t)p.problems[sg.problem].n_segs;
+            const uint32_t old = atomicAdd(p.done + sg.problem, 1u);   // idles at 0xFFFFFFFF: first arrival wraps to 0
+            s_flag = (old == n_segs - 2u) ? 1 : 0;
+            if (s_flag) p.done[sg.problem] = 0xFFFFFFFFu;              // self-cleaning, like the rest of the workspace
+        }
+        __syncthreads();
+        trace_mark(p, 5);   // done counter bumped
+        if (s_flag) {
+            __threadfence();
+            finalize_problem<NT>(p, sg.problem, s_cnt);
+            __syncthreads();
+            trace_mark(p, 6);   // finalized (only the CTA that completed its problem)
+        }
     }
 }
 
 typedef void (*ScanFn)(const ScanParams);
-// defined in bfm_scan_inst.cu (compiled once per register tile R and mode: 0 k = 1, 1 cross-check, 2 k = 2)
-ScanFn pick_scan_r1_m0(int mask, int pm, bool bound);
-ScanFn pick_scan_r1_m1(int mask, int pm, bool bound);
-ScanFn pick_scan_r1_m2(int mask, int pm, bool bound);
-ScanFn pick_scan_r2_m0(int mask, int pm, bool bound);
-ScanFn pick_scan_r2_m1(int mask, int pm, bool bound);
-ScanFn pick_scan_r2_m2(int mask, int pm, bool bound);
-ScanFn pick_scan_r4_m0(int mask, int pm, bool bound);
-ScanFn pick_scan_r4_m1(int mask, int pm, bool bound);
-ScanFn pick_scan_r4_m2(int mask, int pm, bool bound);
+// defined in bfm_scan_inst.cu (compiled once per register tile R and mode: 0 k = 1, 1 cross-check, 2 k = 2);
+// dyn: the persistent form (resident inputs) instead of the static one
+ScanFn pick_scan_r1_m0(int mask, int pm, bool bound, bool dyn);
+ScanFn pick_scan_r1_m1(int mask, int pm, bool bound, bool dyn);
+ScanFn pick_scan_r1_m2(int mask, int pm, bool bound, bool dyn);
+ScanFn pick_scan_r2_m0(int mask, int pm, bool bound, bool dyn);
+ScanFn pick_scan_r2_m1(int mask, int pm, bool bound, bool dyn);
+ScanFn pick_scan_r2_m2(int mask, int pm, bool bound, bool dyn);
+ScanFn pick_scan_r4_m0(int mask, int pm, bool bound, bool dyn);
+ScanFn pick_scan_r4_m1(int mask, int pm, bool bound, bool dyn);
+ScanFn pick_scan_r4_m2(int mask, int pm, bool bound, bool dyn);
 
 }  // namespace bfm

@@ -12,18 +12,19 @@ namespace bfm {
 constexpr int INST_NT = 128;
 
 template <int MASK, int PM>
-static ScanFn inst_fn() {
-    return bfm_scan_kernel<INST_R, (INST_MODE == 2 ? 2 : 1), (INST_MODE == 1), MASK, PM, INST_NT>;
+static ScanFn inst_fn(bool dyn) {
+    if (dyn) return bfm_scan_kernel<INST_R, (INST_MODE == 2 ? 2 : 1), (INST_MODE == 1), MASK, PM, INST_NT, false, true>;
+    return bfm_scan_kernel<INST_R, (INST_MODE == 2 ? 2 : 1), (INST_MODE == 1), MASK, PM, INST_NT, false, false>;
 }
 template <int MASK>
-static ScanFn inst_pm(int pm) {
+static ScanFn inst_pm(int pm, bool dyn) {
     switch (pm) {
-        case 4: return inst_fn<MASK, 4>();
-        case 5: return inst_fn<MASK, 5>();
-        case 6: return inst_fn<MASK, 6>();
-        case 40: return inst_fn<MASK, 40>();
-        case 50: return inst_fn<MASK, 50>();
-        default: return inst_fn<MASK, 8>();
+        case 4: return inst_fn<MASK, 4>(dyn);
+        case 5: return inst_fn<MASK, 5>(dyn);
+        case 6: return inst_fn<MASK, 6>(dyn);
+        case 40: return inst_fn<MASK, 40>(dyn);
+        case 50: return inst_fn<MASK, 50>(dyn);
+        default: return inst_fn<MASK, 8>(dyn);
     }
 }
 
@@ -31,22 +32,25 @@ static ScanFn inst_pm(int pm) {
 #define BFM_CAT(a, b, c, d) BFM_CAT2(a, b, c, d)
 
 // mask: 0 none, 1 dense, 2 window; bound: the k > 2 pass variant (only R = 1, MODE = 2 has it)
-ScanFn BFM_CAT(pick_scan_r, INST_R, _m, INST_MODE)(int mask, int pm, bool bound) {
+ScanFn BFM_CAT(pick_scan_r, INST_R, _m, INST_MODE)(int mask, int pm, bool bound, bool dyn) {
 #if INST_R == 1 && INST_MODE == 2
     if (bound) {
-        switch (mask) {
-            case 1: return bfm_scan_kernel<1, 2, false, 1, 40, INST_NT, true>;
-            case 2: return bfm_scan_kernel<1, 2, false, 2, 40, INST_NT, true>;
-            default: return bfm_scan_kernel<1, 2, false, 0, 40, INST_NT, true>;
+        switch (mask * 2 + (dyn ? 1 : 0)) {
+            case 2: return bfm_scan_kernel<1, 2, false, 1, 40, INST_NT, true, false>;
+            case 3: return bfm_scan_kernel<1, 2, false, 1, 40, INST_NT, true, true>;
+            case 4: return bfm_scan_kernel<1, 2, false, 2, 40, INST_NT, true, false>;
+            case 5: return bfm_scan_kernel<1, 2, false, 2, 40, INST_NT, true, true>;
+            case 1: return bfm_scan_kernel<1, 2, false, 0, 40, INST_NT, true, true>;
+            default: return bfm_scan_kernel<1, 2, false, 0, 40, INST_NT, true, false>;
         }
     }
 #else
     (void)bound;
 #endif
     switch (mask) {
-        case 1: return inst_pm<1>(pm);
-        case 2: return inst_pm<2>(pm);
-        default: return inst_pm<0>(pm);
+        case 1: return inst_pm<1>(pm, dyn);
+        case 2: return inst_pm<2>(pm, dyn);
+        default: return inst_pm<0>(pm, dyn);
     }
 }
 

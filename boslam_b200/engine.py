@@ -340,6 +340,10 @@ class Engine:
         (for loops that match the same batch shape every step: loop closing, the bench's e2e leg)."""
         return BatchPlan(self, problems, k, ratio, cross_check, max_distance, strict)
 
+    def plan_device(self, q, t, problems: np.ndarray, **kw) -> "DevicePlan":
+        """Bind a device-resident batch (CUDA tensors) once; :meth:`DevicePlan.run` is then the bare library call."""
+        return DevicePlan(self, q, t, problems, **kw)
+
     def match_pairs(self, queries: Sequence, trains: Sequence, **kw):
         """Convenience over :meth:`match_batched` for lists of per-keyframe arrays.  Identical query
         objects are stored once (loop closing: one keyframe against many candidates)."""
@@ -524,6 +528,58 @@ class Engine:
         if want_knn:
             return out["knn_idx"], out["knn_dist"], res
         return res
+
+
+class DevicePlan:
+    """A device-resident call bound once: descriptor tensors, problem table, options and output tensors are validated
+    and allocated at construction, ``run()`` is then the bare library call (one kernel launch on torch's current
+    stream, no host synchronisation, a few microseconds of host time).  For loops that match the same shapes every
+    step - a tracking loop against a resident keyframe, the bench's device-time legs.  Results: ``plan.out`` (the
+    dict :meth:`Engine.match_batched_device` returns), valid once the stream has drained."""
+
+    def __init__(self, engine: "Engine", q, t, problems, k=1, ratio=None, cross_check=False, max_distance=None,
+                 strict=False, window=None, want_knn=False):
+        import torch
+        self.engine = engine
+        self.q, self.t = engine._torch_prep(q, "q_packed"), engine._torch_prep(t, "t_packed")
+        self.probs = np.ascontiguousarray(problems, np.int32)
+        if self.probs.ndim != 2 or self.probs.shape[1] != 6:
+            raise ValueError("problems must be int32[P, 6]")
+        self.P = self.probs.shape[0]
+        self.n_out = int((self.probs[:, 4] + self.probs[:, 1]).max()) if self.P else 0
+        if k > _ffi.MAX_K:
+            raise NotImplementedError(f"k > {_ffi.MAX_K} is not supported by this build")
+        self.opts, self.none_pass = engine._options(k, ratio, cross_check, max_distance, strict)
+        self._keep = []
+        if window is not None:
+            engine._mask_args_torch(self.opts, None, window, self.q.shape[0], self.t.shape[0], self._keep)
+        dev = self.q.device
+        self.out = {"m": torch.empty((3, max(self.n_out, 1)), dtype=torch.int32, device=dev),
+                    "count": torch.zeros(max(self.P, 1), dtype=torch.int32, device=dev)}
+        ki = kd = None
+        if want_knn:
+            self.out["knn_idx"] = torch.empty((max(self.n_out, 1), k), dtype=torch.int32, device=dev)
+            self.out["knn_dist"] = torch.empty((max(self.n_out, 1), k), dtype=torch.int32, device=dev)
+            ki, kd = self.out["knn_idx"].data_ptr(), self.out["knn_dist"].data_ptr()
+        m = self.out["m"]
+        self._args = (engine._h, _ffi.MEM_DEVICE, self.q.data_ptr(), self.q.shape[0], self.t.data_ptr(), self.t.shape[0],
+                      self.probs.ctypes.data_as(ctypes.POINTER(_ffi.Problem)), self.P, self.n_out, ctypes.byref(self.opts),
+                      ki, kd, m[0].data_ptr(), m[1].data_ptr(), m[2].data_ptr(), self.out["count"].data_ptr())
+        self._fn = engine._lib.bfm_match_batched
+        self._torch = torch
+
+    def run(self, stream=None):
+        """``stream``: a raw cudaStream_t (int) to skip the current-stream lookup; default torch's current stream."""
+        if self.P and self.n_out:
+            eng = self.engine
+            st = ctypes.c_void_p(stream if stream is not None else self._torch.cuda.current_stream(eng.device).cuda_stream)
+            with eng._lock:
+                rc = self._fn(*self._args, st)
+                if rc:
+                    _ffi.check(eng._h, rc)
+            if self.none_pass:
+                self.out["count"].zero_()
+        return self.out
 
 
 class BatchPlan:

@@ -257,12 +257,13 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
  *       "window_bins" {0=auto, 1=brute-force window kernel},
  *       "taper" {0=auto (4), 1=off, 2, 4, 8: finest divisor of the segment length in the tail of a batch},
  *       "taper_pct" {0=auto (10): percent of the batch's work, at its end, that is cut finer},
- *       "gss_div" {0=auto (3)}, "gss_min" {0=auto (16 rows; 32 with one query per thread)}: guided item lengths of the
- *                     persistent form - an item is 1/gss_div of an even share of the work left when it starts, at least
- *                     gss_min train rows; "taper" = 16 forces guided lengths, 1 switches them off,
- *       "persistent" {0=auto: resident inputs take the persistent form of the kernel - at most one wave of CTAs, each
- *                     walking a planned run of work items and then finalizing the tiles the plan gave it; 1=off: one work
- *                     item per CTA and the CTA that completes a problem finalizes it, as on the gated host path} */
+ *       "persistent" {0=auto, 1=off, 2=always}: resident inputs can take the persistent form of the kernel - at most
+ *                     one wave of CTAs drawing work items from a ticket counter, then finalizing the problems tile by
+ *                     tile inside the same launch; auto uses it for launches of up to ~0.6 G pairs (a tracking frame, a
+ *                     local-mapping batch, a rank's share of a sharded loop-closing batch) and the static form (one
+ *                     work item per CTA, the CTA that completes a problem finalizes it) for longer ones and on the
+ *                     gated host path,
+ *       "taper" = 16 with "gss_div" / "gss_min": guided item lengths (an experiment, see profiles/r02_kernel_forms.md) */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t bfm_kernel_launch_count(bfm_handle_t h);

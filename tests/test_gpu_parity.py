@@ -532,7 +532,7 @@ def test_finalize_paths_agree(eng):
     targs = (sc["des"], sc["kp"], sc["R"], sc["t"], sc["see_vector"], sc["edges"])
     tracks = []
     try:
-        for thr, kernels in ((0, 1), (1, 1)):
+        for thr, kernels in ((2, 1), (1, 1)):
             eng.set_tuning(persistent=thr)
             _eq(eng.knn(q, t, 3), want["knn3"], thr)
             assert eng.launch_info()["kernels_launched"] == 2 * kernels
