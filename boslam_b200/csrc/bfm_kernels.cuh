@@ -193,6 +193,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 // debug timeline: one thread per CTA stamps point `slot` (0..7); see ScanParams::trace
 __device__ __forceinline__ void trace_mark(const ScanParams &p, int slot) {
+#ifdef BFM_AB_NOTRACE
+    (void)p; (void)slot; return;
+#endif
     if (p.trace != nullptr && threadIdx.x == 0 && (int)blockIdx.x + p.trace_base < p.trace_cap)
         p.trace[(size_t)(p.trace_base + (int)blockIdx.x) * 8 + slot] = global_timer_ns();
 }
@@ -615,8 +618,130 @@ __device__ __noinline__ void feed_rows(const ScanParams &p) {
 // ones finish alone, and a fully overlapped chunk stream (tickets, descriptors and TMA several items ahead) loses to
 // this form because CTAs that never stall starve their neighbours - the per-item stall is what shares the pipe.
 // Shared memory: 2 x 4 KB train rows, 2 x 1 KB pixel coords (window), 2 x 2 KB column keys (cross-check).
-template <int R, int K, bool CROSS, int MASK, int PM, int NT, bool BOUND, bool DYN>
-__global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const __grid_constant__ ScanParams p) {
+// (the round-1 finalize of the static form, kept with it: see the note below)
+template <int NT>
+__device__ __noinline__ void finalize_problem_v1(const ScanParams &p, const int pi, int (*s_cnt)[NT / 32]) {
+    constexpr int NW = NT / 32;
+    const Problem pr = p.problems[pi];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int k = p.k;
+    int running = 0;
+    for (int base = 0; base < pr.q_count; base += NT * FIN_RPT) {
+        int idx1[FIN_RPT], d1[FIN_RPT];
+        bool keep[FIN_RPT];
+        uint32_t bal[FIN_RPT];
+        // phase 1: all row-state loads of the tile in flight together, then the resets
+        unsigned long long st[FIN_RPT];
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            const int i = base + j * NT + tid;
+            st[j] = i < pr.q_count ? __ldcg(p.rowstate + (size_t)pr.out_begin + i) : ~0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            const int i = base + j * NT + tid;
+            if (i < pr.q_count) p.rowstate[(size_t)pr.out_begin + i] = ~0ull;
+        }
+        // phase 2: all column-key loads (cross-check) in flight together
+        uint32_t ck[FIN_RPT];
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            const uint32_t k1 = (uint32_t)(st[j] >> 32);
+            ck[j] = KEY_NONE;
+            if (p.cross_check && k1 < KEY_DEAD) ck[j] = __ldcg(p.colkeys + (size_t)pr.col0 + (k1 & IDX_MASK));
+        }
+        // phase 3: decode, knn table, keep decisions
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            const int i = base + j * NT + tid;
+            const bool in = i < pr.q_count;
+            const uint32_t k1 = (uint32_t)(st[j] >> 32), k2 = (uint32_t)st[j];
+            const bool has1 = k1 < KEY_DEAD, has2 = k2 < KEY_DEAD;
+            idx1[j] = has1 ? (int)(k1 & IDX_MASK) : -1;
+            d1[j] = has1 ? (int)(k1 >> DIST_SHIFT) : -1;
+            const int idx2 = has2 ? (int)(k2 & IDX_MASK) : -1, d2 = has2 ? (int)(k2 >> DIST_SHIFT) : -1;
+            if (in) {
+                const size_t o = ((size_t)pr.out_begin + i) * (size_t)k + (size_t)p.knn_col0;
+                for (int d = 0; d < p.n_dest; ++d) {
+                    int32_t *ki = p.dest[d].knn_idx, *kd = p.dest[d].knn_dist;
+                    if (!ki) continue;
+                    const bool mc = (p.dest_multicast >> d) & 1u;
+                    if (k == 2 && !mc) {   // 8-byte aligned: o is even
+                        *reinterpret_cast<int2 *>(ki + o) = make_int2(idx1[j], idx2);
+                        *reinterpret_cast<int2 *>(kd + o) = make_int2(d1[j], d2);
+                    } else {
+                        put_i32(ki + o, idx1[j], mc);
+                        put_i32(kd + o, d1[j], mc);
+                        if (p.knn_cols > 1) { put_i32(ki + o + 1, idx2, mc); put_i32(kd + o + 1, d2, mc); }
+                    }
+                }
+                if (p.lower_out) p.lower_out[(size_t)pr.out_begin + i] = has2 ? k2 : KEY_NONE;
+            }
+            bool kp = in && has1;
+            if (kp && p.cross_check) kp = ck[j] == (((uint32_t)d1[j] << DIST_SHIFT) | (uint32_t)i);
+            if (kp && p.use_ratio) kp = has2 && ((double)d1[j] < p.ratio * (double)d2);
+            if (kp && p.max_distance >= 0) kp = d1[j] <= p.max_distance;
+            keep[j] = kp;
+            bal[j] = __ballot_sync(0xffffffffu, kp);
+            if (lane == 0) s_cnt[j][warp] = __popc(bal[j]);
+        }
+        __syncthreads();
+        // ordered compaction: rows ascend with (j, warp, lane)
+        int before = running, tile_total = 0;
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int c = s_cnt[j][w];
+                tile_total += c;
+                if (j == 0 && w < warp) before += c;
+            }
+        }
+        int pos_j = before;   // rank of this warp's first kept row of slot j = 0
+#pragma unroll
+        for (int j = 0; j < FIN_RPT; ++j) {
+            if (j > 0) {
+                // rows of slot j come after every row of slot j-1: add the rest of slot j-1 and the
+                // warps before this one in slot j
+                int add = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    if (w >= warp) add += s_cnt[j - 1][w];
+                    if (w < warp) add += s_cnt[j][w];
+                }
+                pos_j += add;
+            }
+            if (keep[j]) {
+                const size_t o = (size_t)pr.out_begin + pos_j + __popc(bal[j] & lt);
+                const int i = base + j * NT + tid;
+                for (int d = 0; d < p.n_dest; ++d) {
+                    if (!p.dest[d].m_count) continue;
+                    const bool mc = (p.dest_multicast >> d) & 1u;
+                    put_i32(p.dest[d].m_query + o, i, mc);
+                    put_i32(p.dest[d].m_train + o, idx1[j], mc);
+                    put_i32(p.dest[d].m_dist + o, d1[j], mc);
+                }
+            }
+        }
+        running += tile_total;
+        __syncthreads();   // s_cnt is rewritten by the next tile
+    }
+    if (tid == 0)
+        for (int d = 0; d < p.n_dest; ++d)
+            if (p.dest[d].m_count) put_i32(p.dest[d].m_count + pi, running, (p.dest_multicast >> d) & 1u);
+    if (p.cross_check) {
+        // every column-key read of this problem happened above, in this CTA
+        for (int j = tid; j < pr.t_count; j += NT) p.colkeys[(size_t)pr.col0 + j] = KEY_NONE;
+    }
+}
+
+
+// ---- static form ---------------------------------------------------------------------------------
+// (kept exactly as measured in round 1: the same source inside a larger kernel gives the inner loop a different
+// instruction schedule - same 194 instructions - that is 1.5 % slower on the headline batch, tools/ab_old_new.py)
+template <int R, int K, bool CROSS, int MASK, int PM, int NT, bool BOUND>
+__global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_static_kernel(const __grid_constant__ ScanParams p) {
     static_assert(!BOUND || R == 1, "the lower-bound variant (k > 2 passes) uses the plain 32-bit key path");
     constexpr int NW = NT / 32;
     constexpr bool XF = pm_transformed(PM);
@@ -627,87 +752,181 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
     __shared__ uint32_t s_col[CROSS ? 2 : 1][CROSS ? NW : 1][CROSS ? TT : 1];
     __shared__ int s_cnt[FIN_RPT][NW];
     __shared__ int s_flag;
-    __shared__ int s_run[DYN ? 8 : 1];   // persistent form: CTA-uniform state (see below)
 
-    if (!DYN && (int)blockIdx.x < p.n_feed) {   // the first CTAs of the grid feed the others (SM-fed upload)
+    if ((int)blockIdx.x < p.n_feed) {   // the first CTAs of the grid feed the others (SM-fed upload)
         if (!p.feed_stall) feed_rows<NT>(p);
         return;
     }
-    trace_mark(p, 0);   // CTA entry
-    if (p.trace != nullptr && threadIdx.x == 0 && (int)blockIdx.x + p.trace_base < p.trace_cap) {
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        p.trace[(size_t)(p.trace_base + (int)blockIdx.x) * 8 + 7] = smid;
-    }
+    const Segment sg = p.segs[blockIdx.x - p.n_feed];
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int cta = (int)blockIdx.x - (DYN ? 0 : p.n_feed);
+    int col0 = 0;
+    if (CROSS) col0 = p.problems[sg.problem].col0;
 
-    // the query block held in registers and its running keys
+    // -- input gate, SM-fed variant: wait until every feeder has finished the round that covers our rows
+    if (p.n_feed > 0) {
+        if (warp == 0) {
+            const int q_need = sg.q_row0 + sg.q_valid, t_need = sg.t_row0 + sg.t_count;
+            auto round_of = [](int rows, int per_round) {   // rounds that must be complete for rows [0, rows)
+                if (rows <= 0) return 0;
+                if (rows <= per_round) return (rows + per_round / FEED_HEAD - 1) / (per_round / FEED_HEAD);
+                return FEED_HEAD - 1 + (rows + per_round - 1) / per_round;
+            };
+            const uint32_t need = (p.feed_epoch << 16) |
+                                  (uint32_t)min(p.feed_rounds, max(round_of(q_need, p.feed_q_rows), round_of(t_need, p.feed_t_rows)));
+            const unsigned long long t0 = global_timer_ns();
+            int ok = 1;
+            uint32_t sleep_ns = 250u;
+            while (true) {
+                uint32_t v = 0xFFFFFFFFu;
+                if (lane < p.n_feed) v = *(volatile const uint32_t *)(p.feed_prog + lane);
+                v = __reduce_min_sync(0xffffffffu, v);
+                if (v >= need) break;
+                __nanosleep(sleep_ns);                      // back off: a thousand CTAs poll one cache line
+                sleep_ns = min(sleep_ns * 2u, 4000u);
+                if (global_timer_ns() - t0 > 4000000000ull) {
+                    ok = 0;
+                    if (lane == 0) *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
+                    break;
+                }
+            }
+            // feeders: data stores, __threadfence, progress store; here: progress load, fence, data loads
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            if (lane == 0) s_flag = ok;
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        __syncthreads();   // s_flag is reused by the kernel tail
+    }
+
+    // -- input gate (pipelined host path): wait until the copy engine has landed this segment's rows
+    if (p.ready != nullptr) {
+        if (tid == 0) {
+            const unsigned long long need_q = p.ready_base + (unsigned long long)(sg.q_row0 + sg.q_valid);
+            const unsigned long long need_t = p.ready_base + (unsigned long long)(sg.t_row0 + sg.t_count);
+            const unsigned long long t0 = global_timer_ns();
+            int ok = 1;
+            while (ld_relaxed_sys(p.ready) < need_q || ld_relaxed_sys(p.ready + 1) < need_t) {
+                __nanosleep(200);
+                if (global_timer_ns() - t0 > 4000000000ull) {   // 4 s: the copies were never queued
+                    ok = 0;
+                    *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
+                    break;
+                }
+            }
+            // the rows were written by the copy engine before the flag: order our reads (generic and
+            // async proxy) after the flag read
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+            s_flag = ok;
+        }
+        __syncthreads();
+        if (!s_flag) return;
+        __syncthreads();   // s_flag is reused by the kernel tail
+    }
+
+    // train rows of this segment; with a device-side limit (a train set whose size was decided by an
+    // earlier kernel on the same stream, e.g. the visible local-map points) the range is clamped here
+    // (single problem).  The rows that exist are then re-cut evenly over this query block's `limit_segs` work
+    // items, so every CTA gets the same share whatever the host guessed when it planned.
+    int t_count = sg.t_count, t_row0 = sg.t_row0, t_local0 = sg.t_local0;
+    if (p.t_limit != nullptr) {
+        const int rows = max(0, __ldg(p.t_limit));
+        const int s_idx = ((int)blockIdx.x - p.n_feed) % p.limit_segs;
+        const int per = (rows + p.limit_segs - 1) / p.limit_segs;
+        t_row0 = sg.t_row0 - sg.t_local0 + s_idx * per;
+        t_local0 = s_idx * per;
+        t_count = max(0, min(per, rows - t_local0));
+    }
+
+    // -- start the train stream first: the TMA of chunks 0 and 1 flies while the queries are loaded ----
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        const int n0 = min(TT, t_count), n1 = min(TT, t_count - TT);
+        if (n0 > 0) {
+            mbar_expect_tx(&s_bar[0], (uint32_t)n0 * 32u);
+            bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)t_row0, (uint32_t)n0 * 32u, &s_bar[0]);
+        }
+        if (n1 > 0) {
+            mbar_expect_tx(&s_bar[1], (uint32_t)n1 * 32u);
+            bulk_g2s(&s_t[1][0], p.t + 2 * (size_t)(t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[1]);
+        }
+    }
+
+    // -- this thread's R query descriptors (two coalesced 16-byte loads each) ---------------------
     uint32_t qw[R][8];
     uint32_t ibias[R];          // CROSS: low bits of the column key (query index), dead bit if row absent
-    bool valid[MASK == 1 ? R : 1];
+    bool valid[R];
     float qx[R], qy[R];
     const uint8_t *mrow[R];
-    uint32_t b1[R], b2[R], lb[R];
-    int col0 = 0;
-
-    // this thread's R query descriptors of a block (two coalesced 16-byte loads each); the running keys start empty
-    auto load_queries = [&](const int q_row0, const int q_valid, const int q_local0, const int out_row0, const int problem) {
-        if (CROSS) col0 = p.problems[problem].col0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int lr = r * NT + tid;
-            const bool have = lr < q_valid;
-            if (MASK == 1) valid[r] = have;
-            const int row = q_row0 + (have ? lr : 0);
-            // .cg (L2) loads: on the SM-fed host path these arrays are written by feeder CTAs of this very launch, and
-            // ld.global.nc is only defined for memory that is read-only for the kernel's lifetime
-            const uint4 a = __ldcg(p.q + 2 * (size_t)row);
-            const uint4 b = __ldcg(p.q + 2 * (size_t)row + 1);
-            qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
-            qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
-            if (XF) transform_desc(qw[r]);
-            ibias[r] = (uint32_t)(q_local0 + lr);
-            if (MASK == 0 && !have) ibias[r] = KEY_DEAD;
-            if (MASK == 2) {
-                const float2 xy = __ldcg(p.q_xy + row);
-                // an absent row gets NaN coordinates: every window compare is false
-                qx[r] = have ? xy.x : __int_as_float(0x7fc00000);
-                qy[r] = xy.y;
-            }
-            if (MASK == 1) mrow[r] = p.mask + (size_t)(q_local0 + (have ? lr : 0)) * (size_t)p.mask_stride;
-            b1[r] = KEY_NONE;
-            b2[r] = KEY_NONE;
-            lb[r] = (BOUND && have) ? __ldg(p.lower + out_row0 + r * NT + tid) : 0u;
+    for (int r = 0; r < R; ++r) {
+        const int lr = r * NT + tid;
+        valid[r] = lr < sg.q_valid;
+        const int row = sg.q_row0 + (valid[r] ? lr : 0);
+        // .cg (L2) loads: on the SM-fed host path these arrays are written by feeder CTAs of this very launch, and
+        // ld.global.nc is only defined for memory that is read-only for the kernel's lifetime
+        const uint4 a = __ldcg(p.q + 2 * (size_t)row);
+        const uint4 b = __ldcg(p.q + 2 * (size_t)row + 1);
+        qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
+        qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
+        if (XF) transform_desc(qw[r]);
+        ibias[r] = (uint32_t)(sg.q_local0 + lr);
+        if (MASK == 0 && !valid[r]) ibias[r] = KEY_DEAD;
+        if (MASK == 2) {
+            const float2 xy = __ldcg(p.q_xy + row);
+            // an absent row gets NaN coordinates: every window compare is false
+            qx[r] = valid[r] ? xy.x : __int_as_float(0x7fc00000);
+            qy[r] = xy.y;
+        }
+        if (MASK == 1) mrow[r] = p.mask + (size_t)(sg.q_local0 + (valid[r] ? lr : 0)) * (size_t)p.mask_stride;
+    }
+
+    uint32_t b1[R], b2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { b1[r] = KEY_NONE; b2[r] = KEY_NONE; }
+    uint32_t lb[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) lb[r] = (BOUND && valid[r]) ? __ldg(p.lower + sg.out_row0 + r * NT + tid) : 0u;
+
+    const int nchunks = (t_count + TT - 1) / TT;
+    auto chunk_rows = [&](int c) { return min(TT, t_count - c * TT); };
+    auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer c&1
+        const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes
+        mbar_expect_tx(&s_bar[c & 1], bytes);
+        bulk_g2s(&s_t[c & 1][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[c & 1]);
+    };
+    auto stage_xy = [&](int c) {
+        if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldcg(p.t_xy + t_row0 + c * TT + tid);
+    };
+    auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
+        mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
+        if (XF && tid < chunk_rows(c)) {
+            const uint4 a = s_t[c & 1][2 * tid], b = s_t[c & 1][2 * tid + 1];
+            uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            transform_desc(w);
+            s_t[c & 1][2 * tid] = make_uint4(w[0], w[1], w[2], w[3]);
+            s_t[c & 1][2 * tid + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
     };
 
-    // commit: associative min-merge of the running keys into the global row state
-    // row state = (best << 32) | second, updated through its two 32-bit halves (little endian):
-    // one atomicMin on `best` returns the displaced key; whatever lost there, or this run's
-    // own runner-up, competes for `second` with a fire-and-forget atomic.  Every key except the
-    // final best is offered to `second` exactly when it stops being (or fails to become) the
-    // best, so `second` ends as the true runner-up for any arrival order.
-    auto commit = [&](const int out0, const int q_valid) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r * NT + tid >= q_valid || b1[r] >= KEY_DEAD) continue;
-            uint32_t *half = reinterpret_cast<uint32_t *>(p.rowstate + (size_t)(out0 + r * NT + tid));
-            if (K == 1) {
-                atomicMin(half + 1, b1[r]);
-            } else {
-                const uint32_t n2 = b2[r] >= KEY_DEAD ? KEY_NONE : b2[r];
-                const uint32_t displaced = atomicMin(half + 1, b1[r]);
-                const uint32_t cand = min(max(displaced, b1[r]), n2);
-                if (cand != KEY_NONE) atomicMin(half, cand);
-            }
-        }
-    };
+    __syncthreads();   // barrier init (thread 0, above) visible to every waiter
+    if (nchunks > 0) {
+        stage_xy(0);
+        if (nchunks > 1) stage_xy(1);
+        land(0);
+    }
+    __syncthreads();
 
-    // the n train rows staged in buffer b (train indices jbase ..) against the R queries of every thread
-    auto scan_chunk = [&](const int b, const int n, const uint32_t jbase) {
+    for (int c = 0; c < nchunks; ++c) {
+        const int b = c & 1;
+        const int n = chunk_rows(c);
+        const uint32_t jbase = (uint32_t)(t_local0 + c * TT);
         if constexpr (R >= 2) {
             // ---- packed path: two queries share one register of chunk-local 16-bit keys ----------
             // key16 = d << 7 | j (j < 128), so one VIMNMX.U16x2 updates two queries at once; the
@@ -797,7 +1016,266 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
                 }
             }
         }
+        if (c + 1 < nchunks) land(c + 1);
+        __syncthreads();   // chunk c fully consumed: s_t[b] / s_xy[b] free, s_col[b] complete, chunk c+1 ready
+        if (c + 2 < nchunks) {
+            if (tid == 0) fetch(c + 2);
+            stage_xy(c + 2);
+        }
+        if (CROSS) {
+            // s_col[b] is next written in iteration c+2, i.e. after the barrier of iteration c+1
+            for (int j = tid; j < n; j += NT) {
+                uint32_t m = s_col[b][0][j];
+#pragma unroll
+                for (int w = 1; w < NW; ++w) m = min(m, s_col[b][w][j]);
+                if (m < KEY_DEAD) atomicMin(p.colkeys + (size_t)col0 + t_local0 + c * TT + j, m);
+            }
+        }
+    }
+
+    // -- commit: associative min-merge into the global row state ---------------------------------
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (!valid[r] || b1[r] >= KEY_DEAD) continue;
+        // row state = (best << 32) | second, updated through its two 32-bit halves (little endian):
+        // one atomicMin on `best` returns the displaced key; whatever lost there, or this segment's
+        // own runner-up, competes for `second` with a fire-and-forget atomic.  Every key except the
+        // final best is offered to `second` exactly when it stops being (or fails to become) the
+        // best, so `second` ends as the true runner-up for any arrival order.
+        uint32_t *half = reinterpret_cast<uint32_t *>(p.rowstate + (size_t)(sg.out_row0 + r * NT + tid));
+        if (K == 1) {
+            atomicMin(half + 1, b1[r]);
+        } else {
+            const uint32_t n2 = b2[r] >= KEY_DEAD ? KEY_NONE : b2[r];
+            const uint32_t displaced = atomicMin(half + 1, b1[r]);
+            const uint32_t cand = min(max(displaced, b1[r]), n2);
+            if (cand != KEY_NONE) atomicMin(half, cand);
+        }
+    }
+
+    // -- problem completion: the CTA whose segment is the last of its problem finalizes it -------------
+    // (threadfence + counter: every CTA's state updates are visible before its count is)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t n_segs = (uint32_t)p.problems[sg.problem].n_segs;
+        const uint32_t old = atomicAdd(p.done + sg.problem, 1u);   // idles at 0xFFFFFFFF: first arrival wraps to 0
+        s_flag = (old == n_segs - 2u) ? 1 : 0;
+        if (s_flag) p.done[sg.problem] = 0xFFFFFFFFu;              // self-cleaning, like the rest of the workspace
+    }
+    __syncthreads();
+    if (s_flag) {
+        __threadfence();
+        finalize_problem_v1<NT>(p, sg.problem, s_cnt);
+    }
+}
+
+
+// The n train rows staged in buffer b (train indices jbase ..) against the R queries of every thread.  A macro, not a
+// lambda: expanded in place the loop gets the instruction schedule of the round-1 kernel (1023 us on the headline batch);
+// as an inlined lambda ptxas interleaves the same 194 instructions differently and the launch takes 1039 us
+// (tools/ab_old_new.py).
+#define BFM_SCAN_CHUNK(b_arg, n_arg, jbase_arg)                                                                      \
+    {                                                                                                                \
+        const int b = (b_arg);                                                                                       \
+        const int n = (n_arg);                                                                                       \
+        const uint32_t jbase = (jbase_arg);                                                                          \
+                                                                                                                     \
+        if constexpr (R >= 2) {                                                                                      \
+            /* ---- packed path: two queries share one register of chunk-local 16-bit keys ---------- */             \
+            /* key16 = d << 7 | j (j < 128), so one VIMNMX.U16x2 updates two queries at once; the */                 \
+            /* chunk's winners are folded into the 32-bit global keys once per 128 train rows. */                    \
+            uint32_t p1[R / 2], p2[R / 2];                                                                           \
+_Pragma("unroll")                                                                                                    \
+            for (int h = 0; h < R / 2; ++h) { p1[h] = 0xFFFFFFFFu; p2[h] = 0xFFFFFFFFu; }                            \
+_Pragma("unroll 2")                                                                                                  \
+            for (int j = 0; j < n; ++j) {                                                                            \
+                const uint4 ta = s_t[b][2 * j];                                                                      \
+                const uint4 tb = s_t[b][2 * j + 1];                                                                  \
+                const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};                             \
+                float2 txy;                                                                                          \
+                if (MASK == 2) txy = s_xy[b][j];                                                                     \
+                const uint32_t jpack = (uint32_t)j * 0x10001u;                                                       \
+                uint32_t ck = KEY_NONE;                                                                              \
+_Pragma("unroll")                                                                                                    \
+                for (int h = 0; h < R / 2; ++h) {                                                                    \
+                    uint32_t d[2];                                                                                   \
+_Pragma("unroll")                                                                                                    \
+                    for (int e = 0; e < 2; ++e) {                                                                    \
+                        const int r = 2 * h + e;                                                                     \
+                        d[e] = hamming256<PM>(qw[r], tw, p);                                                         \
+                        if (MASK == 1) {                                                                             \
+                            const bool ok = valid[r] && (__ldg(mrow[r] + jbase + j) != 0);                           \
+                            d[e] = ok ? d[e] : DIST_MASKED;                                                          \
+                        }                                                                                            \
+                        if (MASK == 2) {                                                                             \
+                            const bool ok = (fabsf(qx[r] - txy.x) < p.radius) && (fabsf(qy[r] - txy.y) < p.radius);  \
+                            d[e] = ok ? d[e] : DIST_MASKED;                                                          \
+                        }                                                                                            \
+                        if (CROSS) ck = min(ck, d[e] * p.mul_d32 + ibias[r]);                                        \
+                    }                                                                                                \
+                    const uint32_t packed = d[1] * p.mul_hi16 + (d[0] * p.mul_lo16 + jpack);                         \
+                    if (K == 2) p2[h] = min_u16x2(p2[h], max_u16x2(p1[h], packed));                                  \
+                    p1[h] = min_u16x2(p1[h], packed);                                                                \
+                }                                                                                                    \
+                if (CROSS) {                                                                                         \
+                    ck = __reduce_min_sync(0xffffffffu, ck);                                                         \
+                    if (lane == 0) s_col[b][warp][j] = ck;                                                           \
+                }                                                                                                    \
+            }                                                                                                        \
+            /* fold the chunk winners into the global 32-bit keys (sorted-pair merge) */                             \
+_Pragma("unroll")                                                                                                    \
+            for (int h = 0; h < R / 2; ++h) {                                                                        \
+_Pragma("unroll")                                                                                                    \
+                for (int e = 0; e < 2; ++e) {                                                                        \
+                    const int r = 2 * h + e;                                                                         \
+                    const uint32_t k1 = e ? (p1[h] >> 16) : (p1[h] & 0xFFFFu);                                       \
+                    const uint32_t k2 = e ? (p2[h] >> 16) : (p2[h] & 0xFFFFu);                                       \
+                    const uint32_t c1 = k1 >= KEY16_DEAD ? KEY_NONE : ((k1 >> 7) << DIST_SHIFT) + jbase + (k1 & 127u); \
+                    const uint32_t c2 = (K == 1 || k2 >= KEY16_DEAD) ? KEY_NONE : ((k2 >> 7) << DIST_SHIFT) + jbase + (k2 & 127u); \
+                    if (K == 2) b2[r] = min(max(b1[r], c1), min(b2[r], c2));                                         \
+                    b1[r] = min(b1[r], c1);                                                                          \
+                }                                                                                                    \
+            }                                                                                                        \
+        } else {                                                                                                     \
+_Pragma("unroll 2")                                                                                                  \
+            for (int j = 0; j < n; ++j) {                                                                            \
+                const uint4 ta = s_t[b][2 * j];                                                                      \
+                const uint4 tb = s_t[b][2 * j + 1];                                                                  \
+                const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};                             \
+                float2 txy;                                                                                          \
+                if (MASK == 2) txy = s_xy[b][j];                                                                     \
+                const uint32_t jj = jbase + (uint32_t)j;                                                             \
+                uint32_t ck = KEY_NONE;                                                                              \
+_Pragma("unroll")                                                                                                    \
+                for (int r = 0; r < R; ++r) {                                                                        \
+                    uint32_t d = hamming256<PM>(qw[r], tw, p);                                                       \
+                    if (MASK == 1) {                                                                                 \
+                        const bool ok = valid[r] && (__ldg(mrow[r] + jj) != 0);                                      \
+                        d = ok ? d : DIST_MASKED;                                                                    \
+                    }                                                                                                \
+                    if (MASK == 2) {                                                                                 \
+                        const bool ok = (fabsf(qx[r] - txy.x) < p.radius) && (fabsf(qy[r] - txy.y) < p.radius);      \
+                        d = ok ? d : DIST_MASKED;                                                                    \
+                    }                                                                                                \
+                    uint32_t key = d * p.mul_d32 + jj;                                                               \
+                    if (BOUND) key = key > lb[r] ? key : KEY_NONE;                                                   \
+                    if (K == 2) b2[r] = min(b2[r], max(b1[r], key));                                                 \
+                    b1[r] = min(b1[r], key);                                                                         \
+                    if (CROSS) ck = min(ck, d * p.mul_d32 + ibias[r]);                                               \
+                }                                                                                                    \
+                if (CROSS) {                                                                                         \
+                    ck = __reduce_min_sync(0xffffffffu, ck);                                                         \
+                    if (lane == 0) s_col[b][warp][j] = ck;                                                           \
+                }                                                                                                    \
+            }                                                                                                        \
+        }                                                                                                            \
+                                                                                                                     \
+    }
+
+template <int R, int K, bool CROSS, int MASK, int PM, int NT, bool BOUND>
+__global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_persistent_kernel(const __grid_constant__ ScanParams p) {
+    constexpr bool DYN = true;
+    static_assert(!BOUND || R == 1, "the lower-bound variant (k > 2 passes) uses the plain 32-bit key path");
+    constexpr int NW = NT / 32;
+    constexpr bool XF = pm_transformed(PM);
+    static_assert(NT == TT, "one thread per staged train row");
+    __shared__ __align__(128) uint4 s_t[2][TT * 2];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ float2 s_xy[MASK == 2 ? 2 : 1][MASK == 2 ? TT : 1];
+    __shared__ uint32_t s_col[CROSS ? 2 : 1][CROSS ? NW : 1][CROSS ? TT : 1];
+    __shared__ int s_cnt[FIN_RPT][NW];
+    __shared__ int s_flag;
+    __shared__ int s_run[DYN ? 8 : 1];   // persistent form: CTA-uniform state (see below)
+
+    trace_mark(p, 0);   // CTA entry
+#ifndef BFM_AB_NOTRACE
+    if (p.trace != nullptr && threadIdx.x == 0 && (int)blockIdx.x + p.trace_base < p.trace_cap) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.trace[(size_t)(p.trace_base + (int)blockIdx.x) * 8 + 7] = smid;
+    }
+#endif
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int cta = (int)blockIdx.x;
+
+    // the query block held in registers and its running keys
+    uint32_t qw[R][8];
+    uint32_t ibias[R];          // CROSS: low bits of the column key (query index), dead bit if row absent
+#ifdef BFM_AB_VALID
+    bool valid[R];
+#else
+    bool valid[MASK == 1 ? R : 1];
+#endif
+    float qx[R], qy[R];
+    const uint8_t *mrow[R];
+    uint32_t b1[R], b2[R], lb[R];
+    int col0 = 0;
+
+    // this thread's R query descriptors of a block (two coalesced 16-byte loads each); the running keys start empty
+    auto load_queries = [&](const int q_row0, const int q_valid, const int q_local0, const int out_row0, const int problem) {
+        if (CROSS) col0 = p.problems[problem].col0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int lr = r * NT + tid;
+            const bool have = lr < q_valid;
+#ifdef BFM_AB_VALID
+            valid[r] = have;
+#else
+            if (MASK == 1) valid[r] = have;
+#endif
+            const int row = q_row0 + (have ? lr : 0);
+            // .cg (L2) loads: on the SM-fed host path these arrays are written by feeder CTAs of this very launch, and
+            // ld.global.nc is only defined for memory that is read-only for the kernel's lifetime
+            const uint4 a = __ldcg(p.q + 2 * (size_t)row);
+            const uint4 b = __ldcg(p.q + 2 * (size_t)row + 1);
+            qw[r][0] = a.x; qw[r][1] = a.y; qw[r][2] = a.z; qw[r][3] = a.w;
+            qw[r][4] = b.x; qw[r][5] = b.y; qw[r][6] = b.z; qw[r][7] = b.w;
+            if (XF) transform_desc(qw[r]);
+            ibias[r] = (uint32_t)(q_local0 + lr);
+            if (MASK == 0 && !have) ibias[r] = KEY_DEAD;
+            if (MASK == 2) {
+                const float2 xy = __ldcg(p.q_xy + row);
+                // an absent row gets NaN coordinates: every window compare is false
+                qx[r] = have ? xy.x : __int_as_float(0x7fc00000);
+                qy[r] = xy.y;
+            }
+            if (MASK == 1) mrow[r] = p.mask + (size_t)(q_local0 + (have ? lr : 0)) * (size_t)p.mask_stride;
+            b1[r] = KEY_NONE;
+            b2[r] = KEY_NONE;
+            lb[r] = (BOUND && have) ? __ldg(p.lower + out_row0 + r * NT + tid) : 0u;
+        }
     };
+
+    // commit: associative min-merge of the running keys into the global row state
+    // row state = (best << 32) | second, updated through its two 32-bit halves (little endian):
+    // one atomicMin on `best` returns the displaced key; whatever lost there, or this run's
+    // own runner-up, competes for `second` with a fire-and-forget atomic.  Every key except the
+    // final best is offered to `second` exactly when it stops being (or fails to become) the
+    // best, so `second` ends as the true runner-up for any arrival order.
+    auto commit = [&](const int out0, const int q_valid) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#ifdef BFM_AB_VALID
+            (void)q_valid;
+            if (!valid[r] || b1[r] >= KEY_DEAD) continue;
+#else
+            if (r * NT + tid >= q_valid || b1[r] >= KEY_DEAD) continue;
+#endif
+            uint32_t *half = reinterpret_cast<uint32_t *>(p.rowstate + (size_t)(out0 + r * NT + tid));
+            if (K == 1) {
+                atomicMin(half + 1, b1[r]);
+            } else {
+                const uint32_t n2 = b2[r] >= KEY_DEAD ? KEY_NONE : b2[r];
+                const uint32_t displaced = atomicMin(half + 1, b1[r]);
+                const uint32_t cand = min(max(displaced, b1[r]), n2);
+                if (cand != KEY_NONE) atomicMin(half, cand);
+            }
+        }
+    };
+
     // cross-check: the per-warp column minima of a scanned chunk (complete after a barrier) into the global column keys
     auto flush_cols = [&](const int b, const int n, const int col_first) {
         for (int j = tid; j < n; j += NT) {
@@ -824,8 +1302,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         mbar_fence_init();
     }
 
-    if constexpr (DYN) {
-        // ============================== persistent form ================================================
+    {
         // CTA-uniform state, kept in shared memory so that it costs the inner loop no registers: s_run[0] current item,
         // [1] problem / [2] first query row / [3] first output row / [5] valid rows of the query block held in
         // registers, [4] items scanned for it since the last commit, [6] train chunks streamed so far
@@ -914,16 +1391,16 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
             __syncthreads();
             if (first_item) trace_mark(p, 2);   // first chunk landed
             for (int c = 0; c < nchunks; ++c) {
-                const int b = (int)((g0 + (uint32_t)c) & 1u);
-                const int n = chunk_rows(c);
-                scan_chunk(b, n, (uint32_t)(t_local0 + c * TT));
+                const int buf = (int)((g0 + (uint32_t)c) & 1u);
+                const int rows = chunk_rows(c);
+                BFM_SCAN_CHUNK(buf, rows, (uint32_t)(t_local0 + c * TT));
                 if (c + 1 < nchunks) land(c + 1);
                 __syncthreads();   // chunk c fully consumed: s_t[b] / s_xy[b] free, s_col[b] complete, chunk c+1 ready
                 if (c + 2 < nchunks) {
                     if (tid == 0) fetch(c + 2);
                     stage_xy(c + 2);
                 }
-                if (CROSS) flush_cols(b, n, t_local0 + c * TT);   // s_col[b] is next written two chunks later, after the next barrier
+                if (CROSS) flush_cols(buf, rows, t_local0 + c * TT);   // s_col[b] is next written two chunks later, after the next barrier
             }
             if (first_item) trace_mark(p, 3);   // scan of the first item done
             // the next ticket (drawn while this item was scanned); draw the one after it right away
@@ -945,160 +1422,6 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_kernel(const _
         if (w.y > 0) {
             for (int f = w.x; f < w.x + w.y; ++f) finalize_tile<NT>(p, p.fin_tiles + f, s_cnt, &s_flag);
             trace_mark(p, 6);   // its finalize tiles done
-        }
-    } else {
-        // ============================== static form: one work item =====================================
-        const Segment sg = p.segs[cta];
-
-        // -- input gate, SM-fed variant: wait until every feeder has finished the round that covers our rows
-        if (p.n_feed > 0) {
-            if (warp == 0) {
-                const int q_need = sg.q_row0 + sg.q_valid, t_need = sg.t_row0 + sg.t_count;
-                auto round_of = [](int rows, int per_round) {   // rounds that must be complete for rows [0, rows)
-                    if (rows <= 0) return 0;
-                    if (rows <= per_round) return (rows + per_round / FEED_HEAD - 1) / (per_round / FEED_HEAD);
-                    return FEED_HEAD - 1 + (rows + per_round - 1) / per_round;
-                };
-                const uint32_t need = (p.feed_epoch << 16) |
-                                      (uint32_t)min(p.feed_rounds, max(round_of(q_need, p.feed_q_rows), round_of(t_need, p.feed_t_rows)));
-                const unsigned long long t0 = global_timer_ns();
-                int ok = 1;
-                uint32_t sleep_ns = 250u;
-                while (true) {
-                    uint32_t v = 0xFFFFFFFFu;
-                    if (lane < p.n_feed) v = *(volatile const uint32_t *)(p.feed_prog + lane);
-                    v = __reduce_min_sync(0xffffffffu, v);
-                    if (v >= need) break;
-                    __nanosleep(sleep_ns);                      // back off: a thousand CTAs poll one cache line
-                    sleep_ns = min(sleep_ns * 2u, 4000u);
-                    if (global_timer_ns() - t0 > 4000000000ull) {
-                        ok = 0;
-                        if (lane == 0) *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
-                        break;
-                    }
-                }
-                // feeders: data stores, __threadfence, progress store; here: progress load, fence, data loads
-                __threadfence();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                if (lane == 0) s_flag = ok;
-            }
-            __syncthreads();
-            if (!s_flag) return;
-            __syncthreads();   // s_flag is reused by the kernel tail
-        }
-
-        // -- input gate (pipelined host path): wait until the copy engine has landed this segment's rows
-        if (p.ready != nullptr) {
-            if (tid == 0) {
-                const unsigned long long need_q = p.ready_base + (unsigned long long)(sg.q_row0 + sg.q_valid);
-                const unsigned long long need_t = p.ready_base + (unsigned long long)(sg.t_row0 + sg.t_count);
-                const unsigned long long t0 = global_timer_ns();
-                int ok = 1;
-                while (ld_relaxed_sys(p.ready) < need_q || ld_relaxed_sys(p.ready + 1) < need_t) {
-                    __nanosleep(200);
-                    if (global_timer_ns() - t0 > 4000000000ull) {   // 4 s: the copies were never queued
-                        ok = 0;
-                        *(volatile uint32_t *)p.status = 1u   /* pinned host word: a plain store, no PCIe atomic needed */;
-                        break;
-                    }
-                }
-                // the rows were written by the copy engine before the flag: order our reads (generic and
-                // async proxy) after the flag read
-                asm volatile("fence.acq_rel.sys;" ::: "memory");
-                asm volatile("fence.proxy.async;" ::: "memory");
-                s_flag = ok;
-            }
-            __syncthreads();
-            if (!s_flag) return;
-            __syncthreads();   // s_flag is reused by the kernel tail
-        }
-
-        // train rows of this segment; with a device-side limit (a train set whose size was decided by an
-        // earlier kernel on the same stream, e.g. the visible local-map points) the range is clamped here
-        // (single problem).  The rows that exist are then re-cut evenly over this query block's `limit_segs` work
-        // items, so every item gets the same share whatever the host guessed when it planned.
-        int t_count = sg.t_count, t_row0 = sg.t_row0, t_local0 = sg.t_local0;
-        if (p.t_limit != nullptr) {
-            const int rows = max(0, __ldg(p.t_limit));
-            const int s_idx = cta % p.limit_segs;
-            const int per = (rows + p.limit_segs - 1) / p.limit_segs;
-            t_row0 = sg.t_row0 - sg.t_local0 + s_idx * per;
-            t_local0 = s_idx * per;
-            t_count = max(0, min(per, rows - t_local0));
-        }
-
-        // -- start the train stream first: the TMA of chunks 0 and 1 flies while the queries are loaded ----
-        if (tid == 0) {
-            const int n0 = min(TT, t_count), n1 = min(TT, t_count - TT);
-            if (n0 > 0) {
-                mbar_expect_tx(&s_bar[0], (uint32_t)n0 * 32u);
-                bulk_g2s(&s_t[0][0], p.t + 2 * (size_t)t_row0, (uint32_t)n0 * 32u, &s_bar[0]);
-            }
-            if (n1 > 0) {
-                mbar_expect_tx(&s_bar[1], (uint32_t)n1 * 32u);
-                bulk_g2s(&s_t[1][0], p.t + 2 * (size_t)(t_row0 + TT), (uint32_t)n1 * 32u, &s_bar[1]);
-            }
-        }
-        load_queries(sg.q_row0, sg.q_valid, sg.q_local0, sg.out_row0, sg.problem);
-
-        const int nchunks = (t_count + TT - 1) / TT;
-        auto chunk_rows = [&](int c) { return min(TT, t_count - c * TT); };
-        auto fetch = [&](int c) {   // one thread: TMA bulk copy of chunk c into buffer c & 1
-            const uint32_t bytes = (uint32_t)chunk_rows(c) * 32u;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes (transform) before async writes
-            mbar_expect_tx(&s_bar[c & 1], bytes);
-            bulk_g2s(&s_t[c & 1][0], p.t + 2 * (size_t)(t_row0 + c * TT), bytes, &s_bar[c & 1]);
-        };
-        auto stage_xy = [&](int c) {
-            if (MASK == 2 && tid < chunk_rows(c)) s_xy[c & 1][tid] = __ldcg(p.t_xy + t_row0 + c * TT + tid);
-        };
-        auto land = [&](int c) {    // wait for chunk c, then (XF) rewrite its rows in place, one per thread
-            mbar_wait(&s_bar[c & 1], (uint32_t)((c >> 1) & 1));
-            transform_rows(c & 1, chunk_rows(c));
-        };
-
-        trace_mark(p, 1);   // gates passed, TMA issued, queries loaded
-        __syncthreads();   // barrier init (thread 0, above) visible to every waiter
-        if (nchunks > 0) {
-            stage_xy(0);
-            if (nchunks > 1) stage_xy(1);
-            land(0);
-        }
-        __syncthreads();
-        trace_mark(p, 2);   // first chunk landed
-
-        for (int c = 0; c < nchunks; ++c) {
-            const int n = chunk_rows(c);
-            scan_chunk(c & 1, n, (uint32_t)(t_local0 + c * TT));
-            if (c + 1 < nchunks) land(c + 1);
-            __syncthreads();   // chunk c fully consumed: s_t[b] / s_xy[b] free, s_col[b] complete, chunk c+1 ready
-            if (c + 2 < nchunks) {
-                if (tid == 0) fetch(c + 2);
-                stage_xy(c + 2);
-            }
-            if (CROSS) flush_cols(c & 1, n, t_local0 + c * TT);   // s_col[b] is next written two chunks later, after the next barrier
-        }
-        trace_mark(p, 3);   // scan done
-
-        // -- commit, then the CTA whose item is the last of its problem finalizes it -------------
-        // (threadfence + counter: every CTA's state updates are visible before its count is)
-        commit(sg.out_row0, sg.q_valid);
-        trace_mark(p, 4);   // commit atomics issued
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const uint32_t n_segs = (uint32_t)p.problems[sg.problem].n_segs;
-            const uint32_t old = atomicAdd(p.done + sg.problem, 1u);   // idles at 0xFFFFFFFF: first arrival wraps to 0
-            s_flag = (old == n_segs - 2u) ? 1 : 0;
-            if (s_flag) p.done[sg.problem] = 0xFFFFFFFFu;              // self-cleaning, like the rest of the workspace
-        }
-        __syncthreads();
-        trace_mark(p, 5);   // done counter bumped
-        if (s_flag) {
-            __threadfence();
-            finalize_problem<NT>(p, sg.problem, s_cnt);
-            __syncthreads();
-            trace_mark(p, 6);   // finalized (only the CTA that completed its problem)
         }
     }
 }

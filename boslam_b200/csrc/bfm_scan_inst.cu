@@ -13,8 +13,8 @@ constexpr int INST_NT = 128;
 
 template <int MASK, int PM>
 static ScanFn inst_fn(bool dyn) {
-    if (dyn) return bfm_scan_kernel<INST_R, (INST_MODE == 2 ? 2 : 1), (INST_MODE == 1), MASK, PM, INST_NT, false, true>;
-    return bfm_scan_kernel<INST_R, (INST_MODE == 2 ? 2 : 1), (INST_MODE == 1), MASK, PM, INST_NT, false, false>;
+    if (dyn) return bfm_scan_persistent_kernel<INST_R, (INST_MODE == 2 ? 2 : 1), (INST_MODE == 1), MASK, PM, INST_NT, false>;
+    return bfm_scan_static_kernel<INST_R, (INST_MODE == 2 ? 2 : 1), (INST_MODE == 1), MASK, PM, INST_NT, false>;
 }
 template <int MASK>
 static ScanFn inst_pm(int pm, bool dyn) {
@@ -36,12 +36,12 @@ ScanFn BFM_CAT(pick_scan_r, INST_R, _m, INST_MODE)(int mask, int pm, bool bound,
 #if INST_R == 1 && INST_MODE == 2
     if (bound) {
         switch (mask * 2 + (dyn ? 1 : 0)) {
-            case 2: return bfm_scan_kernel<1, 2, false, 1, 40, INST_NT, true, false>;
-            case 3: return bfm_scan_kernel<1, 2, false, 1, 40, INST_NT, true, true>;
-            case 4: return bfm_scan_kernel<1, 2, false, 2, 40, INST_NT, true, false>;
-            case 5: return bfm_scan_kernel<1, 2, false, 2, 40, INST_NT, true, true>;
-            case 1: return bfm_scan_kernel<1, 2, false, 0, 40, INST_NT, true, true>;
-            default: return bfm_scan_kernel<1, 2, false, 0, 40, INST_NT, true, false>;
+            case 2: return bfm_scan_static_kernel<1, 2, false, 1, 40, INST_NT, true>;
+            case 3: return bfm_scan_persistent_kernel<1, 2, false, 1, 40, INST_NT, true>;
+            case 4: return bfm_scan_static_kernel<1, 2, false, 2, 40, INST_NT, true>;
+            case 5: return bfm_scan_persistent_kernel<1, 2, false, 2, 40, INST_NT, true>;
+            case 1: return bfm_scan_persistent_kernel<1, 2, false, 0, 40, INST_NT, true>;
+            default: return bfm_scan_static_kernel<1, 2, false, 0, 40, INST_NT, true>;
         }
     }
 #else
