@@ -759,6 +759,63 @@ def main():
                        "the symmetric-memory barrier (overlapping the next step's kernel; the last one is waited for inside the "
                        "timed region)" if fe is not None else "") + "; one stream sync per step"}
 
+    # -- e2e, resident form: the descriptors live in a KeyframeBank since keyframe creation (what boslam's map does:
+    #    KeyFrame.des is created once, slam/covisibility_graph.py:119-138); a step sends only this rank's block of the
+    #    pair list (keyframe ids) and gets the match lists back in pinned host memory - plus, at N > 1, the exchange --
+    e2e_res = None
+    if e2e_steps:
+        bank = bb.KeyframeBank(capacity_rows=n_sets * 2 * n_out + 64, engine=eng)
+        pair_sets = []
+        for s_ in range(n_sets):
+            pq, pt = pinned[s_]
+            ids = np.zeros((P_loc, 2), np.int64)
+            for p_ in range(P_loc):
+                kq, kt = (s_ * 2 * P_loc) + p_, (s_ * 2 * P_loc) + P_loc + p_
+                bank.add(kq, pq.array[p_ * N_DESC:(p_ + 1) * N_DESC])
+                bank.add(kt, pt.array[p_ * N_DESC:(p_ + 1) * N_DESC])
+                ids[p_] = (kq, kt)
+            pair_sets.append(ids)
+        fb = None
+        if fused is not None:
+            from boslam_b200.distributed import FusedGather
+            fb = FusedGather(n_out, P_loc, k=2)
+
+        def bank_step(i):
+            if fb is not None:
+                r = fb.run_bank(bank, pair_sets[i % n_sets], k=2, ratio=RATIO)
+                fb.barrier()
+                return r
+            return bank.match_pairs(pair_sets[i % n_sets], k=2, ratio=RATIO, copy=False)
+
+        for i in range(args.warmup):
+            rb = bank_step(i)
+        if fb is not None:
+            fb.wait()
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            rb = bank_step(i)
+        if fb is not None:
+            fb.wait()
+            torch.cuda.synchronize()
+        res_s = max_over_ranks(max(time.perf_counter() - t0, 1e-9))
+        barrier()
+        # same bits as the host-array leg's last step (same input set)
+        same = bool(np.array_equal(rb.counts, res.counts[:P_loc]) and int(rb.counts.sum()) == n_match)
+        if same:
+            for p_ in (0, P_loc // 2, P_loc - 1):
+                same = same and all(np.array_equal(a, b) for a, b in zip(rb[p_], res[p_]))
+        if not same:
+            raise SystemExit("e2e resident leg: the bank's match lists differ from the host-array leg's")
+        e2e_res = {"value": pairs_per_step * e2e_steps / res_s, "unit": "pairs/s", "ms_per_step": res_s / e2e_steps * 1e3,
+                   "h2d_bytes_per_step": int(P_loc * 24), "d2h_bytes_per_step": n_match * 12 + P_loc * 4, "bytes_are": "per rank",
+                   "exchange_in_timed_region": fb is not None, "same_lists_as_e2e": same,
+                   "how": "KeyframeBank.match_pairs: descriptors resident in HBM since keyframe creation, a step uploads this "
+                          "rank's block of the pair list as a problem table, ONE kernel launch matches it and writes the match "
+                          "lists into pinned host memory" + (" and into every rank's symmetric table, then the barrier" if fb is not None else "") +
+                          "; one stream sync per step"}
+
     line = {
         "metric": "hamming_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -771,7 +828,7 @@ def main():
                                 if fused is not None else f"pair list split x{world}, NCCL all_gather of match tables"
                                 if gather_mode == "nccl" else f"DIAGNOSTIC: pair list split x{world} with NO exchange")
                 if world > 1 else "single GPU"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": int(launches), "roofline": roofline,
         "launch": {k: info[k] for k in ("scan_grid", "scan_block", "queries_per_thread", "popc_mode",
                                         "train_rows_per_segment")},
         "frames_per_s": N_PAIRS * args.steps / (ms * 1e-3),

@@ -28,6 +28,10 @@ class KeyframeBank:
         self._rows = torch.empty((max(int(capacity_rows), 1), 32), dtype=torch.uint8, device=self._dev)
         self._used = 0
         self._where: Dict[int, Tuple[int, int]] = {}   # keyframe id -> (first row, rows)
+        # the same map as arrays indexed by keyframe id (ids are small non-negative integers in boslam: a counter,
+        # slam/nodes.py:14-17), so a pair list becomes a problem table by fancy indexing, without a Python loop
+        self._start = np.zeros(1024, np.int32)
+        self._count = np.full(1024, -1, np.int32)
         self._dead = 0                                 # rows of erased keyframes (reclaimed by compaction)
         self._out: Optional[HostBatchBuffers] = None
 
@@ -52,11 +56,13 @@ class KeyframeBank:
         if n:
             self._rows[self._used:self._used + n].copy_(self._torch.from_numpy(d), non_blocking=False)
         self._where[kf_id] = (self._used, n)
+        self._index(kf_id, self._used, n)
         self._used += n
 
     def erase(self, kf_id: int) -> None:
         """``CovisibilityGraph.erase_kf`` counterpart: the rows are reclaimed at the next compaction."""
         b, n = self._where.pop(kf_id)
+        self._index(kf_id, 0, -1)
         self._dead += n
 
     def _compact(self, need_rows: int) -> None:
@@ -69,26 +75,57 @@ class KeyframeBank:
         for kf_id, (b, n) in list(self._where.items()):
             fresh[pos:pos + n].copy_(self._rows[b:b + n])
             self._where[kf_id] = (pos, n)
+            self._index(kf_id, pos, n)
             pos += n
         self._rows, self._used, self._dead = fresh, pos, 0
+
+    def _index(self, kf_id, start, n):
+        if isinstance(kf_id, (int, np.integer)) and 0 <= kf_id < (1 << 24):
+            if kf_id >= len(self._start):
+                m = max(2 * len(self._start), int(kf_id) + 1)
+                self._start = np.concatenate([self._start, np.zeros(m - len(self._start), np.int32)])
+                self._count = np.concatenate([self._count, np.full(m - len(self._count), -1, np.int32)])
+            self._start[kf_id], self._count[kf_id] = start, n
+
+    def problem_table(self, pairs) -> np.ndarray:
+        """int32[P, 6] problem table of ``pairs`` = [(query keyframe id, train keyframe id), ...] over the bank's rows."""
+        ids = np.asarray(pairs)
+        P = len(ids)
+        tab = np.zeros((P, 6), np.int32)
+        if P == 0:
+            return tab
+        if ids.ndim == 2 and ids.dtype.kind in "iu" and ids.min() >= 0 and ids.max() < len(self._start):
+            qi, ti = ids[:, 0], ids[:, 1]
+            if (self._count[qi] >= 0).all() and (self._count[ti] >= 0).all():
+                tab[:, 0], tab[:, 1] = self._start[qi], self._count[qi]
+                tab[:, 2], tab[:, 3] = self._start[ti], self._count[ti]
+                tab[1:, 4] = np.cumsum(tab[:-1, 1])
+                return tab
+        out_rows = 0
+        for p, (qi, ti) in enumerate(pairs):     # ids that are not small integers, or unknown ids (KeyError)
+            qb, qn = self._where[qi]
+            tb, tn = self._where[ti]
+            tab[p] = (qb, qn, tb, tn, out_rows, 0)
+            out_rows += qn
+        return tab
 
     def descriptors(self, kf_id: int) -> np.ndarray:
         b, n = self._where[kf_id]
         return self._rows[b:b + n].cpu().numpy()
 
     def match_pairs(self, pairs: Sequence[Tuple[int, int]], k: int = 1, ratio=None, cross_check: bool = False,
-                    max_distance=None, strict: bool = False, want_knn: bool = False) -> BatchResult:
+                    max_distance=None, strict: bool = False, want_knn: bool = False, replicas=None,
+                    copy: bool = True) -> BatchResult:
         """One batched launch over ``pairs`` = [(query keyframe id, train keyframe id), ...].
-        Returns a :class:`BatchResult` (and the dense knn tables first with ``want_knn``)."""
+        Returns a :class:`BatchResult` (and the dense knn tables first with ``want_knn``).
+
+        ``replicas``: device destinations (:meth:`boslam_b200.distributed.FusedGather.destinations`) the same epilogue
+        writes as well - the multi-GPU exchange of a sharded pair list.  ``copy=False`` returns views of the bank's
+        pinned result buffers (valid until the next call) instead of copies."""
         torch = self._torch
         P = len(pairs)
-        tab = np.zeros((P, 6), np.int32)
-        out_rows = 0
-        for p, (qi, ti) in enumerate(pairs):
-            qb, qn = self._where[qi]
-            tb, tn = self._where[ti]
-            tab[p] = (qb, qn, tb, tn, out_rows, 0)
-            out_rows += qn
+        tab = self.problem_table(pairs)
+        out_rows = int(tab[-1, 4] + tab[-1, 1]) if P else 0
         if P == 0 or out_rows == 0:
             e = np.zeros(0, np.int32)
             res = BatchResult(e, e.copy(), e.copy(), np.zeros(P, np.int32), tab[:, 4].copy())
@@ -102,14 +139,15 @@ class KeyframeBank:
             dest["knn_idx"], dest["knn_dist"] = ob.knn_idx.ctypes.data, ob.knn_dist.ctypes.data
         with torch.cuda.device(self._dev):
             self.engine.match_batched_device(self._rows, self._rows, tab, k=k, ratio=ratio, cross_check=cross_check,
-                                             max_distance=max_distance, strict=strict, want_knn=want_knn, out=dest)
+                                             max_distance=max_distance, strict=strict, want_knn=want_knn, out=dest,
+                                             replicas=replicas)
             torch.cuda.current_stream(self._dev).synchronize()   # results are in pinned host memory now
         none_pass = self.engine._gate(max_distance, strict) == -2
-        counts = ob.count[:P].copy()
+        cp = (lambda a: a.copy()) if copy else (lambda a: a)
+        counts = cp(ob.count[:P])
         if none_pass:
             counts[:] = 0
-        res = BatchResult(ob.m[0][:out_rows].copy(), ob.m[1][:out_rows].copy(), ob.m[2][:out_rows].copy(), counts,
-                          tab[:, 4].copy())
+        res = BatchResult(cp(ob.m[0][:out_rows]), cp(ob.m[1][:out_rows]), cp(ob.m[2][:out_rows]), counts, tab[:, 4].copy())
         if want_knn:
-            return ob.knn_idx[:out_rows].copy(), ob.knn_dist[:out_rows].copy(), res
+            return cp(ob.knn_idx[:out_rows]), cp(ob.knn_dist[:out_rows]), res
         return res

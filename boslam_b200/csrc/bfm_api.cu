@@ -37,7 +37,7 @@ constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
 // length - 256-pair batch 1046 -> 1026 us (980 -> 998 G pairs/s), pinned host path 1120 -> 1104 us
 // (tools/taper_probe.py, profiles/r01f_taper_probe.log)
 constexpr int GSS_MAX_ROWS = 512;
-constexpr long long PERSISTENT_MAX_PAIRS = 600ll * 1000 * 1000;   // launches above this (~0.5 ms) take the static form
+constexpr long long PERSISTENT_MAX_PAIRS = 300ll * 1000 * 1000;   // launches above this (~0.3 ms) take the static form
 constexpr int TAPER_AUTO = 4;
 constexpr int TAPER_PCT_AUTO = 10;
 constexpr int N_TABLE_SLOTS = 4;
@@ -133,6 +133,7 @@ struct bfm_handle_s {
     std::vector<Problem> probs_host, plan_probs;
     // plan cache + workspace hygiene
     bool plan_valid = false, state_clean = false;
+    bool check_clean = false;   // BFM_CHECK_CLEAN in the environment at bfm_create
     int plan_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int plan_seg_rows = 0;
     std::vector<bfm_problem_t> plan_problems;
@@ -216,16 +217,27 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
         // waves for the best wave efficiency, discounted by the per-CTA fixed cost (~4 rows).
         const long long lo = std::max<long long>(MIN_SEG_ROWS, steps / ((long long)slots * 12));
         const long long hi = std::max<long long>(lo, steps / ((long long)slots * 3) + 1);
+        // (the search visits ~256 candidate lengths; a batch is mostly a few distinct shapes, so it runs over the
+        // histogram of (query blocks, train rows) instead of over every problem: 256 equal pairs cost 0.65 ms otherwise,
+        // which a loop-closing step with a fresh candidate list would pay every time)
+        std::vector<std::pair<std::pair<int, int>, long long>> shapes;
+        for (int p = 0; p < n_problems; ++p) {
+            const bfm_problem_t &pr = problems[p];
+            if (pr.q_count <= 0 || pr.t_count <= 0) continue;
+            const std::pair<int, int> key((pr.q_count + bq - 1) / bq, pr.t_count);
+            if (!shapes.empty() && shapes.back().first == key) { ++shapes.back().second; continue; }
+            bool found = false;
+            for (size_t i = 0; i < shapes.size() && i < 16 && !found; ++i)
+                if (shapes[i].first == key) { ++shapes[i].second; found = true; }
+            if (!found) shapes.emplace_back(key, 1);
+        }
         double best = -1.0;
         L = (int)lo;
-        const long long stride = std::max<long long>(1, (hi - lo) / 256);
+        const long long n_cand = std::max<long long>(8, std::min<long long>(256, 20000 / std::max<size_t>(shapes.size(), 1)));   // bounded work for ragged batches
+        const long long stride = std::max<long long>(1, (hi - lo) / n_cand);
         for (long long cand = hi; cand >= lo; cand -= stride) {
             long long n = 0;
-            for (int p = 0; p < n_problems; ++p) {
-                const bfm_problem_t &pr = problems[p];
-                if (pr.q_count <= 0 || pr.t_count <= 0) continue;
-                n += (long long)((pr.q_count + bq - 1) / bq) * ((pr.t_count + cand - 1) / cand);
-            }
+            for (const auto &sh : shapes) n += sh.second * sh.first.first * ((sh.first.second + cand - 1) / cand);
             const double waves = (double)n / slots;
             const double eff = waves / std::ceil(waves - 1e-9);
             const double score = eff * (double)cand / ((double)cand + 4.0);
@@ -408,7 +420,13 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         return BFM_OK;
     }
     // stream hand-over: the workspace and the device tables are shared by all calls on this handle
-    if (h->last_pending && h->last_stream != st) CU_TRY(h, cudaStreamWaitEvent(st, h->last_ev, 0));
+    if (h->last_pending && h->last_stream != st) {
+        // (work left on the handle's own stream is marked lazily - a host call synchronises before it returns, and a
+        // tracking call costs no event when nobody follows on another stream; caller streams get their event eagerly,
+        // they may not exist any more when the next call arrives)
+        if (h->last_stream == h->stream) CU_TRY(h, cudaEventRecord(h->last_ev, h->stream));
+        CU_TRY(h, cudaStreamWaitEvent(st, h->last_ev, 0));
+    }
     if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(t)) & 15)
         return fail(h, BFM_ERR_INVALID, "descriptor arrays must be 16-byte aligned");
     if (n_dests < 1 || n_dests > bfm::MAX_DEST || !dests)
@@ -467,6 +485,12 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         hinted.t_count = std::min(problems[0].t_count, std::max(128, (guess + 1023) & ~1023));
         plan_problems = &hinted;
     }
+    // The static form wins on long launches (the hardware hands a freed CTA slot to the next work item, and a CTA that
+    // has waited longest is served first, so the items of a large batch drain in order), the persistent form on short
+    // ones (one wave, no second and third wave of CTA launches, tile-parallel finalize): profiles/r02_kernel_forms.md
+    long long total_pairs = 0;
+    for (int p = 0; p < n_problems; ++p) total_pairs += (long long)std::max(0, problems[p].q_count) * std::max(0, problems[p].t_count);
+    const bool persistent = !gate && !binned && (h->persistent == 2 || (h->persistent == 0 && total_pairs <= PERSISTENT_MAX_PAIRS));
     if (binned) r = 1;
     if (r != 1 && r != 2 && r != 4) {
         // largest register tile that still leaves >= 2 work items per CTA slot
@@ -480,7 +504,9 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
                     units += (long long)((plan_problems[p].q_count + NT * cand - 1) / (NT * cand)) *
                              ((plan_problems[p].t_count + 2 * MIN_SEG_ROWS - 1) / (2 * MIN_SEG_ROWS));
             r = cand;
-            if (units >= 2ll * occ * h->sm_count) break;
+            // (four queries per thread pay off from ~40 keyframe pairs: 32 pairs 153 vs 149 us, 20 pairs 105 vs 101 us
+            // with two - shorter work items, shorter tail; profiles/r02_kernel_forms.md)
+            if (units >= (cand == 4 && persistent ? 4ll : 2ll) * occ * h->sm_count) break;
         }
     }
     {
@@ -492,12 +518,6 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
     // resident inputs take the persistent form (at most one wave, tile-parallel finalize inside the same launch)
-    // The static form wins on long launches (the hardware hands a freed CTA slot to the next work item, and a CTA that
-    // has waited longest is served first, so the items of a large batch drain in order), the persistent form on short
-    // ones (one wave, no second and third wave of CTA launches, tile-parallel finalize): profiles/r02_kernel_forms.md
-    long long total_pairs = 0;
-    for (int p = 0; p < n_problems; ++p) total_pairs += (long long)std::max(0, problems[p].q_count) * std::max(0, problems[p].t_count);
-    const bool persistent = !gate && !binned && (h->persistent == 2 || (h->persistent == 0 && total_pairs <= PERSISTENT_MAX_PAIRS));
     const int plan_sig[8] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots,
                              h->taper * 1000 + h->taper_pct + 100000 * h->gss_div + 10000000 * h->gss_min, persistent ? 1 : 0};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
@@ -514,7 +534,33 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             if ((long long)spans[i - 1].first + spans[i - 1].second > spans[i].first)
                 return fail(h, BFM_ERR_INVALID, "two problems share output rows (out_begin ranges overlap)");
     }
-    if (!plan_hit && binned) {
+    // same shapes, other rows (a loop-closing step with a fresh candidate list: every keyframe has its 2000 descriptors,
+    // only their places in the bank differ): the cut of the cached plan still holds, its work items are re-based on
+    // the new rows instead of planned again (256 pairs: ~0.15 ms of planning -> ~10 us)
+    bool shape_hit = false;
+    if (!plan_hit && !binned && h->plan_valid && plan_problems == problems && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
+        h->plan_problems.size() == (size_t)n_problems && !h->segs_host.empty()) {
+        shape_hit = true;
+        for (int p = 0; p < n_problems && shape_hit; ++p)
+            shape_hit = problems[p].q_count == h->plan_problems[p].q_count && problems[p].t_count == h->plan_problems[p].t_count;
+        if (shape_hit) {
+            for (Segment &sg : h->segs_host) {
+                const bfm_problem_t &pr = problems[sg.problem];
+                const bool placeholder = sg.q_valid == 0 && sg.t_count == 0;   // the one item of an empty problem
+                sg.q_row0 = placeholder ? 0 : pr.q_begin + sg.q_local0;
+                sg.out_row0 = pr.out_begin + sg.q_local0;
+                sg.t_row0 = placeholder ? 0 : pr.t_begin + sg.t_local0;
+            }
+            for (int p = 0; p < n_problems; ++p) {
+                const int n_segs = h->plan_probs[p].n_segs;
+                h->plan_probs[p] = h->probs_host[p];
+                h->plan_probs[p].n_segs = n_segs;
+            }
+        }
+    }
+    if (shape_hit) {
+        // (nothing to plan)
+    } else if (!plan_hit && binned) {
         h->segs_host.clear();
         h->seg_begin.assign(2, 0);
         h->plan_seg_rows = 0;
@@ -740,7 +786,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
     h->state_clean = true;  // every slot touched is restored by the CTA that finalizes its problem
-    CU_TRY(h, cudaEventRecord(h->last_ev, st));
+    if (st != h->stream) CU_TRY(h, cudaEventRecord(h->last_ev, st));
     h->last_stream = st;
     h->last_pending = true;
 
@@ -757,7 +803,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         CU_TRY(h, cudaEventElapsedTime(&h->info.scan_ms, h->ev[0], h->ev[1]));
         h->info.total_ms = h->info.scan_ms;
     }
-    if (std::getenv("BFM_CHECK_CLEAN") && !gate) {  // debugging aid: the workspace must be all-ones after every call
+    if (h->check_clean && !gate) {  // debugging aid: the workspace must be all-ones after every call
         CU_TRY(h, cudaDeviceSynchronize());
         std::vector<unsigned char> host(h->state.cap);
         CU_TRY(h, cudaMemcpy(host.data(), h->state.p, h->state.cap, cudaMemcpyDeviceToHost));
@@ -814,6 +860,7 @@ int bfm_create(int device, bfm_handle_t *out) {
     bfm_handle_t h = new bfm_handle_s();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
+    h->check_clean = std::getenv("BFM_CHECK_CLEAN") != nullptr;
     std::memset(h->occ_cache, 0, sizeof(h->occ_cache));
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) == cudaSuccess;

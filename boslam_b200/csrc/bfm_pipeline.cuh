@@ -130,6 +130,9 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
     } else if (h->pipeline_chunks == 0 && n_problems >= 4 && !dense && qb + tb >= ((size_t)(h->pipeline_min_kb > 0 ? h->pipeline_min_kb : 1024) << 10)) {
         G = std::min(12, n_problems);
     }
+    // (one large problem - a frame against the local map, 0.7 MB - keeps the plain copy: the gated form measured
+    // slower for it, 197 vs 141 us end to end, because its work items are query-block major and every block needs
+    // the whole train set; profiles/r02_small_calls.md)
     const bool trace = std::getenv("BFM_TRACE") != nullptr;
     const auto cpu0 = std::chrono::steady_clock::now();
     auto cpu_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - cpu0).count(); };
@@ -273,12 +276,31 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
                                 "launched %.3f, staged %.3f, kernel done %.3f ms (direct=%d)\n",
                                 h->pool->size() + 1, gate.n_feed, gate.rounds, t_submitted, t_launched, t_staged, cpu_ms(), (int)direct);
     } else if (G <= 1) {
-        if (qb) CU_TRY(h, cudaMemcpyAsync(din + o_q, q, qb, cudaMemcpyHostToDevice, st));
-        if (tb) CU_TRY(h, cudaMemcpyAsync(din + o_t, t, tb, cudaMemcpyHostToDevice, st));
-        if (mask_b) CU_TRY(h, cudaMemcpyAsync(din + o_m, o->mask, mask_b, cudaMemcpyHostToDevice, st));
-        if (qxy_b) {
-            CU_TRY(h, cudaMemcpyAsync(din + o_qxy, o->q_xy, qxy_b, cudaMemcpyHostToDevice, st));
-            CU_TRY(h, cudaMemcpyAsync(din + o_txy, o->t_xy, txy_b, cudaMemcpyHostToDevice, st));
+        if (in_total <= ((size_t)160 << 10) && !mask_b) {
+            // a small frame (two ORB frames: 64 KB): the arrays are gathered into the pinned staging block with the
+            // device layout and go up in ONE copy - each cudaMemcpyAsync from pageable memory costs ~6 us of host time
+            if (h->h_stage_cap < in_total) {
+                if (h->h_stage) CU_TRY(h, cudaFreeHost(h->h_stage));
+                h->h_stage = nullptr;
+                h->h_stage_cap = 0;
+                const size_t want = std::max(in_total + in_total / 4 + 4096, (size_t)256 << 10);
+                CU_TRY(h, cudaMallocHost(&h->h_stage, want));
+                h->h_stage_cap = want;
+            }
+            char *stage = static_cast<char *>(h->h_stage);
+            if (qb) std::memcpy(stage + o_q, q, qb);
+            if (tb) std::memcpy(stage + o_t, t, tb);
+            if (qxy_b) std::memcpy(stage + o_qxy, o->q_xy, qxy_b);
+            if (txy_b) std::memcpy(stage + o_txy, o->t_xy, txy_b);
+            CU_TRY(h, cudaMemcpyAsync(din, stage, in_total, cudaMemcpyHostToDevice, st));
+        } else {
+            if (qb) CU_TRY(h, cudaMemcpyAsync(din + o_q, q, qb, cudaMemcpyHostToDevice, st));
+            if (tb) CU_TRY(h, cudaMemcpyAsync(din + o_t, t, tb, cudaMemcpyHostToDevice, st));
+            if (mask_b) CU_TRY(h, cudaMemcpyAsync(din + o_m, o->mask, mask_b, cudaMemcpyHostToDevice, st));
+            if (qxy_b) {
+                CU_TRY(h, cudaMemcpyAsync(din + o_qxy, o->q_xy, qxy_b, cudaMemcpyHostToDevice, st));
+                CU_TRY(h, cudaMemcpyAsync(din + o_txy, o->t_xy, txy_b, cudaMemcpyHostToDevice, st));
+            }
         }
         const double t_copies = cpu_ms();
         rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t),

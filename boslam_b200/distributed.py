@@ -187,6 +187,17 @@ class FusedGather:
         own, peers = self.destinations()
         return plan.run(q, t, host_out, replicas=[own] + list(peers))
 
+    def run_bank(self, bank, pairs, **kw):
+        """The same step over a :class:`boslam_b200.KeyframeBank` (descriptors resident since keyframe creation,
+        ``pairs`` = this rank's block of (query id, train id)): one launch matches the block, writes the match lists
+        into the bank's pinned host buffers AND into slice ``rank`` of every rank's table.  Synchronous; follow with
+        :meth:`barrier`.  Returns the bank's :class:`BatchResult` (views of its pinned buffers)."""
+        n = self.step
+        if n >= self.SLOTS:
+            self._barrier_done[n - self.SLOTS + 1].synchronize()
+        own, peers = self.destinations()
+        return bank.match_pairs(pairs, replicas=[own] + list(peers), copy=False, **kw)
+
     def barrier(self):
         """All ranks' kernels of this step have finished (and their NVLink writes with them): the slot is
         complete on every rank once this barrier has run.  It is queued on a side stream behind this step's

@@ -29,6 +29,14 @@ def _is_torch(x) -> bool:
     return type(x).__module__.split(".")[0] == "torch"
 
 
+def _addr(a: np.ndarray) -> int:
+    """Address of a numpy array's first byte (0.7 us; ``a.ctypes.data`` builds a helper object: 1.9 us)."""
+    try:
+        return ctypes.addressof(ctypes.c_char.from_buffer(a))
+    except (TypeError, ValueError):      # read-only or empty arrays
+        return a.ctypes.data
+
+
 def _check_desc_np(a, name: str) -> np.ndarray:
     """cv2 raises on non-uint8 descriptors; so do we.  Non-contiguous is accepted."""
     a = np.asarray(a)
@@ -147,6 +155,9 @@ class Engine:
         self.device = int(device)
         self._lock = threading.Lock()  # the C handle is not re-entrant
         self._fin = weakref.finalize(self, self._lib.bfm_destroy, h)
+        self._opt_cache = {}           # option sets of the plain match call -> (struct, byref, gate nothing passes)
+        self._cnt = np.zeros(4, np.int32)
+        self._cnt_ptr = self._cnt.ctypes.data
 
     # -- housekeeping -------------------------------------------------------------------------
     def close(self):
@@ -256,6 +267,38 @@ class Engine:
         cross_check -> cv2 ``BFMatcher(crossCheck=True).match``; ratio -> Lowe test on the 2-NN;
         max_distance (+ strict) -> the gates of slam/tracking.py:121 (``<=``) and :57 (``<``).
         """
+        if type(query) is np.ndarray and type(train) is np.ndarray and mask is None and window is None:
+            # the call shape of the reference (slam/tracking.py:56,121): two plain descriptor arrays.  Everything that
+            # does not depend on the data - options, the ctypes plumbing - is cached per option set: ~8 us of Python
+            # instead of ~27
+            q, t = query, train
+            if (q.dtype == np.uint8 and t.dtype == np.uint8 and q.ndim == 2 and t.ndim == 2 and q.shape[1] == DESC_BYTES and
+                    t.shape[1] == DESC_BYTES and q.strides == (DESC_BYTES, 1) and t.strides == (DESC_BYTES, 1)):
+                nq, nt = q.shape[0], t.shape[0]
+                key = (k, ratio, cross_check, max_distance, strict)
+                hit = self._opt_cache.get(key)
+                if hit is None:
+                    self._check_limits(0, 0, k)
+                    opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
+                    hit = self._opt_cache[key] = (opts, ctypes.byref(opts), none_pass)
+                    if len(self._opt_cache) > 64:
+                        self._opt_cache.clear()
+                if nq == 0 or nt == 0 or hit[2]:
+                    e = np.zeros(0, np.int32)
+                    return e, e.copy(), np.zeros(0, np.float32)
+                if nt >= _ffi.MAX_TRAIN_ROWS or nq >= _ffi.MAX_QUERY_ROWS:
+                    self._check_limits(nq, nt, k)
+                qa, ta = _addr(q), _addr(t)
+                if not ((qa | ta) & 15):
+                    buf = np.empty((3, nq), np.int32)
+                    b = _addr(buf)
+                    with self._lock:
+                        rc = self._lib.bfm_match(self._h, _ffi.MEM_HOST, qa, nq, ta, nt, hit[1], b, b + 4 * nq, b + 8 * nq,
+                                                 self._cnt_ptr, None)
+                        if rc:
+                            _ffi.check(self._h, rc)
+                        n = int(self._cnt[0])
+                    return buf[0, :n], buf[1, :n], buf[2, :n].astype(np.float32)
         if _is_torch(query):
             return self._match_torch(query, train, k, ratio, cross_check, mask, window, max_distance, strict)
         q = _check_desc_np(query, "query")

@@ -245,3 +245,29 @@ def test_default_engines_of_dead_threads_are_closed(eng):
         alive = [k for k, (e, th_) in E._default_engines.items() if th_.is_alive()]
         dead = [k for k, (e, th_) in E._default_engines.items() if not th_.is_alive()]
     assert len(alive) >= 1 and len(dead) <= 1
+
+
+@pytest.mark.parametrize("persistent", [1, 2])
+def test_same_shapes_other_rows_reuse_the_plan(eng, persistent):
+    """A loop-closing step names other keyframes than the step before, of the same sizes: the cached cut of the work is
+    re-based on the new rows instead of being planned again.  Results must follow the rows - in both forms of the
+    kernel, with an empty keyframe in the list, for k = 2 + ratio and for cross-check."""
+    sizes = [300, 300, 0, 450, 300, 450, 300, 300, 450, 300]
+    kfs = {i: synth.correlated(max(n, 1), max(n, 1), 700 + i)[1][:n] for i, n in enumerate(sizes)}
+    bank = bb.KeyframeBank(capacity_rows=8192, engine=eng)
+    for i, d in kfs.items():
+        bank.add(i, d)
+    same = lambda a: [j for j in kfs if len(kfs[j]) == len(kfs[a])]
+    step1 = [(0, 1), (3, 5), (2, 0), (4, 6), (8, 3), (7, 9)]
+    # the same shapes, every keyframe replaced by another one of its size (so every row offset differs)
+    step2 = [(9, 7), (5, 8), (2, 4), (6, 1), (3, 5), (0, 4)]
+    assert [(len(kfs[a]), len(kfs[b])) for a, b in step1] == [(len(kfs[a]), len(kfs[b])) for a, b in step2]
+    try:
+        eng.set_tuning(persistent=persistent)
+        for kw, okw in ((dict(k=2, ratio=0.9), dict(k=2, ratio=0.9)), (dict(cross_check=True, max_distance=70), dict(cross_check_=True, max_distance=70))):
+            for step in (step1, step2, step1, step2[::-1]):
+                res = bank.match_pairs(step, **kw)
+                for p, (a, b) in enumerate(step):
+                    _eq(res[p], orc.match(kfs[a], kfs[b], **okw), (persistent, kw, a, b))
+    finally:
+        eng.set_tuning(persistent=0)
