@@ -490,6 +490,10 @@ def main():
 
     eng = bb.Engine(local_rank)
     dev = torch.device("cuda", local_rank)
+    tune = {}
+    if os.environ.get("BFM_TUNE"):   # diagnostics: e.g. BFM_TUNE=feeders=-1,feed_rows=16384 (A/B of the upload modes)
+        tune = {k: int(v) for k, v in (kv.split("=") for kv in os.environ["BFM_TUNE"].split(","))}
+        eng.set_tuning(**tune)
     # -- the workload: ONE list of 256 pairs per step; this rank's contiguous block of it ------
     blk0, blk1 = partition_pairs([N_DESC * N_DESC] * N_PAIRS, world)[rank]
     P_loc = blk1 - blk0
@@ -750,6 +754,8 @@ def main():
         e2e = {"value": pairs_per_step * e2e_steps / e2e_s, "unit": "pairs/s",
                "h2d_bytes_per_step": int(2 * n_out * 32 + tab.nbytes), "d2h_bytes_per_step": n_match * 12 + P_loc * 4,
                "bytes_are": "per rank", "ms_per_step": e2e_s / e2e_steps * 1e3, "matches_last_step_this_rank": n_match,
+               "h2d_gbs_per_gpu": 2 * n_out * 32 / (e2e_s / e2e_steps) / 1e9, "h2d_gbs_all_gpus": world * 2 * n_out * 32 / (e2e_s / e2e_steps) / 1e9,
+               "tuning": tune or None,
                "copy_chunks": eng.launch_info().get("copy_chunks"), "exchange_in_timed_region": fe is not None,
                "exchange_verified": e2e_ok,
                "how": "numpy (pinned) in -> numpy (pinned) out through Engine.plan_batch(...).run: ONE kernel launch per step whose "

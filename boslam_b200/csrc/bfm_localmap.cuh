@@ -167,6 +167,81 @@ __global__ void __launch_bounds__(LM_NT) lm_gather_kernel(const int32_t *hdr, co
     }
 }
 
+// ---- keyframe vote (reference slam/tracking.py:154) -------------------------------------
+// Counter(ids_matching_kfs[inds[inliers]]).most_common(top): the keyframes that own the map points the pose
+// optimisation kept, most frequent first, ties in order of first appearance (Counter.most_common sorts stably by
+// count).  One CTA: the (keyframe id, position) pairs of the inliers are sorted in shared memory (bitonic), runs
+// of equal ids become (count, first position) records, and those are sorted again by count.
+constexpr int VOTE_NT = 1024, VOTE_MAX = 4096;
+constexpr size_t VOTE_SMEM = (size_t)VOTE_MAX * 12;
+
+template <typename T>
+__device__ __forceinline__ void vote_bitonic(T *a, const int n_pow2) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += VOTE_NT) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const T x = a[i], y = a[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(VOTE_NT) lm_vote_kernel(const int32_t *m_train, const int32_t *vis_edge, const int32_t *edge_kf,
+                                                          const int32_t *inliers, const int32_t n_inliers, const int32_t n_matches,
+                                                          const int32_t top, int32_t *out /* [0] n, [1 .. top] ids, [1 + top ..] counts */) {
+    extern __shared__ __align__(16) unsigned char s_vote[];   // VOTE_SMEM bytes (more than 48 KB: opted in by the host)
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(s_vote);
+    uint32_t *s_run = reinterpret_cast<uint32_t *>(s_vote + (size_t)VOTE_MAX * 8);
+    __shared__ int s_n;
+    int n_pow2 = 1;
+    while (n_pow2 < n_inliers) n_pow2 <<= 1;
+    if (threadIdx.x == 0) s_n = 0;
+    for (int i = threadIdx.x; i < n_pow2; i += VOTE_NT) {
+        unsigned long long key = ~0ull;
+        if (i < n_inliers) {
+            const int k = inliers[i];
+            if (k >= 0 && k < n_matches) {
+                const uint32_t kf = (uint32_t)edge_kf[vis_edge[m_train[k]]] ^ 0x80000000u;   // signed order
+                key = ((unsigned long long)kf << 32) | (uint32_t)i;
+            }
+        }
+        s_key[i] = key;
+    }
+    __syncthreads();
+    vote_bitonic(s_key, n_pow2);
+    // runs of equal keyframe ids: (count, first position, keyframe) - the first element of a run holds its lowest position
+    for (int i = threadIdx.x; i < n_pow2; i += VOTE_NT) {
+        const unsigned long long key = s_key[i];
+        if (key != ~0ull && (i == 0 || (s_key[i - 1] >> 32) != (key >> 32))) {
+            int e = i + 1;
+            while (e < n_pow2 && s_key[e] != ~0ull && (s_key[e] >> 32) == (key >> 32)) ++e;   // (the padding sorts behind keyframe INT_MAX)
+            const int r = atomicAdd(&s_n, 1);
+            // most frequent first, then first appearance (a position < 4096: 12 bits)
+            s_run[r] = ((uint32_t)(VOTE_MAX - (e - i)) << 12) | (uint32_t)(key & 0xFFFu);
+        }
+    }
+    __syncthreads();
+    const int n_runs = s_n;
+    int r_pow2 = 1;
+    while (r_pow2 < n_runs) r_pow2 <<= 1;
+    for (int i = n_runs + threadIdx.x; i < r_pow2; i += VOTE_NT) s_run[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    vote_bitonic(s_run, r_pow2);
+    const int n_out = min(n_runs, top);
+    if (threadIdx.x == 0) out[0] = n_out;
+    for (int r = threadIdx.x; r < n_out; r += VOTE_NT) {
+        const uint32_t rec = s_run[r];
+        out[1 + r] = edge_kf[vis_edge[m_train[inliers[rec & 0xFFFu]]]];   // the keyframe of the run's first inlier
+        out[1 + top + r] = VOTE_MAX - (int32_t)(rec >> 12);
+    }
+}
+
 // scatter of an update batch into the store (slots may repeat: last writer in batch order wins is NOT
 // guaranteed, callers pass each slot once per call)
 __global__ void lm_scatter_kernel(int32_t n, const int32_t *slots, int32_t capacity, const uint4 *desc, const double *pt3d,

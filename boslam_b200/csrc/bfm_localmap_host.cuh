@@ -11,6 +11,10 @@ struct bfm_map_s {
     void *h_in = nullptr, *h_out = nullptr;   // pinned staging
     size_t h_in_cap = 0, h_out_cap = 0;
     int32_t last_visible = 0;  // visible edges of the previous call: the planning hint for the next one
+    // device views of the last bfm_track_local_map call (valid until the next call that uses the map's workspace):
+    // what bfm_keyframe_vote reads
+    const int32_t *last_m_train = nullptr, *last_vis_edge = nullptr;
+    int32_t last_matches = -1, last_edges = 0;
 };
 
 namespace {
@@ -86,6 +90,7 @@ int bfm_map_update(bfm_map_t m, int32_t n, const int32_t *slots, const uint8_t *
     h->err.clear();
     if (n < 0 || (n > 0 && !slots)) return fail(h, BFM_ERR_INVALID, "bad update batch");
     if (n == 0) return BFM_OK;
+    m->last_matches = -1;   // the workspace is reused
     for (int i = 0; i < n; ++i)
         if (slots[i] < 0 || slots[i] >= m->capacity) return fail(h, BFM_ERR_INVALID, "slot " + std::to_string(slots[i]) + " is outside the store");
     CU_TRY(h, cudaSetDevice(h->device));
@@ -135,6 +140,7 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     if (opts->mask_kind != BFM_MASK_NONE && opts->mask_kind != BFM_MASK_WINDOW) return fail(h, BFM_ERR_INVALID, "bad mask_kind");
     *n_visible = 0;
     *n_matches = 0;
+    m->last_matches = -1;
     if (n_edges == 0) return BFM_OK;
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
@@ -262,6 +268,10 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     *n_visible = nv;
     *n_matches = nm;
     m->last_visible = nv;   // tracking is temporally coherent: the next frame's plan is sized for about this many rows
+    m->last_m_train = d_m + nqa;
+    m->last_vis_edge = d_vedge;
+    m->last_matches = nm;
+    m->last_edges = n_edges;
     if (visible_edges) std::memcpy(visible_edges, h_vedge, (size_t)nv * 4);
     if (visible_pixels) std::memcpy(visible_pixels, h_vpix, (size_t)nv * 16);
     if (m_query) std::memcpy(m_query, h_m, (size_t)nm * 4);
@@ -273,6 +283,58 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
     if (trace)
         std::fprintf(stderr, "[bfm trace] track_local_map: inputs staged %.1f us, %d kernels + copies queued %.1f us, synced %.1f us, "
                      "outputs copied %.1f us (in %zu B, out %zu B)\n", t_staged, kernels, t_queued, t_synced, cpu_us(), in_bytes, out_bytes);
+    return BFM_OK;
+}
+
+int bfm_keyframe_vote(bfm_map_t m, const int32_t *edge_kf, int32_t n_edges, const int32_t *inliers, int32_t n_inliers,
+                      int32_t top, int32_t *kf_ids, int32_t *kf_counts, int32_t *n_kfs) {
+    if (!m) return BFM_ERR_INVALID;
+    bfm_handle_t h = m->h;
+    h->err.clear();
+    if (!n_kfs || top < 0 || n_inliers < 0 || (n_inliers > 0 && (!inliers || !edge_kf)) || (top > 0 && (!kf_ids || !kf_counts)))
+        return fail(h, BFM_ERR_INVALID, "NULL argument or negative size");
+    *n_kfs = 0;
+    if (m->last_matches < 0) return fail(h, BFM_ERR_INVALID, "bfm_keyframe_vote follows bfm_track_local_map on the same map (no call in between)");
+    if (n_edges != m->last_edges) return fail(h, BFM_ERR_INVALID, "edge_kf must have one entry per edge of the tracking call");
+    if (n_inliers > VOTE_MAX) return fail(h, BFM_ERR_UNSUPPORTED, "more than 4096 inliers");
+    if (n_inliers == 0 || top == 0) return BFM_OK;
+    top = std::min(top, n_inliers);
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    // inputs behind the tracking call's scratch (which holds the match list): one H2D copy, one kernel, one D2H copy
+    Carver in(nullptr);
+    in.take<int32_t>(n_edges);
+    in.take<int32_t>(n_inliers);
+    const size_t in_bytes = in.off, out_bytes = align256((size_t)(1 + 2 * top) * 4);
+    DevBuf &vb = h->lower;   // (free on this path: the tracking call is k <= 2)
+    int rc = ensure(h, vb, in_bytes + out_bytes);
+    if (rc) return rc;
+    rc = ensure_pinned(h, &m->h_in, &m->h_in_cap, in_bytes + out_bytes);
+    if (rc) return rc;
+    Carver hi(m->h_in), di(vb.p);
+    int32_t *h_kf = hi.take<int32_t>(n_edges), *d_kf = di.take<int32_t>(n_edges);
+    int32_t *h_inl = hi.take<int32_t>(n_inliers), *d_inl = di.take<int32_t>(n_inliers);
+    std::memcpy(h_kf, edge_kf, (size_t)n_edges * 4);
+    std::memcpy(h_inl, inliers, (size_t)n_inliers * 4);
+    int32_t *d_out = reinterpret_cast<int32_t *>(static_cast<char *>(vb.p) + in_bytes);
+    int32_t *h_out = reinterpret_cast<int32_t *>(static_cast<char *>(m->h_in) + in_bytes);
+    CU_TRY(h, cudaMemcpyAsync(vb.p, m->h_in, in_bytes, cudaMemcpyHostToDevice, st));
+    static bool opted_in = false;   // 48 KB of sort keys + 16 KB of run records
+    if (!opted_in) {
+        CU_TRY(h, cudaFuncSetAttribute(lm_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VOTE_SMEM));
+        opted_in = true;
+    }
+    lm_vote_kernel<<<1, VOTE_NT, VOTE_SMEM, st>>>(m->last_m_train, m->last_vis_edge, d_kf, d_inl, n_inliers, m->last_matches, top, d_out);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaMemcpyAsync(h_out, d_out, (size_t)(1 + 2 * top) * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    h->launches += 1;
+    h->info = bfm_launch_info_t{};
+    h->info.kernels_launched = 1;
+    const int n = h_out[0];
+    *n_kfs = n;
+    std::memcpy(kf_ids, h_out + 1, (size_t)n * 4);
+    std::memcpy(kf_counts, h_out + 1 + top, (size_t)n * 4);
     return BFM_OK;
 }
 

@@ -168,6 +168,25 @@ class MapStore:
         return TrackResult(vis_e[:v], vis_p[:v] if want_pixels else None, mq[:m], mt[:m], md[:m].astype(np.float32), me[:m], mp3[:m], mkp[:m])
 
 
+    def vote(self, edge_kf, inliers, top: int = 100):
+        """``Counter(ids_matching_kfs[inds[inliers]]).most_common(top)`` (reference ``slam/tracking.py:154``) over the
+        match list of the last :meth:`track` call, which is still on the device: ``edge_kf[e]`` = id of the keyframe
+        of edge ``e`` (one per edge passed to ``track``), ``inliers`` = positions in the returned match list that the
+        pose optimisation kept.  Returns ``[(keyframe id, count), ...]``, most frequent first, ties in order of first
+        appearance - the order ``Counter.most_common`` yields.  Call it before the next ``track`` / ``update``."""
+        edge_kf = np.ascontiguousarray(edge_kf, np.int32).ravel()
+        inl = np.ascontiguousarray(inliers, np.int32).ravel()
+        top = int(top)
+        ids = np.empty(max(top, 1), np.int32)
+        cnt = np.empty(max(top, 1), np.int32)
+        n = ctypes.c_int32(0)
+        with self.engine._lock:
+            rc = self._lib.bfm_keyframe_vote(self._m, edge_kf.ctypes.data, edge_kf.shape[0], inl.ctypes.data, inl.shape[0], top,
+                                             ids.ctypes.data, cnt.ctypes.data, ctypes.byref(n))
+            _ffi.check(self.engine._h, rc)
+        return list(zip(ids[:n.value].tolist(), cnt[:n.value].tolist()))
+
+
 def select_representative(obs, counts, engine: Optional[Engine] = None, device: int = 0) -> np.ndarray:
     """Batched ``MapPoint.add_observation`` descriptor choice (reference ``slam/nodes.py:146-153``):
     ``obs`` uint8[P, max_obs, 32] (each point's stored observations, first ``counts[p]`` rows valid),

@@ -222,6 +222,17 @@ int bfm_track_local_map(bfm_map_t m, const bfm_track_params_t *tp, const int32_t
                         int32_t *m_dist, int32_t *m_edge, double *m_pts3d, double *m_kp, int32_t *n_visible,
                         int32_t *n_matches);
 
+/* Keyframe vote, reference slam/tracking.py:154:
+ *     Counter(ids_matching_kfs[inds[inliers]]).most_common(top)
+ * over the match list of the LAST bfm_track_local_map call on this map (still on the device; no other call on the map
+ * in between).  edge_kf[e] = id of the keyframe of edge e (the caller's table behind ids_matching_kfs, :108, one
+ * entry per edge of the tracking call); inliers[i] = positions in that call's match list which the pose optimisation
+ * kept (CamOnlyBA's inlier set, :128-139; positions outside the list are ignored).  kf_ids / kf_counts [top]: the
+ * keyframes most frequent first, ties in order of first appearance among the inliers, exactly as Counter.most_common
+ * orders them; *n_kfs = how many were written.  At most 4096 inliers (a frame has 2000 features).  Host pointers. */
+int bfm_keyframe_vote(bfm_map_t m, const int32_t *edge_kf, int32_t n_edges, const int32_t *inliers, int32_t n_inliers,
+                      int32_t top, int32_t *kf_ids, int32_t *kf_counts, int32_t *n_kfs);
+
 /* ---- representative descriptor of map points --------------------------------
  * reference slam/nodes.py:146-153 (MapPoint.add_observation), batched over the map points a new keyframe
  * touches (slam/covisibility_graph.py:124-134): obs uint8[n_points][max_obs][32] holds each point's stored

@@ -113,3 +113,13 @@ def track_local_map(store_desc, store_pt3d, store_normal, edges, frame_des, fram
                                max_distance=max_distance, strict=strict)
     return {"visible_edges": vis, "visible_pixels": vpix, "inds_frame": mq, "inds": mt, "distance": md,
             "edges": vis[mt], "pts3d": pts3d[mt], "kp": kp[mq]}
+
+
+def keyframe_vote(edge_kf, visible_edges, inds, inliers, top=100):
+    """reference slam/tracking.py:142-154: ids_matching_kfs is the keyframe id of every VISIBLE edge (appended at :108
+    for the edges that pass :103-104), and the vote is Counter(ids_matching_kfs[inds[inliers]]).most_common(top)."""
+    from collections import Counter
+    ids_matching_kfs = np.asarray(edge_kf)[np.asarray(visible_edges)]
+    inds = np.asarray(inds)
+    inliers = np.asarray(inliers, dtype=np.int64).flatten()
+    return [(int(k), int(c)) for k, c in Counter(ids_matching_kfs[inds[inliers]].tolist()).most_common(top)]

@@ -160,3 +160,31 @@ def test_select_representative_matches_reference_loop(max_obs):
     assert (got[counts == 0] == -1).all()
     full = np.full(777, max_obs, np.int32)
     assert np.array_equal(bb.select_representative(obs, full), ro.select_batch(obs, full))
+
+
+@pytest.mark.gpu
+def test_keyframe_vote_matches_counter_most_common():
+    """SURVEY 8(f) row 3, reference slam/tracking.py:154: the vote for the next reference keyframe over the inliers of
+    the pose optimisation - ids, counts AND the order Counter.most_common yields (count, then first appearance)."""
+    eng = bb.Engine(0)
+    sc = synth.local_map_scene(4000, 6000, 1500, seed=21)
+    store = bb.MapStore(4000, engine=eng)
+    store.update(np.arange(4000), sc["desc"], sc["pt3d"], sc["normal"])
+    r = store.track(sc["des"], sc["kp"], sc["R"], sc["t"], sc["see_vector"], sc["edges"])
+    assert len(r.inds) > 50
+    rng = np.random.default_rng(5)
+    ne = len(sc["edges"])
+    for trial, n_kf in enumerate((1, 3, 17, 400)):
+        # keyframe ids as boslam makes them (a counter), negative and large ones too; edges grouped by keyframe or not
+        ids = rng.choice(np.concatenate([np.arange(-3, 50), [2 ** 31 - 1, -2 ** 31]]), n_kf, replace=n_kf > 50)
+        edge_kf = np.sort(rng.integers(0, n_kf, ne)) if trial % 2 == 0 else rng.integers(0, n_kf, ne)
+        edge_kf = ids[edge_kf].astype(np.int32)
+        for inliers in (np.arange(len(r.inds)), rng.permutation(len(r.inds))[:len(r.inds) // 2], np.zeros(0, np.int64), np.array([0, 0, 1, 0])):
+            for top in (100, 2, 1):
+                want = lmo.keyframe_vote(edge_kf, r.visible_edges, r.inds, inliers, top)
+                assert store.vote(edge_kf, inliers, top) == want, (n_kf, len(inliers), top)
+    # misuse: the vote reads the match list of the last track call on the device
+    store.update(np.arange(2), sc["desc"][:2])
+    with pytest.raises(bb.BfmError):
+        store.vote(np.zeros(ne, np.int32), [0])
+    eng.close()

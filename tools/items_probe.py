@@ -7,19 +7,12 @@ import boslam_b200 as bb
 from boslam_b200 import synth
 
 eng = bb.Engine(0)
-cases = [("batch 256 x 2000^2 k2", [2000] * 256, [2000] * 256, dict(k=2, ratio=0.8)),
-         ("batch 128 x 2000^2 k2", [2000] * 128, [2000] * 128, dict(k=2, ratio=0.8)),
+cases = [("batch 32 x 2000^2 k2", [2000] * 32, [2000] * 32, dict(k=2, ratio=0.8)),
          ("batch 64 x 2000^2 k2", [2000] * 64, [2000] * 64, dict(k=2, ratio=0.8)),
-         ("batch 32 x 2000^2 k2", [2000] * 32, [2000] * 32, dict(k=2, ratio=0.8)),
-         ("batch 20 x 2000^2 k2", [2000] * 20, [2000] * 20, dict(k=2, ratio=0.8)),
          ("batch 20 x 2000^2 cross", [2000] * 20, [2000] * 20, dict(cross_check=True, max_distance=30)),
-         ("single 1000^2 cross", [1000], [1000], dict(cross_check=True, max_distance=30)),
          ("single 2000 x 20000 k2", [2000], [20000], dict(k=2, ratio=0.8)),
-         ("single 2000 x 20000 cross", [2000], [20000], dict(cross_check=True, max_distance=30)),
-         ("single 4096^2 k2", [4096], [4096], dict(k=2, ratio=0.8)),
-         ("single 2048^2 k2", [2048], [2048], dict(k=2, ratio=0.8))]
-knobsets = [dict(persistent=1), dict(persistent=2), dict(persistent=2, taper=1), dict(persistent=2, queries_per_thread=4), dict(persistent=2, queries_per_thread=2),
-            dict(persistent=2, queries_per_thread=1), dict(persistent=2, waves=1), dict(persistent=2, waves=2), dict(persistent=2, waves=4)]
+         ("single 4096^2 k2", [4096], [4096], dict(k=2, ratio=0.8))]
+knobsets = [dict(persistent=1), dict(persistent=2)] + [dict(persistent=2, segment_rows=s, queries_per_thread=r) for r in (2, 4) for s in (16, 24, 32, 48, 64, 96)]
 for name, qs, ts, kw in cases:
     q = torch.from_numpy(synth.uniform(sum(qs), 7)).cuda()
     t = torch.from_numpy(synth.uniform(sum(ts), 8)).cuda()
