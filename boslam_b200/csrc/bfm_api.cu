@@ -37,7 +37,7 @@ constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
 // length - 256-pair batch 1046 -> 1026 us (980 -> 998 G pairs/s), pinned host path 1120 -> 1104 us
 // (tools/taper_probe.py, profiles/r01f_taper_probe.log)
 constexpr int GSS_MAX_ROWS = 512;
-constexpr long long PERSISTENT_MAX_PAIRS = 300ll * 1000 * 1000;   // launches above this (~0.3 ms) take the static form
+constexpr long long PERSISTENT_MAX_PAIRS = 160ll * 1000 * 1000;   // launches above this (~0.15 ms) take the static form
 constexpr int TAPER_AUTO = 4;
 constexpr int TAPER_PCT_AUTO = 10;
 constexpr int N_TABLE_SLOTS = 4;
@@ -209,6 +209,14 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
         // that remain to whoever is done first; 2000 x 20000: 57.7 -> 56.6 us, 4096^2: 33.2 -> 31.0 us)
         const long long target = (long long)slots * (h->waves > 0 ? h->waves : 1);
         L = (int)std::max<long long>(MIN_SEG_ROWS, (steps + target - 1) / target);
+        if (h->waves == 0) {
+            // never a few items more than CTAs (8192 x 4096: 1216 items on 1184 CTAs took 71 us, the transposed problem
+            // with exactly 1184 items 51 us): every query block gets floor(slots / blocks) equal train ranges
+            const bfm_problem_t &pr = problems[0];
+            const long long nqb = std::max(1, (pr.q_count + bq - 1) / bq);
+            const long long nsp = std::max<long long>(1, slots / nqb);
+            L = (int)std::max<long long>(L, (pr.t_count + nsp - 1) / nsp);
+        }
     } else {
         // All CTAs of a launch cost about the same, so a grid of n CTAs over `slots` resident ones runs
         // about ceil(n / slots) waves; avoid a nearly empty last wave.  (Measured effect on the 256-pair
@@ -491,6 +499,14 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     long long total_pairs = 0;
     for (int p = 0; p < n_problems; ++p) total_pairs += (long long)std::max(0, problems[p].q_count) * std::max(0, problems[p].t_count);
     const bool persistent = !gate && !binned && (h->persistent == 2 || (h->persistent == 0 && total_pairs <= PERSISTENT_MAX_PAIRS));
+    // static form with a few large problems: the CTA that completes a problem would walk all its rows alone (64 tiles
+    // x ~5 us at 64k rows, fully exposed when there is nothing else to scan) - finalize tiles in a second launch instead
+    bool defer = false;
+    if (!persistent && !binned && !gate && n_problems <= 16) {
+        int max_rows = 0;
+        for (int p = 0; p < n_problems; ++p) max_rows = std::max(max_rows, problems[p].q_count);
+        defer = max_rows >= 4096;
+    }
     if (binned) r = 1;
     if (r != 1 && r != 2 && r != 4) {
         // largest register tile that still leaves >= 2 work items per CTA slot
@@ -519,7 +535,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
     // resident inputs take the persistent form (at most one wave, tile-parallel finalize inside the same launch)
     const int plan_sig[8] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots,
-                             h->taper * 1000 + h->taper_pct + 100000 * h->gss_div + 10000000 * h->gss_min, persistent ? 1 : 0};
+                             h->taper * 1000 + h->taper_pct + 100000 * h->gss_div + 10000000 * h->gss_min, (persistent ? 1 : 0) + (defer ? 2 : 0)};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
                           h->plan_problems.size() == (size_t)n_problems &&
                           std::memcmp(h->plan_problems.data(), problems, sizeof(bfm_problem_t) * (size_t)n_problems) == 0;
@@ -572,6 +588,14 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         h->plan_seg_rows = seg_rows;
         h->plan_probs = h->probs_host;
         for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = h->seg_begin[p + 1] - h->seg_begin[p];
+        if (defer) {
+            // (static form, a few large problems: one finalize tile per CTA of a second launch)
+            long long n_tiles = 0;
+            for (int p = 0; p < n_problems; ++p) n_tiles += std::max(1, (std::max(0, problems[p].q_count) + FT_ROWS_TILE - 1) / FT_ROWS_TILE);
+            h->plan_ctas = (int)n_tiles;
+            plan_tiles(problems, n_problems, h->plan_ctas, h->fin_tiles_host, h->cta_tiles_host);
+            for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = 0;   // the tiles do not wait: the scan has completed
+        }
         if (persistent) {
             long long n_tiles = 0;
             for (int p = 0; p < n_problems; ++p) n_tiles += std::max(1, (std::max(0, problems[p].q_count) + FT_ROWS_TILE - 1) / FT_ROWS_TILE);
@@ -582,7 +606,8 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     seg_rows = h->plan_seg_rows;
     const size_t n_segs = h->segs_host.size();
-    const size_t n_ctas_p = persistent ? h->cta_tiles_host.size() : 0, n_tiles_p = persistent ? h->fin_tiles_host.size() : 0;
+    const bool tiles = persistent || defer;
+    const size_t n_ctas_p = tiles ? h->cta_tiles_host.size() : 0, n_tiles_p = tiles ? h->fin_tiles_host.size() : 0;
 
     // -- workspace: [row state u64 | column keys u32 | done counters u32], all-ones when idle.  It is
     //    self-cleaning (the finalizing CTA restores every slot it read), so a memset is only queued
@@ -598,7 +623,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     uint32_t *colkeys = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes);
     uint32_t *done = reinterpret_cast<uint32_t *>(static_cast<char *>(h->state.p) + state_bytes + col_bytes);
     uint32_t *fin_done = done + n_problems;
-    if (persistent) {
+    if (tiles) {
         const unsigned finc_gen = h->finc.generation;
         rc = ensure(h, h->finc, n_tiles_p * 4);
         if (rc) return rc;
@@ -635,7 +660,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         }
         std::memcpy(h->h_tables[slot], h->plan_probs.data(), prob_bytes);
         std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes, h->segs_host.data(), seg_bytes);
-        if (persistent) {
+        if (tiles) {
             std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes + seg_bytes, h->cta_tiles_host.data(), n_ctas_p * sizeof(int2));
             std::memcpy(static_cast<char *>(h->h_tables[slot]) + prob_bytes + seg_bytes + work_bytes, h->fin_tiles_host.data(),
                         n_tiles_p * sizeof(bfm::FinTile));
@@ -666,7 +691,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     sp.rowstate = rowstate;
     sp.colkeys = colkeys;
     sp.done = done;
-    if (persistent) {
+    if (tiles) {
         sp.cta_tiles = reinterpret_cast<const int2 *>(static_cast<char *>(h->tables.p) + prob_bytes + seg_bytes);
         sp.n_items = (int32_t)n_segs;
         sp.n_ctas = (int32_t)n_ctas_p;
@@ -774,15 +799,20 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         sp.trace = pass == 0 ? h->trace : nullptr;
         sp.trace_cap = h->trace_cap;
         sp.trace_base = 0;
+        if (tiles) sp.fin_epoch = ++h->fin_epoch;
         if (persistent) {
-            sp.fin_epoch = ++h->fin_epoch;
             sp.queue = h->d_queue + 32 * h->queue_phase;          // (separate 128-byte lines)
             sp.queue_other = h->d_queue + 32 * (h->queue_phase ^ 1);
             h->queue_phase ^= 1;
         }
+        sp.defer_finalize = defer ? 1 : 0;
         const unsigned grid = persistent ? (unsigned)n_ctas_p : (unsigned)(n_segs + (pass == 0 ? n_feed : 0));
         fn<<<grid, NT, 0, st>>>(sp);
         CU_TRY(h, cudaGetLastError());
+        if (defer) {
+            bfm::bfm_tiles_kernel<<<(unsigned)n_tiles_p, NT, 0, st>>>(sp);
+            CU_TRY(h, cudaGetLastError());
+        }
     }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[1], st));
     h->state_clean = true;  // every slot touched is restored by the CTA that finalizes its problem
@@ -790,8 +820,8 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     h->last_stream = st;
     h->last_pending = true;
 
-    h->launches += binned ? 3 : passes;
-    h->info.kernels_launched = binned ? 3 : passes;
+    h->launches += binned ? 3 : passes * (defer ? 2 : 1);
+    h->info.kernels_launched = binned ? 3 : passes * (defer ? 2 : 1);
     h->info.scan_grid = binned ? bin_grid : (persistent ? (int32_t)n_ctas_p : (int32_t)n_segs);
     h->info.scan_block = NT;
     h->info.queries_per_thread = r;

@@ -131,6 +131,7 @@ struct ScanParams {
     const uint32_t *lower;           // [out rows] or NULL (first pass)
     uint32_t *lower_out;             // [out rows] or NULL: finalize stores the row's second key of this pass
     int32_t knn_col0, knn_cols;      // this pass fills columns [knn_col0, knn_col0 + knn_cols) of the knn table
+    int32_t defer_finalize;          // static form, 1: the scan only reduces; bfm_tiles_kernel finalizes tile by tile
     // ---- finalize (run by the CTA that completes a problem's last segment) ----------------------
     int32_t k;             // columns (row stride) of the knn table
     int32_t cross_check;
@@ -1055,6 +1056,7 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_static_kernel(
 
     // -- problem completion: the CTA whose segment is the last of its problem finalizes it -------------
     // (threadfence + counter: every CTA's state updates are visible before its count is)
+    if (p.defer_finalize) return;   // one very large problem: finalized by the tile-parallel kernels below
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -1425,6 +1427,17 @@ __global__ void __launch_bounds__(NT, MASK == 0 ? 8 : 6) bfm_scan_persistent_ker
         }
     }
 }
+
+#ifndef BFM_SCAN_INST_ONLY   // defined once, in bfm_api.cu
+// Static form with a few large problems (a brute-force sweep point): a second launch finalizes them tile by tile, one
+// tile per CTA, instead of one CTA walking 65536 rows (64 tiles x ~5 us).  The scan has completed (stream order), so
+// the tiles' wait on the done counter is satisfied at once (the table says 0 work items).
+__global__ void __launch_bounds__(128) bfm_tiles_kernel(const __grid_constant__ ScanParams p) {
+    __shared__ int s_cnt[FIN_RPT][4];
+    __shared__ int s_flag;
+    finalize_tile<128>(p, p.fin_tiles + blockIdx.x, s_cnt, &s_flag);
+}
+#endif
 
 typedef void (*ScanFn)(const ScanParams);
 // defined in bfm_scan_inst.cu (compiled once per register tile R and mode: 0 k = 1, 1 cross-check, 2 k = 2);

@@ -1,6 +1,7 @@
 // bfm_scan_inst.cu - instantiates the matching kernel (bfm_kernels.cuh) for ONE register tile and mode.
 // Compiled nine times (INST_R in {1, 2, 4} x INST_MODE in {0: k = 1, 1: cross-check, 2: k = 2}) so the variants
 // build in parallel; bfm_api.cu picks one through bfm_pick_scan_r<R>_m<MODE>().
+#define BFM_SCAN_INST_ONLY
 #include "bfm_kernels.cuh"
 
 #ifndef INST_R

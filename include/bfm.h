@@ -270,7 +270,7 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
  *       "taper_pct" {0=auto (10): percent of the batch's work, at its end, that is cut finer},
  *       "persistent" {0=auto, 1=off, 2=always}: resident inputs can take the persistent form of the kernel - at most
  *                     one wave of CTAs drawing work items from a ticket counter, then finalizing the problems tile by
- *                     tile inside the same launch; auto uses it for launches of up to 0.3 G pairs (a tracking frame, a
+ *                     tile inside the same launch; auto uses it for launches of up to 0.16 G pairs (a tracking frame, a
  *                     local-mapping batch, a rank's share of a sharded loop-closing batch) and the static form (one
  *                     work item per CTA, the CTA that completes a problem finalizes it) for longer ones and on the
  *                     gated host path,
