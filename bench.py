@@ -674,7 +674,7 @@ def main():
         pass
     popc_issued = 4 if info["popc_mode"] in (4, 40) else (5 if info["popc_mode"] in (5, 50) else info["popc_mode"])
     roofline = {
-        "bound": "int_popc", "kernel": "bfm_scan_kernel", "achieved": achieved_popc / 1e9, "peak": popc["ops_per_s"] / 1e9,
+        "bound": "int_popc", "kernel": "bfm_scan_static_kernel" if info["scan_grid"] == info["segments"] else "bfm_scan_persistent_kernel", "achieved": achieved_popc / 1e9, "peak": popc["ops_per_s"] / 1e9,
         "unit": "GPOPC/s", "frac": achieved_popc / popc["ops_per_s"],
         "traffic": from_file.get("dram_bytes_per_launch") if world == 1 else None,
         "traffic_source": from_file.get("source") if world == 1 else None,
@@ -835,8 +835,10 @@ def main():
                                 if gather_mode == "nccl" else f"DIAGNOSTIC: pair list split x{world} with NO exchange")
                 if world > 1 else "single GPU"},
         "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": int(launches), "roofline": roofline,
-        "launch": {k: info[k] for k in ("scan_grid", "scan_block", "queries_per_thread", "popc_mode",
-                                        "train_rows_per_segment")},
+        "launch": dict({k: info[k] for k in ("scan_grid", "scan_block", "queries_per_thread", "popc_mode",
+                                             "train_rows_per_segment", "segments", "kernels_launched")},
+                       form="static: one work item per CTA" if info["scan_grid"] == info["segments"] else
+                            "persistent: one wave of CTAs drawing work items from a ticket counter"),
         "frames_per_s": N_PAIRS * args.steps / (ms * 1e-3),
         "verify": verify,
     }

@@ -85,6 +85,7 @@ struct bfm_handle_s {
     uint32_t fin_epoch = 0;
     int persistent = 0;  // tuning: 0 auto (resident inputs take the persistent form), 1 off
     int gss_div = 0, gss_min = 0;   // tuning: guided item lengths
+    int ctas_per_sm = 0;            // tuning: resident CTAs per SM of the persistent form (0 = as many as fit)
     std::vector<int2> cta_tiles_host;
     std::vector<bfm::FinTile> fin_tiles_host;
     int plan_ctas = 0;        // grid of the persistent form
@@ -530,6 +531,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         int rc = occupancy(h, r, mode, mask, pm, &occ);
         if (rc) return rc;
         slots = occ * h->sm_count;
+        if (persistent && h->ctas_per_sm > 0) slots = std::min(occ, h->ctas_per_sm) * h->sm_count;
     }
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
@@ -1067,6 +1069,9 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "taper_pct") {
         if (value < 0 || value > 90) return fail(h, BFM_ERR_INVALID, "taper_pct must be 0 (auto) .. 90");
         h->taper_pct = value;
+    } else if (k == "ctas_per_sm") {
+        if (value < 0 || value > 32) return fail(h, BFM_ERR_INVALID, "ctas_per_sm must be 0 (auto) .. 32");
+        h->ctas_per_sm = value;
     } else if (k == "gss_div" || k == "gss_min") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, k + " must be >= 0");
         (k == "gss_div" ? h->gss_div : h->gss_min) = value;

@@ -12,14 +12,14 @@ cases = [("batch 32 x 2000^2 k2", [2000] * 32, [2000] * 32, dict(k=2, ratio=0.8)
          ("batch 20 x 2000^2 cross", [2000] * 20, [2000] * 20, dict(cross_check=True, max_distance=30)),
          ("single 2000 x 20000 k2", [2000], [20000], dict(k=2, ratio=0.8)),
          ("single 4096^2 k2", [4096], [4096], dict(k=2, ratio=0.8))]
-knobsets = [dict(persistent=1), dict(persistent=2)] + [dict(persistent=2, segment_rows=s, queries_per_thread=r) for r in (2, 4) for s in (16, 24, 32, 48, 64, 96)]
+knobsets = [dict(persistent=2)] + [dict(persistent=2, ctas_per_sm=c, queries_per_thread=r) for r in (2, 4) for c in (3, 4, 5, 6, 7)]
 for name, qs, ts, kw in cases:
     q = torch.from_numpy(synth.uniform(sum(qs), 7)).cuda()
     t = torch.from_numpy(synth.uniform(sum(ts), 8)).cuda()
     tab = bb.make_problems(qs, ts)
     line = f"{name:26s}"
     for knobs in knobsets:
-        eng.set_tuning(segment_rows=0, persistent=0, queries_per_thread=0, taper=0, waves=0)
+        eng.set_tuning(segment_rows=0, persistent=0, queries_per_thread=0, taper=0, waves=0, ctas_per_sm=0)
         eng.set_tuning(**knobs)
         out = eng.match_batched_device(q, t, tab, **kw)
         for _ in range(3):
