@@ -152,6 +152,8 @@ struct ScanParams {
         int32_t *m_query, *m_train, *m_dist;         // [out rows]
         int32_t *m_count;                            // [problems]
     } dest[MAX_DEST];
+    // (new fields go to the END of this struct: even the offsets of the fields above change the register assignment
+    // ptxas gives the static kernel's inner loop, tests/test_hotloop_fingerprint.py)
 };
 
 // ---- PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------------------
