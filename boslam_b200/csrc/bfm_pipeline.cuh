@@ -131,8 +131,8 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         G = std::min(12, n_problems);
     }
     // (one large problem - a frame against the local map, 0.7 MB - keeps the plain copy: the gated form measured
-    // slower for it, 197 vs 141 us end to end, because its work items are query-block major and every block needs
-    // the whole train set; profiles/r02_small_calls.md)
+    // slower for it, 197 us with query-block-major work items and 212 us with train-range-major items and 2048-row feed
+    // rounds against 137 us: seventeen latency-bound feed rounds cost more than the 25 us of DMA they would hide)
     const bool trace = std::getenv("BFM_TRACE") != nullptr;
     const auto cpu0 = std::chrono::steady_clock::now();
     auto cpu_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - cpu0).count(); };
