@@ -46,7 +46,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_PAIRS, N_DESC, RATIO = 256, 2000, 0.8
+N_PAIRS, N_DESC, RATIO = int(os.environ.get("BFM_BENCH_PAIRS", "256")), 2000, 0.8   # (BFM_BENCH_PAIRS: diagnostics only; the bench line is the 256-pair list)
 
 
 def _env_int(name, default):
@@ -716,7 +716,7 @@ def main():
     res = None
     for i in range(args.warmup if e2e_steps else 0):
         res = host_step(i)
-    if fe is not None:
+    if fe is not None and e2e_steps:
         fe.wait()
     barrier()
     torch.cuda.synchronize()
