@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "bfm_abi_version", "bfm_create", "bfm_destroy", "bfm_last_error", "bfm_match_batched", "bfm_knn",
     "bfm_match", "bfm_match_batched_multi", "bfm_match_batched_host_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
     "bfm_device_info", "bfm_host_alloc", "bfm_host_free", "bfm_map_create", "bfm_map_destroy", "bfm_map_update",
-    "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview", "bfm_debug_timeline", "bfm_plan_preview_tiles", "bfm_keyframe_vote",
+    "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview", "bfm_debug_timeline", "bfm_plan_preview_tiles", "bfm_keyframe_vote", "bfm_synchronize",
 )
 
 
@@ -103,6 +103,7 @@ def lib():
                                           vp, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
         L.bfm_select_representative.argtypes = [vp, vp, vp, i32, i32, vp]
         L.bfm_keyframe_vote.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+        L.bfm_synchronize.argtypes = [vp]
         L.bfm_knn.argtypes = [vp, ctypes.c_int, vp, i32, vp, i32, ctypes.POINTER(Options), vp, vp, vp]
         L.bfm_match.argtypes = [vp, ctypes.c_int, vp, i32, vp, i32, ctypes.POINTER(Options), vp, vp, vp, vp, vp]
         L.bfm_get_launch_info.argtypes = [vp, ctypes.POINTER(LaunchInfo)]

@@ -16,6 +16,9 @@ from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 
+import ctypes
+
+from . import _ffi
 from .engine import BatchResult, Engine, HostBatchBuffers, _check_desc_np
 
 
@@ -34,6 +37,8 @@ class KeyframeBank:
         self._count = np.full(1024, -1, np.int32)
         self._dead = 0                                 # rows of erased keyframes (reclaimed by compaction)
         self._out: Optional[HostBatchBuffers] = None
+        self._bound = {}                               # bound call configurations (see match_pairs)
+        self._own_stream = ctypes.c_void_p(-1)         # BFM_STREAM_OWN: the engine's own stream
 
     def __contains__(self, kf_id) -> bool:
         return kf_id in self._where
@@ -126,6 +131,26 @@ class KeyframeBank:
         P = len(pairs)
         tab = self.problem_table(pairs)
         out_rows = int(tab[-1, 4] + tab[-1, 1]) if P else 0
+        # steady state of a loop over pair lists (loop closing, the bench): same options, same destinations, result
+        # buffers that are large enough - only the problem table is new.  Everything else is marshalled once.
+        if P and out_rows and not want_knn and not copy:
+            key = (k, ratio, cross_check, max_distance, strict, id(replicas) if replicas is not None else 0)
+            hit = self._bound.get(key)
+            ob = self._out
+            if hit is not None and ob is not None and ob.n_out >= out_rows and ob.n_problems >= P and hit[0] is ob and hit[4] is replicas:
+                _ob, opts_ref, arr, n, _rep, _opts = hit
+                eng = self.engine
+                rows = self._rows
+                with eng._lock:
+                    rc = eng._lib.bfm_match_batched_multi(eng._h, rows.data_ptr(), rows.shape[0], rows.data_ptr(), rows.shape[0],
+                                                          tab.ctypes.data_as(ctypes.POINTER(_ffi.Problem)), P, out_rows, opts_ref, arr, n,
+                                                          self._own_stream)
+                    if rc:
+                        _ffi.check(eng._h, rc)
+                    rc = eng._lib.bfm_synchronize(eng._h)
+                    if rc:
+                        _ffi.check(eng._h, rc)
+                return BatchResult(ob.m[0][:out_rows], ob.m[1][:out_rows], ob.m[2][:out_rows], ob.count[:P], tab[:, 4].copy())
         if P == 0 or out_rows == 0:
             e = np.zeros(0, np.int32)
             res = BatchResult(e, e.copy(), e.copy(), np.zeros(P, np.int32), tab[:, 4].copy())
@@ -143,6 +168,16 @@ class KeyframeBank:
                                              replicas=replicas)
             torch.cuda.current_stream(self._dev).synchronize()   # results are in pinned host memory now
         none_pass = self.engine._gate(max_distance, strict) == -2
+        if not want_knn and not copy and not none_pass:   # bind this configuration for the next call
+            opts, _ = self.engine._options(k, ratio, cross_check, max_distance, strict)
+            dlist = [dest] + list(replicas or [])
+            arr = (_ffi.Outputs * len(dlist))()
+            for d, o in zip(arr, dlist):
+                Engine._fill_outputs(d, o, False)
+            if len(self._bound) >= 8 or any(v[0] is not ob for v in self._bound.values()):
+                self._bound = {}
+            self._bound[(k, ratio, cross_check, max_distance, strict, id(replicas) if replicas is not None else 0)] = \
+                (ob, ctypes.byref(opts), arr, len(dlist), replicas, opts)
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
         counts = cp(ob.count[:P])
         if none_pass:

@@ -1089,6 +1089,14 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
 
 int64_t bfm_kernel_launch_count(bfm_handle_t h) { return h ? h->launches : 0; }
 
+int bfm_synchronize(bfm_handle_t h) {
+    if (!h) return BFM_ERR_INVALID;
+    h->err.clear();
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return BFM_OK;
+}
+
 int bfm_debug_timeline(bfm_handle_t h, uint64_t *device_buf, int32_t capacity_ctas) {
     if (!h || capacity_ctas < 0) return BFM_ERR_INVALID;
     h->trace = capacity_ctas > 0 ? reinterpret_cast<unsigned long long *>(device_buf) : nullptr;

@@ -547,6 +547,40 @@ class Engine:
                         o["count"].zero_()
         return out
 
+    def bind_device_multi(self, problems, dests, want_knn=False, k=1, ratio=None, cross_check=False, max_distance=None,
+                          strict=False):
+        """Marshal a device-resident multi-destination call once (problem table, options, destination structs - raw
+        device pointers as :meth:`boslam_b200.distributed.FusedGather.destinations` builds them);
+        :meth:`run_device_multi` then takes only the two descriptor tensors."""
+        probs = np.ascontiguousarray(problems, np.int32)
+        P = probs.shape[0]
+        n_out = int((probs[:, 4] + probs[:, 1]).max()) if P else 0
+        if k > _ffi.MAX_K:
+            raise NotImplementedError(f"k > {_ffi.MAX_K} is not supported by this build")
+        opts, none_pass = self._options(k, ratio, cross_check, max_distance, strict)
+        if none_pass:
+            raise ValueError("a gate nothing can pass has no bound form: use match_batched_device")
+        arr = (_ffi.Outputs * len(dests))()
+        for d, o in zip(arr, dests):
+            self._fill_outputs(d, o, want_knn)
+        return (probs, probs.ctypes.data_as(ctypes.POINTER(_ffi.Problem)), P, n_out, opts, ctypes.byref(opts), arr, len(dests))
+
+    def run_device_multi(self, q, t, bound):
+        _probs, pp, P, n_out, _opts, opts_ref, arr, n = bound
+        if q.dtype != self._u8() or t.dtype != self._u8() or not q.is_cuda or not t.is_cuda or not q.is_contiguous() or not t.is_contiguous():
+            raise ValueError("run_device_multi needs contiguous CUDA uint8[rows, 32] tensors")
+        if P and n_out:
+            with self._lock:
+                rc = self._lib.bfm_match_batched_multi(self._h, q.data_ptr(), q.shape[0], t.data_ptr(), t.shape[0], pp, P, n_out,
+                                                       opts_ref, arr, n, self._stream())
+                if rc:
+                    _ffi.check(self._h, rc)
+
+    @staticmethod
+    def _u8():
+        import torch
+        return torch.uint8
+
     @staticmethod
     def _fill_outputs(d, o, want_knn):
         """One bfm_outputs_t from a dict of tensors (m int32[3, n], count, knn_idx, knn_dist) or of raw
@@ -675,6 +709,40 @@ class BatchPlan:
                     rc = eng._lib.bfm_match_batched(eng._h, _ffi.MEM_HOST, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
                                                     self._pp, self.P, self.n_out, self._opts_ref, None, None, m[0].ctypes.data,
                                                     m[1].ctypes.data, m[2].ctypes.data, out.count.ctypes.data, None)
+                    _ffi.check(eng._h, rc)
+        cnt = out.count[:self.P]
+        if self.none_pass:
+            cnt[:] = 0
+        return BatchResult(out.m[0], out.m[1], out.m[2], cnt, self._offsets)
+
+    def bind_replicas(self, out: HostBatchBuffers, replicas):
+        """Marshal the destinations of :meth:`run` with ``replicas`` once (the structs of a sharded step's slot never
+        change); :meth:`run_bound` is then the bare library call."""
+        if out.n_out < self.n_out or out.n_problems < self.P:
+            raise ValueError("out= buffers are too small for this batch")
+        m = out.m
+        host = _ffi.Outputs()
+        host.m_query, host.m_train, host.m_dist = m[0].ctypes.data, m[1].ctypes.data, m[2].ctypes.data
+        host.m_count = out.count.ctypes.data
+        dests = (_ffi.Outputs * len(replicas))()
+        for d, o in zip(dests, replicas):
+            Engine._fill_outputs(d, o, False)
+        return (out, host, ctypes.byref(host), dests, len(replicas))
+
+    def run_bound(self, q: np.ndarray, t: np.ndarray, bound) -> BatchResult:
+        out, _host, host_ref, dests, n = bound
+        if (q.dtype != np.uint8 or t.dtype != np.uint8 or q.strides != (DESC_BYTES, 1) or t.strides != (DESC_BYTES, 1) or
+                q.shape[0] < self.nq_min or t.shape[0] < self.nt_min):
+            raise ValueError("BatchPlan.run_bound needs C-contiguous uint8[rows, 32] arrays covering the planned rows")
+        qa, ta = _addr(q), _addr(t)
+        if (qa | ta) & 15:
+            raise ValueError("descriptor arrays must be 16-byte aligned")
+        eng = self.engine
+        if self.P and self.n_out:
+            with eng._lock:
+                rc = eng._lib.bfm_match_batched_host_multi(eng._h, qa, q.shape[0], ta, t.shape[0], self._pp, self.P, self.n_out,
+                                                           self._opts_ref, host_ref, dests, n)
+                if rc:
                     _ffi.check(eng._h, rc)
         cnt = out.count[:self.P]
         if self.none_pass:

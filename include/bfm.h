@@ -276,6 +276,8 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
  *                     gated host path,
  *       "taper" = 16 with "gss_div" / "gss_min": guided item lengths (an experiment, see profiles/r02_kernel_forms.md) */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
+/* Wait until everything queued on the handle's own stream (BFM_STREAM_OWN calls) has completed. */
+int bfm_synchronize(bfm_handle_t h);
 /* total kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t bfm_kernel_launch_count(bfm_handle_t h);
 /* Debug timeline of the matching kernel (tools/timeline_probe.py): with a device buffer uint64[capacity_ctas][8],

@@ -269,5 +269,10 @@ def test_same_shapes_other_rows_reuse_the_plan(eng, persistent):
                 res = bank.match_pairs(step, **kw)
                 for p, (a, b) in enumerate(step):
                     _eq(res[p], orc.match(kfs[a], kfs[b], **okw), (persistent, kw, a, b))
+        # the bound form (copy=False: views of the bank's pinned buffers, arguments marshalled once): same lists
+        for step in (step1, step2, step1, step2[::-1], step1):
+            res = bank.match_pairs(step, k=2, ratio=0.9, copy=False)
+            for p, (a, b) in enumerate(step):
+                _eq(res[p], orc.match(kfs[a], kfs[b], k=2, ratio=0.9), (persistent, "bound", a, b))
     finally:
         eng.set_tuning(persistent=0)
