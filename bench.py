@@ -621,8 +621,10 @@ def main():
             raise SystemExit("fused gather verification failed: a rank's symmetric table differs from the NCCL gather of the local tables")
     # one checksum of the WHOLE gathered result of input set 0: identical for every world size (W = 1, 2, 4, 8
     # must be byte-identical)
+    # (the tables are laid out [rank][...]; the match lists [rank][3][rows] are turned into [3][all rows], the order a single
+    # GPU produces, so that the bytes - and the checksum - do not depend on how many ranks there are)
     crc = 0
-    for a in (all_ki, all_kd, all_c, all_m):
+    for a in (all_ki, all_kd, all_c, all_m.permute(1, 0, 2).contiguous()):
         crc = zlib.crc32(a.cpu().numpy().tobytes(), crc)
     verify["tables_crc32"] = int(crc)
     verify["matches_set0"] = int(all_c.sum().item())

@@ -92,6 +92,7 @@ struct bfm_handle_s {
     uint32_t *d_queue = nullptr;   // two ticket counters used by alternate launches (each launch zeroes the other one)
     int queue_phase = 0;
     DevBuf bins;     // binned window search: train rows in grid-cell order + cell table
+    int bins_problems = 0;   // problems the counters of `bins` are laid out for
     void *h_tables[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring
     size_t h_tables_cap[N_TABLE_SLOTS] = {0, 0, 0, 0};
     cudaEvent_t table_ev[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
@@ -450,6 +451,19 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             return fail(h, BFM_ERR_INVALID, "knn_idx / knn_dist must be 8-byte aligned");
     }
 
+    // projection-window search over a binned train set (bfm_window.cuh): finite radius, every problem's train set
+    // small enough for the cell tables; a batch of window problems takes it too (blockIdx.y = problem)
+    bool binned = o->mask_kind == BFM_MASK_WINDOW && (o->k + 1) / 2 == 1 && h->window_bins != 1 && !gate && n_problems <= 4096 &&
+                  std::isfinite(o->window_radius) && o->window_radius > 0.0f && (t_limit == nullptr || n_problems == 1);
+    int bin_max_q = 0, bin_max_t = 0;
+    for (int p = 0; p < n_problems && binned; ++p) {
+        bin_max_q = std::max(bin_max_q, problems[p].q_count);
+        bin_max_t = std::max(bin_max_t, problems[p].t_count);
+        if (problems[p].t_count > bfm::WB_MAX_ROWS) binned = false;
+    }
+    if (bin_max_q <= 0 || bin_max_t <= 0) binned = false;
+    const int bin_grid = binned ? (bin_max_q + bfm::WS_NT / 32 - 1) / (bfm::WS_NT / 32) : 0;
+
     // -- validate problems, lay out column keys ------------------------------------------------
     h->probs_host.resize(n_problems);
     long long col_rows = 0;
@@ -468,7 +482,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         d.n_segs = 0;                // filled from the plan below
         d.pad = 0;
         h->probs_host[p] = d;
-        if (o->cross_check) col_rows += pr.t_count;
+        if (o->cross_check || binned) col_rows += pr.t_count;   // (binned: also the row offset of the problem's binned rows)
     }
     if (col_rows >= (1ll << 31)) return fail(h, BFM_ERR_INVALID, "batch too large for cross-check");
 
@@ -479,11 +493,6 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     const int pm = (h->popc_mode && passes == 1) ? h->popc_mode : 40;  // measured best for every mode: profiles/sweep_r01.json
     int r = passes > 1 ? 1 : h->qpt;
     int slots = 0, seg_rows = 0;
-    // projection-window search over a binned train set (bfm_window.cuh): single problem, finite radius
-    const bool binned = mask == BFM_MASK_WINDOW && n_problems == 1 && passes == 1 && h->window_bins != 1 && !gate &&
-                        std::isfinite(o->window_radius) && o->window_radius > 0.0f && problems[0].q_count > 0 &&
-                        problems[0].t_count > 0 && problems[0].t_count <= bfm::WB_MAX_ROWS;
-    const int bin_grid = binned ? (problems[0].q_count + bfm::WS_NT / 32 - 1) / (bfm::WS_NT / 32) : 0;
     // a device-side train count: plan the work items for the rows the caller expects to exist (the kernel re-cuts
     // whatever does exist evenly over them, so the guess only affects efficiency, never the result)
     bfm_problem_t hinted;
@@ -583,7 +592,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         h->seg_begin.assign(2, 0);
         h->plan_seg_rows = 0;
         h->plan_probs = h->probs_host;
-        h->plan_probs[0].n_segs = bin_grid;   // the search kernel's CTAs play the role of segments
+        for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = bin_grid;   // the search kernel's CTAs play the role of segments
     } else if (!plan_hit) {
         // (a device-side train count re-cuts the rows that exist over equal items per query block: no guided lengths)
         plan_segments(h, plan_problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows, persistent);
@@ -755,38 +764,38 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     }
     if (h->timing) CU_TRY(h, cudaEventRecord(h->ev[0], st));
     if (binned) {
-        const bfm_problem_t &pr = problems[0];
-        const size_t T = (size_t)pr.t_count;
-        // layout: [counters + ticket | cell offsets | rows in cell order: desc, xy, orig | cell, rank per row]
-        const size_t o_cnt = 0, o_cs = align256((bfm::WB_CELLS + 1) * 4), o_desc = align256(o_cs + (bfm::WB_CELLS + 1) * 4),
+        const size_t T = (size_t)col_rows, P = (size_t)n_problems;
+        // layout: [counters per problem + tickets | cell offsets per problem | rows in cell order: desc, xy, orig | cell, rank per row]
+        const size_t o_cnt = 0, o_cs = align256((P * bfm::WB_CELLS + P) * 4), o_desc = align256(o_cs + P * (bfm::WB_CELLS + 1) * 4),
                      o_xy = align256(o_desc + T * 32), o_orig = align256(o_xy + T * 8), o_cell = align256(o_orig + T * 4),
                      o_rank = align256(o_cell + T * 4), total = align256(o_rank + T * 4);
         const unsigned bins_gen = h->bins.generation;
         rc = ensure(h, h->bins, total);
         if (rc) return rc;
         char *bb = static_cast<char *>(h->bins.p);
-        // the counters (and the ticket behind them) are self-cleaning: zeroed once per allocation
-        if (h->bins.generation != bins_gen) CU_TRY(h, cudaMemsetAsync(h->bins.p, 0, o_cs, st));
+        // the counters (and the tickets behind them) are self-cleaning: zeroed once per allocation and when the number of
+        // problems - the layout of the block - changes
+        if (h->bins.generation != bins_gen || h->bins_problems != n_problems) CU_TRY(h, cudaMemsetAsync(h->bins.p, 0, o_cs, st));
+        h->bins_problems = n_problems;
         bfm::BinView bv{reinterpret_cast<uint4 *>(bb + o_desc), reinterpret_cast<float2 *>(bb + o_xy),
                         reinterpret_cast<int32_t *>(bb + o_orig), reinterpret_cast<int32_t *>(bb + o_cs)};
         int32_t *d_cnt = reinterpret_cast<int32_t *>(bb + o_cnt);
-        uint32_t *d_ticket = reinterpret_cast<uint32_t *>(d_cnt + bfm::WB_CELLS);
+        uint32_t *d_ticket = reinterpret_cast<uint32_t *>(d_cnt + P * bfm::WB_CELLS);
         int32_t *d_cell = reinterpret_cast<int32_t *>(bb + o_cell), *d_rank = reinterpret_cast<int32_t *>(bb + o_rank);
         const double cell = 2.0 * (double)o->window_radius * (1.0 + 1e-6) + 1e-30;
         const double inv_cell = 1.0 / cell;
-        const int bgrid = (pr.t_count + 255) / 256;
-        bfm::wb_count_kernel<<<bgrid, 256, 0, st>>>(sp.t_xy + pr.t_begin, pr.t_count, t_limit, inv_cell, d_cnt, d_ticket, d_cell, d_rank, bv.cell_start);
+        const dim3 bgrid((unsigned)((bin_max_t + 255) / 256), (unsigned)n_problems);
+        bfm::wb_count_kernel<<<bgrid, 256, 0, st>>>(sp.t_xy, d_probs, t_limit, inv_cell, d_cnt, d_ticket, d_cell, d_rank, bv.cell_start);
         CU_TRY(h, cudaGetLastError());
-        bfm::wb_scatter_kernel<<<bgrid, 256, 0, st>>>(sp.t + 2 * (size_t)pr.t_begin, sp.t_xy + pr.t_begin, pr.t_count, t_limit, d_cell, d_rank, bv);
+        bfm::wb_scatter_kernel<<<bgrid, 256, 0, st>>>(sp.t, sp.t_xy, d_probs, t_limit, d_cell, d_rank, bv);
         CU_TRY(h, cudaGetLastError());
         ScanParams sq = sp;
-        sq.q = sp.q + 2 * (size_t)pr.q_begin;
-        sq.q_xy = sp.q_xy + pr.q_begin;
         sq.knn_col0 = 0;
         sq.knn_cols = std::min(2, o->k);
-        if (mode == 1) bfm::wb_search_kernel<1, true><<<bin_grid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell, pr.q_count);
-        else if (mode == 2) bfm::wb_search_kernel<2, false><<<bin_grid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell, pr.q_count);
-        else bfm::wb_search_kernel<1, false><<<bin_grid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell, pr.q_count);
+        const dim3 sgrid((unsigned)bin_grid, (unsigned)n_problems);
+        if (mode == 1) bfm::wb_search_kernel<1, true><<<sgrid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell);
+        else if (mode == 2) bfm::wb_search_kernel<2, false><<<sgrid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell);
+        else bfm::wb_search_kernel<1, false><<<sgrid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell);
         CU_TRY(h, cudaGetLastError());
     }
     for (int pass = 0; pass < (binned ? 0 : passes); ++pass) {

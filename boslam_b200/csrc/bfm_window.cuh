@@ -36,12 +36,20 @@ __device__ __forceinline__ int wb_wrap(long long c) { return (int)(((c % WB_G) +
 
 // pass 1 (many CTAs): cell of every train row, rank inside its cell (the atomic's return value);
 // the last CTA to finish turns the counters into cell offsets and zeroes them for the next call.
-__global__ void __launch_bounds__(256) wb_count_kernel(const float2 *t_xy, int32_t n_rows, const int32_t *t_limit, double inv_cell,
-                                                       int32_t *cnt, uint32_t *ticket, int32_t *cell_of, int32_t *rank_of,
-                                                       int32_t *cell_start) {
+// (a batch: blockIdx.y = problem; every problem has its own counters, ticket and cell table, and its rows sit at
+// offset Problem::col0 - the sum of the train rows of the problems before it - in the binned arrays)
+__global__ void __launch_bounds__(256) wb_count_kernel(const float2 *t_xy_all, const Problem *problems, const int32_t *t_limit, double inv_cell,
+                                                       int32_t *cnt_all, uint32_t *ticket_all, int32_t *cell_of_all, int32_t *rank_of_all,
+                                                       int32_t *cell_start_all) {
     __shared__ int s_warp[32];
     __shared__ int s_last;
     const int tid = threadIdx.x;
+    const Problem pr = problems[blockIdx.y];
+    const float2 *t_xy = t_xy_all + pr.t_begin;
+    int32_t *cnt = cnt_all + (size_t)blockIdx.y * WB_CELLS, *cell_start = cell_start_all + (size_t)blockIdx.y * (WB_CELLS + 1);
+    int32_t *cell_of = cell_of_all + pr.col0, *rank_of = rank_of_all + pr.col0;
+    uint32_t *ticket = ticket_all + blockIdx.y;
+    const int n_rows = pr.t_count;
     const int n = t_limit ? max(0, min(n_rows, *t_limit)) : n_rows;
     const int i = blockIdx.x * 256 + tid;
     if (i < n) {
@@ -92,8 +100,16 @@ __global__ void __launch_bounds__(256) wb_count_kernel(const float2 *t_xy, int32
 }
 
 // pass 2 (many CTAs): rows to their place in cell order
-__global__ void __launch_bounds__(256) wb_scatter_kernel(const uint4 *t_desc, const float2 *t_xy, int32_t n_rows, const int32_t *t_limit,
-                                                         const int32_t *cell_of, const int32_t *rank_of, BinView out) {
+__global__ void __launch_bounds__(256) wb_scatter_kernel(const uint4 *t_desc_all, const float2 *t_xy_all, const Problem *problems,
+                                                         const int32_t *t_limit, const int32_t *cell_of_all, const int32_t *rank_of_all,
+                                                         BinView out_all) {
+    const Problem pr = problems[blockIdx.y];
+    const uint4 *t_desc = t_desc_all + 2 * (size_t)pr.t_begin;
+    const float2 *t_xy = t_xy_all + pr.t_begin;
+    const int32_t *cell_of = cell_of_all + pr.col0, *rank_of = rank_of_all + pr.col0;
+    BinView out{out_all.desc + 2 * (size_t)pr.col0, out_all.xy + pr.col0, out_all.orig + pr.col0,
+                out_all.cell_start + (size_t)blockIdx.y * (WB_CELLS + 1)};
+    const int n_rows = pr.t_count;
     const int n = t_limit ? max(0, min(n_rows, *t_limit)) : n_rows;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
@@ -107,16 +123,22 @@ __global__ void __launch_bounds__(256) wb_scatter_kernel(const uint4 *t_desc, co
 constexpr int WS_NT = 256;   // 8 queries per CTA, one warp each
 
 template <int K, bool CROSS>
-__global__ void __launch_bounds__(WS_NT) wb_search_kernel(const __grid_constant__ ScanParams p, const BinView bins,
-                                                          const double inv_cell, const int32_t n_query) {
+__global__ void __launch_bounds__(WS_NT) wb_search_kernel(const __grid_constant__ ScanParams p, const BinView bins_all,
+                                                          const double inv_cell) {
     __shared__ int s_cnt[FIN_RPT][WS_NT / 32];
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pi = blockIdx.y;
+    const Problem pr = p.problems[pi];
+    const BinView bins{bins_all.desc + 2 * (size_t)pr.col0, bins_all.xy + pr.col0, bins_all.orig + pr.col0,
+                       bins_all.cell_start + (size_t)pi * (WB_CELLS + 1)};
+    const int n_query = pr.q_count;
     const int qi = blockIdx.x * (WS_NT / 32) + warp;
     if (qi < n_query) {
-        const uint4 a = __ldg(p.q + 2 * (size_t)qi), b = __ldg(p.q + 2 * (size_t)qi + 1);
+        const size_t qrow = (size_t)pr.q_begin + qi;
+        const uint4 a = __ldg(p.q + 2 * qrow), b = __ldg(p.q + 2 * qrow + 1);
         const uint32_t qw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        const float2 qxy = __ldg(p.q_xy + qi);
+        const float2 qxy = __ldg(p.q_xy + qrow);
         uint32_t b1 = KEY_NONE, b2 = KEY_NONE;
         if (!(isnan(qxy.x) || isnan(qxy.y))) {
             const long long cx0 = wb_cell_coord(qxy.x - p.radius, inv_cell), cx1 = min(wb_cell_coord(qxy.x + p.radius, inv_cell), cx0 + 2);
@@ -135,7 +157,7 @@ __global__ void __launch_bounds__(WS_NT) wb_search_kernel(const __grid_constant_
                         const uint32_t key = (d << DIST_SHIFT) | orig;
                         if (K == 2) b2 = min(b2, max(b1, key));
                         b1 = min(b1, key);
-                        if (CROSS) atomicMin(p.colkeys + orig, (d << DIST_SHIFT) | (uint32_t)qi);
+                        if (CROSS) atomicMin(p.colkeys + (size_t)pr.col0 + orig, (d << DIST_SHIFT) | (uint32_t)qi);
                     }
                 }
             }
@@ -150,19 +172,19 @@ __global__ void __launch_bounds__(WS_NT) wb_search_kernel(const __grid_constant_
             b1 = m1;
             b2 = m2;
         }
-        if (lane == 0) p.rowstate[(size_t)p.problems[0].out_begin + qi] = ((unsigned long long)b1 << 32) | (K == 2 ? b2 : KEY_NONE);
+        if (lane == 0) p.rowstate[(size_t)pr.out_begin + qi] = ((unsigned long long)b1 << 32) | (K == 2 ? b2 : KEY_NONE);
     }
-    // last CTA finalizes (problem 0; its n_segs is this grid's size)
+    // the last CTA of a problem finalizes it (every problem counts gridDim.x arrivals: CTAs past its queries just arrive)
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const uint32_t old = atomicAdd(p.done, 1u);
+        const uint32_t old = atomicAdd(p.done + pi, 1u);
         s_flag = (old == (uint32_t)gridDim.x - 2u) ? 1 : 0;
-        if (s_flag) p.done[0] = 0xFFFFFFFFu;
+        if (s_flag) p.done[pi] = 0xFFFFFFFFu;
     }
     __syncthreads();
     if (s_flag) {
         __threadfence();
-        finalize_problem<WS_NT>(p, 0, s_cnt);
+        finalize_problem<WS_NT>(p, pi, s_cnt);
     }
 }

@@ -276,3 +276,43 @@ def test_same_shapes_other_rows_reuse_the_plan(eng, persistent):
                 _eq(res[p], orc.match(kfs[a], kfs[b], k=2, ratio=0.9), (persistent, "bound", a, b))
     finally:
         eng.set_tuning(persistent=0)
+
+
+def test_window_batches_take_the_binned_search(eng):
+    """A batch of projection-window problems (ragged, with an empty train set, an empty query set and a one-row problem)
+    goes through the binned search like a single one does: three launches for the whole batch, and the same bits as
+    the brute-force window kernel and the oracle (dense mask built from the same predicate) - k = 2 + ratio, k = 1 +
+    gate, cross-check, device tensors and host arrays."""
+    import torch
+    shapes = [(300, 900), (1, 1), (450, 0), (0, 200), (700, 2500), (64, 64), (500, 1300)]
+    qs, ts, qx, tx = [], [], [], []
+    for i, (nq, nt) in enumerate(shapes):
+        q, t, qxy, txy, _ = synth.window_scene(max(nq, 1), max(nt, 1), 40 + i)
+        qs.append(q[:nq]); ts.append(t[:nt]); qx.append(qxy[:nq]); tx.append(txy[:nt])
+    qp, tp = np.concatenate(qs), np.concatenate(ts)
+    qxy, txy = np.concatenate(qx), np.concatenate(tx)
+    tab = bb.make_problems([a for a, _ in shapes], [b for _, b in shapes])
+    radius = 14.0
+    dense = [orc.window_mask(qx[i], tx[i], radius) if shapes[i][0] and shapes[i][1] else None for i in range(len(shapes))]
+    for kw, okw in ((dict(k=2, ratio=0.85), dict(k=2, ratio=0.85)), (dict(k=1, max_distance=50), dict(k=1, max_distance=50)),
+                    (dict(cross_check=True), dict(cross_check_=True))):
+        want = []
+        for i, (nq, nt) in enumerate(shapes):
+            want.append(orc.match(qs[i], ts[i], mask=dense[i], **okw) if nq and nt else (np.zeros(0, np.int32),) * 3)
+        try:
+            got = {}
+            for bins in (0, 1):
+                eng.set_tuning(window_bins=bins)
+                got[bins] = eng.match_batched(qp, tp, tab, window=(qxy, txy, radius), **kw)
+                if bins == 0:
+                    assert eng.launch_info()["kernels_launched"] == 3, "count + scatter + search for the whole batch"
+                dev = eng.match_batched(torch.from_numpy(qp).cuda(), torch.from_numpy(tp).cuda(), tab,
+                                        window=(torch.from_numpy(qxy).cuda(), torch.from_numpy(txy).cuda(), radius), **kw)
+                for p in range(len(shapes)):
+                    _eq(got[bins][p], want[p], (kw, bins, p))
+                    _eq(dev[p], want[p], (kw, bins, p, "device"))
+        finally:
+            eng.set_tuning(window_bins=0)
+    # the workspace is clean afterwards: an ordinary call right behind
+    q2, t2, _ = synth.correlated(500, 800, 124)
+    _eq(eng.match(q2, t2, cross_check=True), c_oracle.cross_check(q2, t2))
