@@ -798,6 +798,16 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         else bfm::wb_search_kernel<1, false><<<sgrid, bfm::WS_NT, 0, st>>>(sq, bv, inv_cell);
         CU_TRY(h, cudaGetLastError());
     }
+    if (gate && passes > 1 && !binned) {
+        // CUDA loads a kernel when it is first launched, and that load can wait for the device to go idle.  The first pass
+        // of a gated call spins until the host has queued the rest of the upload - which it only does after ALL passes
+        // have been launched - so a later pass whose kernel is not loaded yet would stall the host for the gate's whole
+        // time-out (tools/repro_gate.py).  Load every pass's kernel before the first launch.
+        for (int pass = 0; pass < passes; ++pass) {
+            cudaFuncAttributes attr;
+            CU_TRY(h, cudaFuncGetAttributes(&attr, reinterpret_cast<const void *>(pick_scan(r, mode, mask, pm, pass > 0, persistent))));
+        }
+    }
     for (int pass = 0; pass < (binned ? 0 : passes); ++pass) {
         sp.knn_col0 = 2 * pass;
         sp.knn_cols = std::min(2, o->k - 2 * pass);

@@ -316,3 +316,19 @@ def test_window_batches_take_the_binned_search(eng):
     # the workspace is clean afterwards: an ordinary call right behind
     q2, t2, _ = synth.correlated(500, 800, 124)
     _eq(eng.match(q2, t2, cross_check=True), c_oracle.cross_check(q2, t2))
+
+
+def test_first_gated_multi_pass_call_does_not_stall_on_a_kernel_load():
+    """CUDA loads a kernel at its first launch and may wait for the device to go idle to do so.  A gated knnMatch with
+    k > 2 launches its second pass while the first one spins on the upload; in a fresh process whose earlier calls used
+    other kernels that stalled the host for the gate's 4 s time-out and failed the call.  The library loads the kernels
+    of all passes before the first launch (tools/repro_gate.py, run in its own process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "repro_gate.py")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("gated k=3 call:")][-1]
+    assert "same tables" in line, line
+    assert float(line.split()[-2]) < 1.0, line

@@ -39,7 +39,10 @@ for it in range(iters):
     ref = None
     runs = []
     for chunks in (1, int(rng.integers(2, 25))):
-        eng.set_tuning(pipeline_chunks=chunks, feeders=[0, -1, int(rng.integers(1, 33))][it % 3], host_threads=[0, 0, -1, 3][it % 4])
+        knobs = dict(pipeline_chunks=chunks, feeders=[0, -1, int(rng.integers(1, 33))][it % 3], host_threads=[0, 0, -1, 3][it % 4])
+        if os.environ.get("STRESS_VERBOSE"):
+            print(f"iter {it}: P={P} mode={mode} rows={int(qn.sum())}x{int(tn.sum())} {knobs}", flush=True)
+        eng.set_tuning(**knobs)
         runs.append(("host pageable chunks=%d" % chunks, eng.match_batched(q, t, tab, want_knn=want_knn, **kw)))
         n_out = int(qn.sum())
         if n_out and len(q) and len(t):
