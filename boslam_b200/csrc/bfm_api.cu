@@ -346,41 +346,39 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
     }
 }
 
-// The persistent form (resident inputs): at most ONE wave of CTAs drawing the work items of plan_segments from a ticket
-// counter; when the queue is empty the problems are finalized tile by tile (FT rows of one problem per tile).  Tile
-// (p, j) belongs to CTA owner(p, j), non-decreasing in j: a tile only waits for the tiles before it, i.e. for CTAs with
-// a lower or equal index, which the hardware dispatched no later than its own (the rule the feeder CTAs of the host
-// path rely on as well).  Owners rotate over the grid so the tiles of a batch spread evenly.
+// The persistent form (resident inputs): at most ONE wave of CTAs; CTA c starts with work item c of plan_segments and
+// draws further items from a ticket counter; when the queue is empty the problems are finalized tile by tile (FT rows
+// of one problem per tile).  The tiles, in (problem, tile) order, are dealt in contiguous runs to the LOWEST-indexed
+// quarter of the grid (one tile each while they last): a tile waits for the tiles before it - CTAs with a lower or
+// equal index, dispatched no later than its own - and for its problem's work items, which may include the first items
+// of CTAs that are not resident yet when the GPU is shared with another kernel.  Those CTAs start as soon as a slot is
+// free, and slots do come free: every resident CTA that owns no tile exits when the queue is empty, and the owners
+// are at most a quarter of the grid, so even three such launches sharing the GPU cannot fill it with waiting owners
+// (tools/share_gpu_probe.py runs two of them against each other).  Every wait also has a 2 s time-out.
 constexpr int FT_ROWS_TILE = NT * bfm::FT_RPT;
 
 void plan_tiles(const bfm_problem_t *problems, int n_problems, int n_ctas, std::vector<bfm::FinTile> &tiles,
                 std::vector<int2> &cta_tiles) {
-    struct Owned { bfm::FinTile t; int owner; };
-    std::vector<Owned> own;
+    tiles.clear();
     int slot = 0;
     for (int p = 0; p < n_problems; ++p) {
         const int rows = std::max(0, problems[p].q_count);
         const int nt = std::max(1, (rows + FT_ROWS_TILE - 1) / FT_ROWS_TILE);
-        int base = slot % n_ctas;
-        if (nt <= n_ctas && base + nt > n_ctas) base = 0;
         for (int j = 0; j < nt; ++j) {
-            Owned o;
-            o.t.problem = p; o.t.row0 = j * FT_ROWS_TILE; o.t.index = j; o.t.n_tiles = nt; o.t.slot0 = slot;
-            o.t.pad[0] = o.t.pad[1] = o.t.pad[2] = 0;
-            o.owner = nt <= n_ctas ? base + j : (int)((long long)j * n_ctas / nt);
-            own.push_back(o);
+            bfm::FinTile t;
+            t.problem = p; t.row0 = j * FT_ROWS_TILE; t.index = j; t.n_tiles = nt; t.slot0 = slot;
+            t.pad[0] = t.pad[1] = t.pad[2] = 0;
+            tiles.push_back(t);
         }
         slot += nt;
     }
-    std::stable_sort(own.begin(), own.end(), [](const Owned &a, const Owned &b) { return a.owner < b.owner; });
+    const long long n = (long long)tiles.size();
+    const long long owners = std::min<long long>(n, std::max<long long>(1, n_ctas / 4));
     cta_tiles.assign((size_t)n_ctas, make_int2(0, 0));
-    tiles.clear();
-    tiles.reserve(own.size());
-    for (size_t i = 0; i < own.size(); ++i) {
-        int2 &w = cta_tiles[own[i].owner];
+    for (long long i = 0; i < n; ++i) {
+        int2 &w = cta_tiles[(size_t)(i * owners / n)];   // contiguous runs, owner index non-decreasing in tile order
         if (w.y == 0) w.x = (int)i;
         ++w.y;
-        tiles.push_back(own[i].t);
     }
 }
 

@@ -332,3 +332,16 @@ def test_first_gated_multi_pass_call_does_not_stall_on_a_kernel_load():
     line = [l for l in r.stdout.splitlines() if l.startswith("gated k=3 call:")][-1]
     assert "same tables" in line, line
     assert float(line.split()[-2]) < 1.0, line
+
+
+def test_two_persistent_launches_share_the_gpu():
+    """Two engines on two threads run persistent launches in which the finalize tiles outnumber their owners, at the same
+    time: neither grid is fully resident, tiles wait for work items of CTAs that start later - every call must still
+    return the right lists, and none may come near the 2 s of a tile's time-out (tools/share_gpu_probe.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "share_gpu_probe.py"), "80"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
+    assert "wrong results [0, 0]" in r.stdout

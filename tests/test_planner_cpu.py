@@ -135,12 +135,19 @@ def test_tile_owners_never_wait_for_a_later_cta(q_counts, n_ctas):
     _check_tiles(tab, tiles, tile_cta, n_ctas)
 
 
-def test_tiles_of_the_headline_batch_spread_over_the_grid():
-    tab = bb.make_problems([2000] * 256, [2000] * 256)
+def test_tile_owners_are_the_lowest_quarter_of_the_grid():
+    """Owners are dealt from CTA 0 upwards, one tile each while they last and never more than a quarter of the grid: the
+    CTAs that own no tile exit when the queue is empty, so a grid that is only partly resident (a shared GPU) always gets
+    its remaining CTAs started."""
+    tab = bb.make_problems([2000] * 32, [2000] * 32)                 # a rank's share at 8 GPUs: 128 tiles
     tiles, tile_cta = _ffi.plan_preview_tiles(tab, SLOTS)
     _check_tiles(tab, tiles, tile_cta, SLOTS)
-    assert len(tiles) == 1024 and np.bincount(tile_cta, minlength=SLOTS).max() <= 2
+    assert len(tiles) == 128 and tile_cta.tolist() == list(range(128))
+    tab = bb.make_problems([300] * 1000, [300] * 1000)               # many small problems: more tiles than a quarter of the grid
+    tiles, tile_cta = _ffi.plan_preview_tiles(tab, SLOTS)
+    _check_tiles(tab, tiles, tile_cta, SLOTS)
+    assert tile_cta.max() == SLOTS // 4 - 1 and np.bincount(tile_cta).max() <= 4
     one = bb.make_problems([70000], [70000])
-    tiles, tile_cta = _ffi.plan_preview_tiles(one, 64)      # more tiles than CTAs: consecutive tiles share a CTA, in order
+    tiles, tile_cta = _ffi.plan_preview_tiles(one, 64)               # more tiles than CTAs: consecutive tiles share a CTA, in order
     _check_tiles(one, tiles, tile_cta, 64)
-    assert len(tiles) == 137 and np.bincount(tile_cta, minlength=64).max() <= 3
+    assert len(tiles) == 137 and tile_cta.max() == 15 and np.bincount(tile_cta).max() <= 9
