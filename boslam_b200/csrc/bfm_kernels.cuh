@@ -330,7 +330,7 @@ __device__ __forceinline__ void red_release_gpu_add(uint32_t *p, uint32_t v) {
 // (they are finalized by CTAs dispatched no later than this one, so the wait cannot deadlock).  Returns the tile's count.
 template <int NT, int RPT, bool LOOKBACK>
 __device__ __forceinline__ int finalize_rows(const ScanParams &p, const Problem &pr, const int pi, const int base, int running,
-                                             int (*s_cnt)[NT / 32], const FinTile *ft) {
+                                             int (*s_cnt)[NT / 32], const FinTile *ft, uint32_t *arrivals = nullptr) {
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
@@ -408,7 +408,13 @@ __device__ __forceinline__ int finalize_rows(const ScanParams &p, const Problem 
     if (LOOKBACK) {
         // publish this tile's count, then add up the tiles before it (every thread sums them all: index <= a few dozen
         // for any real frame; the words sit in L2)
-        if (tid == 0) *(volatile uint32_t *)(p.fin_count + ft->slot0 + ft->index) = (p.fin_epoch << 12) | (uint32_t)tile_total;
+        if (tid == 0) {
+            *(volatile uint32_t *)(p.fin_count + ft->slot0 + ft->index) = (p.fin_epoch << 12) | (uint32_t)tile_total;
+            // Every read this tile makes of the problem's column keys and row states has returned (the keep
+            // decisions behind the barrier above consumed them): count the tile as done reading NOW, so the round
+            // trip of the atomic runs under the look-back and the match stores instead of after them.
+            *arrivals = atomicAdd(p.fin_done + pi, 1u);   // idles at all-ones
+        }
         const uint32_t tag = p.fin_epoch << 12;
         for (int t = lane; t < ft->index; t += 32) {
             uint32_t v;
@@ -491,14 +497,10 @@ __device__ __noinline__ void finalize_tile(const ScanParams &p, const FinTile *f
         }
     }
     __syncthreads();
-    finalize_rows<NT, FT_RPT, true>(p, pr, pi, ftp->row0, 0, s_cnt, ftp);
-    // the tile that finishes last restores what all tiles of the problem have read
-    if (tid == 0) {
-        // (this tile's reads of the column keys have returned - the keep decisions above consumed them - so the
-        // tile that resets them after seeing this count cannot overtake them: no fence)
-        const uint32_t old = atomicAdd(p.fin_done + pi, 1u);   // idles at all-ones
-        *s_flag = (old == (uint32_t)ftp->n_tiles - 2u) ? 1 : 0;
-    }
+    uint32_t old = 0;
+    finalize_rows<NT, FT_RPT, true>(p, pr, pi, ftp->row0, 0, s_cnt, ftp, &old);
+    // the tile that arrives last restores what all tiles of the problem have read (no fence: see finalize_rows)
+    if (tid == 0) *s_flag = (old == (uint32_t)ftp->n_tiles - 2u) ? 1 : 0;
     __syncthreads();
     if (*s_flag) {
         if (tid == 0) {

@@ -247,11 +247,14 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
             }
             sh->left[r].store(cnt, std::memory_order_relaxed);
         }
+        std::vector<std::function<void()>> work;
+        work.reserve(jobs.size());
         for (const Job &j : jobs)
-            h->pool->submit([j, sh, advance]() {
+            work.emplace_back([j, sh, advance]() {
                 stream_copy(j.dst, j.src, j.n);   // non-temporal: the next reader is the GPU, over PCIe
                 if (sh->left[j.r].fetch_sub(1, std::memory_order_acq_rel) == 1) advance();
             });
+        h->pool->submit_batch(std::move(work));
         advance();   // leading rounds without bytes
         const double t_submitted = cpu_ms();
         gate.epoch = next_feed_epoch(h, st);

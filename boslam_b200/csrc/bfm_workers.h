@@ -71,6 +71,17 @@ public:
         }
         cv_.notify_one();
     }
+    // many jobs under ONE lock and one wake-up of every worker: a lock + notify per job costs ~1.5 us each, and a
+    // staged call queues two dozen of them before it may launch its kernel
+    void submit_batch(std::vector<std::function<void()>> &&jobs) {
+        if (jobs.empty()) return;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            pending_ += (int)jobs.size();
+            for (auto &j : jobs) q_.push_back(std::move(j));
+        }
+        cv_.notify_all();
+    }
     // the calling thread works through the queue too, then waits for the jobs other threads still run
     void help_and_wait() {
         for (;;) {
