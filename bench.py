@@ -696,6 +696,37 @@ def main():
                 "frac": hbm_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": hbm_bytes,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
     }
+    tensor_form = info["popc_mode"] == 0
+    if tensor_form:
+        # Tensor form (boslam_b200/csrc/bfm_tensor.cuh): a step is three launches - expansion to s8, the tcgen05 scan, the
+        # tile-parallel finalize.  The dominant kernel is the scan; its duration comes from the library's events around
+        # that launch alone (CUDA events on the launching stream, every step of a separate loop), its share of the step
+        # is reported next to it.  Algorithmic work: 256 multiply-adds per pair = 512 ops.
+        int8_peak = 2.0 * peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62))
+        tops = pairs_per_launch * 512 / (scan_iso * 1e-3) / 1e12
+        alu_pairs = 64 * 148 * clocks.get("sm_mhz", 1965.0) * 1e6 / 3.0 if isinstance(clocks, dict) and clocks.get("sm_mhz") else None
+        roofline = {
+            "bound": "tensor", "kernel": "bfm_tc::scan_kernel (tcgen05.mma kind::i8, TMEM accumulators)",
+            "achieved": tops, "peak": int8_peak, "unit": "TOP/s", "frac": tops / int8_peak,
+            "traffic": from_file.get("tensor_dram_bytes_per_launch") if world == 1 else None,
+            "traffic_source": from_file.get("tensor_source") if world == 1 else None,
+            "algorithmic": f"512 s8 ops (256 multiply-adds) per descriptor pair x {pairs_per_launch:.4g} pairs per launch",
+            "peak_source": ("2 x the dense bf16 figure of MEASURED_PEAKS.json (sustained: the kernel is timed inside a long step); B200's s8 "
+                            "tensor rate is twice its bf16 rate, the file holds no s8 measurement" if "bf16_tflops" in peaks else "fallback"),
+            "kernel_ms": scan_iso, "kernel_ms_how": "library events around the scan launch alone, every step of a separate loop",
+            "step_ms": ms / args.steps, "kernel_share_of_step": scan_iso / (ms / args.steps) if world == 1 else None,
+            # what binds it in practice: the epilogue turns every distance into a key and keeps the two smallest per row,
+            # 1 IMAD + 3 VIMNMX per pair and thread; the ALU pipe issues 64 lanes per clock and SM
+            "epilogue_alu": ({"pairs_per_s_bound": alu_pairs, "frac": pairs_per_launch / (scan_iso * 1e-3) / alu_pairs,
+                              "how": "3 min/max per pair on the 64-lane ALU pipe x 148 SMs x SM clock under load"} if alu_pairs else None),
+            "popc_form": {"peak_pairs_per_s": popc["ops_per_s"] / 4.0, "note": "bound of the POPC kernel this form replaces (4 POPC per pair on the XU pipe)"},
+            "from_file": from_file or None,
+            "hbm": {"achieved": (hbm_bytes + 2 * 256 * 2 * n_out) / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (hbm_bytes + 2 * 256 * 2 * n_out) / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                    "algorithmic_bytes_per_launch": hbm_bytes + 2 * 256 * 2 * n_out,
+                    "note": "descriptors in + expanded planes written and read once + row state",
+                    "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+        }
 
     # -- e2e: numpy in -> numpy out through the public API, pinned host inputs.  At N > 1 the same call also delivers
     #    the exchange: its epilogue writes this rank's lists into every rank's table, then the barrier --
@@ -827,7 +858,7 @@ def main():
     line = {
         "metric": "hamming_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "s8" if info["popc_mode"] == 0 else "u32", "data": "synthetic",   # s8 operands, s32 accumulators
         "config": bench_config(),
         "run": {"pairs_this_rank": P_loc, "input_sets": n_sets, "input_mb_per_rank": n_sets * set_bytes / 1e6,
                 "parallelism": (f"pair list split x{world}, match tables gathered by the kernel epilogue over NVLink "
@@ -839,7 +870,8 @@ def main():
         "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_res, "gpu_launches": int(launches), "roofline": roofline,
         "launch": dict({k: info[k] for k in ("scan_grid", "scan_block", "queries_per_thread", "popc_mode",
                                              "train_rows_per_segment", "segments", "kernels_launched")},
-                       form="static: one work item per CTA" if info["scan_grid"] == info["segments"] else
+                       form="tensor: s8 expansion + tcgen05 scan (one persistent CTA per SM) + tile-parallel finalize" if info["popc_mode"] == 0 else
+                            "static: one work item per CTA" if info["scan_grid"] == info["segments"] else
                             "persistent: one wave of CTAs drawing work items from a ticket counter"),
         "frames_per_s": N_PAIRS * args.steps / (ms * 1e-3),
         "verify": verify,

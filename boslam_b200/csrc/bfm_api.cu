@@ -38,6 +38,7 @@ constexpr int MIN_SEG_ROWS = 32; // smallest train range worth a CTA
 // (tools/taper_probe.py, profiles/r01f_taper_probe.log)
 constexpr int GSS_MAX_ROWS = 512;
 constexpr long long PERSISTENT_MAX_PAIRS = 160ll * 1000 * 1000;   // launches above this (~0.15 ms) take the static form
+constexpr long long TENSOR_MIN_PAIRS = 8ll * 1000 * 1000;         // eligible launches from this size on take the tensor form
 constexpr int TAPER_AUTO = 4;
 constexpr int TAPER_PCT_AUTO = 10;
 constexpr int N_TABLE_SLOTS = 4;
@@ -92,6 +93,9 @@ struct bfm_handle_s {
     uint32_t *d_queue = nullptr;   // two ticket counters used by alternate launches (each launch zeroes the other one)
     int queue_phase = 0;
     DevBuf bins;     // binned window search: train rows in grid-cell order + cell table
+    DevBuf xq, xt;   // tensor form: the descriptors expanded to one s8 per bit, two planes of [rows + slack][128] bytes
+    int tensor = 0;  // tuning: 0 auto (large resident batches without mask / cross-check), 1 off, 2 whenever eligible
+    long long x_rows[2] = {0, 0};   // rows of the expanded planes the cached plan was made for (queries, train)
     int bins_problems = 0;   // problems the counters of `bins` are laid out for
     void *h_tables[N_TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};  // pinned staging ring
     size_t h_tables_cap[N_TABLE_SLOTS] = {0, 0, 0, 0};
@@ -119,7 +123,7 @@ struct bfm_handle_s {
     size_t h_stage_cap = 0;
     uint32_t *h_ready = nullptr;  // pinned: staged rounds published by the host (read by the feeder CTAs)
     int host_threads = 0;         // tuning: 0 auto, -1 off
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0], [1] around a call's launches; [2], [3] around the tensor scan alone
     // stream hand-over: every call leaves an event on its stream; a call that arrives on a DIFFERENT stream waits
     // for it before it touches the shared workspace / tables (device calls are asynchronous)
     cudaEvent_t last_ev = nullptr;
@@ -346,6 +350,88 @@ void plan_segments(bfm_handle_t h, const bfm_problem_t *problems, int n_problems
     }
 }
 
+// Tensor form (bfm_tensor.cuh): work items of 256 query rows x a train range that is a multiple of 128 rows (the last
+// range of a problem ends where the problem ends).  Every problem gets an 8-aligned base in the expanded planes
+// (xq0 / xt0).  One CTA per SM walks the items with a fixed stride, so the cost of a cut is rounds x (tiles per item +
+// ~3 tiles of per-item prologue); the cut with the lowest cost over the batch's shape histogram is taken.
+void tensor_bases(const bfm_problem_t *problems, int n_problems, std::vector<int32_t> &xq0, std::vector<int32_t> &xt0, long long *rows) {
+    xq0.resize(n_problems);
+    xt0.resize(n_problems);
+    long long q = 0, t = 0;
+    for (int p = 0; p < n_problems; ++p) {
+        xq0[p] = (int32_t)q;
+        xt0[p] = (int32_t)t;
+        q += (std::max(0, problems[p].q_count) + 7) & ~7;
+        t += (std::max(0, problems[p].t_count) + 7) & ~7;
+    }
+    rows[0] = q;
+    rows[1] = t;
+}
+
+void plan_items_tensor(const bfm_problem_t *problems, int n_problems, int n_sms, const std::vector<int32_t> &xq0, const std::vector<int32_t> &xt0,
+                       std::vector<Segment> &segs, std::vector<int> &seg_begin, int *seg_rows_out) {
+    std::vector<std::pair<std::pair<int, int>, long long>> shapes;   // (query blocks, train tiles) -> problems
+    int max_tiles = 1;
+    for (int p = 0; p < n_problems; ++p) {
+        const bfm_problem_t &pr = problems[p];
+        if (pr.q_count <= 0 || pr.t_count <= 0) continue;
+        const std::pair<int, int> key((pr.q_count + bfm::TC_BQ - 1) / bfm::TC_BQ, (pr.t_count + bfm::TC_BT - 1) / bfm::TC_BT);
+        max_tiles = std::max(max_tiles, key.second);
+        if (!shapes.empty() && shapes.back().first == key) { ++shapes.back().second; continue; }
+        bool found = false;
+        for (size_t i = 0; i < shapes.size() && i < 16 && !found; ++i)
+            if (shapes[i].first == key) { ++shapes[i].second; found = true; }
+        if (!found) shapes.emplace_back(key, 1);
+    }
+    const int cap = 8192;   // tiles per item: the keys hold a 21-bit column offset
+    int best_L = std::min(max_tiles, cap);
+    double best_cost = -1.0;
+    const int n_cand = std::min(std::min(max_tiles, cap), 512);
+    for (int c = 0; c <= n_cand; ++c) {
+        const int L = c == 0 ? std::min(max_tiles, cap) : c;
+        long long items = 0;
+        int seg_tiles = 1;
+        for (const auto &sh : shapes) {
+            const int nsp = (sh.first.second + L - 1) / L;
+            items += sh.second * sh.first.first * nsp;
+            seg_tiles = std::max(seg_tiles, (sh.first.second + nsp - 1) / nsp);
+        }
+        const long long rounds = (items + n_sms - 1) / std::max(n_sms, 1);
+        const double cost = (double)rounds * (seg_tiles + 3.0);
+        if (best_cost < 0 || cost < best_cost - 1e-9) { best_cost = cost; best_L = L; }
+    }
+    *seg_rows_out = best_L * bfm::TC_BT;
+    segs.clear();
+    seg_begin.assign((size_t)n_problems + 1, 0);
+    for (int p = 0; p < n_problems; ++p) {
+        const bfm_problem_t &pr = problems[p];
+        seg_begin[p] = (int)segs.size();
+        if (pr.q_count > 0 && pr.t_count > 0) {
+            const int tiles = (pr.t_count + bfm::TC_BT - 1) / bfm::TC_BT;
+            const int nsp = (tiles + best_L - 1) / best_L;
+            const int base = tiles / nsp, rem = tiles % nsp;
+            for (int qb = 0; qb * bfm::TC_BQ < pr.q_count; ++qb) {
+                int t0 = 0;
+                for (int sidx = 0; sidx < nsp; ++sidx) {
+                    const int cnt = std::min((base + (sidx < rem ? 1 : 0)) * bfm::TC_BT, pr.t_count - t0);
+                    Segment sg;
+                    sg.q_row0 = xq0[p] + qb * bfm::TC_BQ;
+                    sg.q_valid = std::min(bfm::TC_BQ, pr.q_count - qb * bfm::TC_BQ);
+                    sg.q_local0 = qb * bfm::TC_BQ;
+                    sg.out_row0 = pr.out_begin + qb * bfm::TC_BQ;
+                    sg.t_row0 = xt0[p] + t0;
+                    sg.t_count = cnt;
+                    sg.t_local0 = t0;
+                    sg.problem = p;
+                    segs.push_back(sg);
+                    t0 += cnt;
+                }
+            }
+        }
+        seg_begin[p + 1] = (int)segs.size();
+    }
+}
+
 // The persistent form (resident inputs): at most ONE wave of CTAs; CTA c starts with work item c of plan_segments and
 // draws further items from a ticket counter; when the queue is empty the problems are finalized tile by tile (FT rows
 // of one problem per tile).  The tiles, in (problem, tile) order, are dealt in contiguous runs to the LOWEST-indexed
@@ -506,7 +592,11 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     // ones (one wave, no second and third wave of CTA launches, tile-parallel finalize): profiles/r02_kernel_forms.md
     long long total_pairs = 0;
     for (int p = 0; p < n_problems; ++p) total_pairs += (long long)std::max(0, problems[p].q_count) * std::max(0, problems[p].t_count);
-    const bool persistent = !gate && !binned && (h->persistent == 2 || (h->persistent == 0 && total_pairs <= PERSISTENT_MAX_PAIRS));
+    // Tensor form (bfm_tensor.cuh): distances as s8 dot products on tcgen05, 3x the POPC kernel on the headline batch.
+    // Resident inputs, one pass (k <= 2), no mask, no cross-check, a train count known on the host.
+    const bool tensor = !gate && !binned && mode != 1 && mask == BFM_MASK_NONE && passes == 1 && t_limit == nullptr && h->tensor != 1 &&
+                        (h->tensor == 2 || total_pairs >= TENSOR_MIN_PAIRS);
+    const bool persistent = !tensor && !gate && !binned && (h->persistent == 2 || (h->persistent == 0 && total_pairs <= PERSISTENT_MAX_PAIRS));
     // static form with a few large problems: the CTA that completes a problem would walk all its rows alone (64 tiles
     // x ~5 us at 64k rows, fully exposed when there is nothing else to scan) - finalize tiles in a second launch instead
     bool defer = false;
@@ -515,6 +605,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         for (int p = 0; p < n_problems; ++p) max_rows = std::max(max_rows, problems[p].q_count);
         defer = max_rows >= 4096;
     }
+    if (tensor) defer = true;   // the tensor scan only reduces; the tile-parallel kernel finalizes
     if (binned) r = 1;
     if (r != 1 && r != 2 && r != 4) {
         // largest register tile that still leaves >= 2 work items per CTA slot
@@ -543,7 +634,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     // -- plan cache: same problems + same variant as the previous call -> the device tables are
     //    already in place (steady state of a tracking loop with fixed shapes, bench loops) ----------
     // resident inputs take the persistent form (at most one wave, tile-parallel finalize inside the same launch)
-    const int plan_sig[8] = {n_problems, binned ? 100 : r, mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots,
+    const int plan_sig[8] = {n_problems, binned ? 100 : (tensor ? 200 : r), mode, h->segment_rows, h->waves + 4096 * (plan_problems == &hinted ? hinted.t_count : 0), slots,
                              h->taper * 1000 + h->taper_pct + 100000 * h->gss_div + 10000000 * h->gss_min, (persistent ? 1 : 0) + (defer ? 2 : 0)};
     const bool plan_hit = h->plan_valid && std::memcmp(plan_sig, h->plan_sig, sizeof(plan_sig)) == 0 &&
                           h->plan_problems.size() == (size_t)n_problems &&
@@ -572,14 +663,17 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
             for (Segment &sg : h->segs_host) {
                 const bfm_problem_t &pr = problems[sg.problem];
                 const bool placeholder = sg.q_valid == 0 && sg.t_count == 0;   // the one item of an empty problem
-                sg.q_row0 = placeholder ? 0 : pr.q_begin + sg.q_local0;
                 sg.out_row0 = pr.out_begin + sg.q_local0;
+                if (tensor) continue;   // (its rows are rows of the expanded planes: a function of the shapes alone)
+                sg.q_row0 = placeholder ? 0 : pr.q_begin + sg.q_local0;
                 sg.t_row0 = placeholder ? 0 : pr.t_begin + sg.t_local0;
             }
             for (int p = 0; p < n_problems; ++p) {
                 const int n_segs = h->plan_probs[p].n_segs;
+                const int32_t xt0 = h->plan_probs[p].col0, xq0 = h->plan_probs[p].pad;
                 h->plan_probs[p] = h->probs_host[p];
                 h->plan_probs[p].n_segs = n_segs;
+                if (tensor) { h->plan_probs[p].col0 = xt0; h->plan_probs[p].pad = xq0; }
             }
         }
     }
@@ -593,10 +687,18 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = bin_grid;   // the search kernel's CTAs play the role of segments
     } else if (!plan_hit) {
         // (a device-side train count re-cuts the rows that exist over equal items per query block: no guided lengths)
-        plan_segments(h, plan_problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows, persistent);
+        std::vector<int32_t> xq0, xt0;
+        if (tensor) {
+            tensor_bases(problems, n_problems, xq0, xt0, h->x_rows);
+            plan_items_tensor(problems, n_problems, h->sm_count, xq0, xt0, h->segs_host, h->seg_begin, &seg_rows);
+        } else {
+            plan_segments(h, plan_problems, n_problems, r, slots, h->segs_host, h->seg_begin, &seg_rows, persistent);
+        }
         h->plan_seg_rows = seg_rows;
         h->plan_probs = h->probs_host;
         for (int p = 0; p < n_problems; ++p) h->plan_probs[p].n_segs = h->seg_begin[p + 1] - h->seg_begin[p];
+        if (tensor)
+            for (int p = 0; p < n_problems; ++p) { h->plan_probs[p].col0 = xt0[p]; h->plan_probs[p].pad = xq0[p]; }
         if (defer) {
             // (static form, a few large problems: one finalize tile per CTA of a second launch)
             long long n_tiles = 0;
@@ -644,6 +746,19 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     if (passes > 1) {
         rc = ensure(h, h->lower, (size_t)n_out_rows * 4);
         if (rc) return rc;
+    }
+    unsigned long long x_plane[2] = {0, 0};
+    if (tensor) {
+        // expanded planes; the slack rows (and whatever earlier calls left behind) are only ever multiplied into
+        // columns and rows nobody reads, but they must exist - and be zero once, so that they hold s8 values
+        DevBuf *xb[2] = {&h->xq, &h->xt};
+        for (int a = 0; a < 2; ++a) {
+            x_plane[a] = (unsigned long long)(h->x_rows[a] + bfm::TC_SLACK_ROWS) * 128ull;
+            const unsigned gen = xb[a]->generation;
+            rc = ensure(h, *xb[a], (size_t)(2 * x_plane[a]));
+            if (rc) return rc;
+            if (xb[a]->generation != gen) CU_TRY(h, cudaMemsetAsync(xb[a]->p, 0, xb[a]->cap, st));
+        }
     }
     const size_t prob_bytes = (size_t)n_problems * sizeof(Problem);
     const size_t seg_bytes = n_segs * sizeof(Segment), work_bytes = (n_ctas_p * sizeof(int2) + 15) & ~(size_t)15;
@@ -826,8 +941,29 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         }
         sp.defer_finalize = defer ? 1 : 0;
         const unsigned grid = persistent ? (unsigned)n_ctas_p : (unsigned)(n_segs + (pass == 0 ? n_feed : 0));
-        fn<<<grid, NT, 0, st>>>(sp);
-        CU_TRY(h, cudaGetLastError());
+        if (tensor) {
+            bfm::TensorLaunch tl;
+            tl.q = q; tl.t = t;
+            tl.probs = d_probs;
+            tl.n_problems = n_problems;
+            int max_rows = 0;
+            for (int p = 0; p < n_problems; ++p) max_rows = std::max(max_rows, std::max(problems[p].q_count, problems[p].t_count));
+            tl.max_rows = max_rows;
+            tl.xq = h->xq.p; tl.xt = h->xt.p;
+            tl.xq_plane = x_plane[0]; tl.xt_plane = x_plane[1];
+            tl.items = d_segs;
+            tl.n_items = (int)n_segs;
+            tl.grid = (int)std::min<size_t>(n_segs, (size_t)h->sm_count);
+            tl.rowstate = rowstate;
+            tl.status = h->h_status;
+            tl.ev_scan[0] = h->timing ? h->ev[2] : nullptr;
+            tl.ev_scan[1] = h->timing ? h->ev[3] : nullptr;
+            const int trc = bfm::tensor_launch(tl, st);
+            if (trc) return fail(h, BFM_ERR_CUDA, std::string("tensor form launch failed: ") + cudaGetErrorString((cudaError_t)trc));
+        } else {
+            fn<<<grid, NT, 0, st>>>(sp);
+            CU_TRY(h, cudaGetLastError());
+        }
         if (defer) {
             bfm::bfm_tiles_kernel<<<(unsigned)n_tiles_p, NT, 0, st>>>(sp);
             CU_TRY(h, cudaGetLastError());
@@ -839,18 +975,19 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     h->last_stream = st;
     h->last_pending = true;
 
-    h->launches += binned ? 3 : passes * (defer ? 2 : 1);
-    h->info.kernels_launched = binned ? 3 : passes * (defer ? 2 : 1);
-    h->info.scan_grid = binned ? bin_grid : (persistent ? (int32_t)n_ctas_p : (int32_t)n_segs);
-    h->info.scan_block = NT;
-    h->info.queries_per_thread = r;
-    h->info.popc_mode = pm;
+    h->launches += binned ? 3 : passes * (defer ? 2 : 1) + (tensor ? 1 : 0);
+    h->info.kernels_launched = binned ? 3 : passes * (defer ? 2 : 1) + (tensor ? 1 : 0);
+    h->info.scan_grid = binned ? bin_grid : (tensor ? (int32_t)std::min<size_t>(n_segs, (size_t)h->sm_count) : persistent ? (int32_t)n_ctas_p : (int32_t)n_segs);
+    h->info.scan_block = tensor ? 320 : NT;
+    h->info.queries_per_thread = tensor ? 0 : r;   // (tensor form: a thread of the epilogue owns one query row)
+    h->info.popc_mode = tensor ? 0 : pm;           // 0: no POPC at all - distances come from tcgen05.mma
     h->info.segments = (int32_t)n_segs;
     h->info.train_rows_per_segment = seg_rows;
     if (h->timing && !gate) {
         CU_TRY(h, cudaEventSynchronize(h->ev[1]));
         CU_TRY(h, cudaEventElapsedTime(&h->info.scan_ms, h->ev[0], h->ev[1]));
         h->info.total_ms = h->info.scan_ms;
+        if (tensor) CU_TRY(h, cudaEventElapsedTime(&h->info.scan_ms, h->ev[2], h->ev[3]));   // the scan alone; total_ms: expansion + scan + finalize
     }
     if (h->check_clean && !gate) {  // debugging aid: the workspace must be all-ones after every call
         CU_TRY(h, cudaDeviceSynchronize());
@@ -913,7 +1050,7 @@ int bfm_create(int device, bfm_handle_t *out) {
     std::memset(h->occ_cache, 0, sizeof(h->occ_cache));
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < 2; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 4; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->last_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_prog, 256) == cudaSuccess && cudaMemset(h->d_prog, 0, 256) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_queue, 256) == cudaSuccess && cudaMemset(h->d_queue, 0, 256) == cudaSuccess;
@@ -921,6 +1058,7 @@ int bfm_create(int device, bfm_handle_t *out) {
          cudaMallocHost(&h->h_marks, sizeof(unsigned long long) * 2 * MAX_COPY_CHUNKS) == cudaSuccess &&
          cudaMallocHost(&h->h_status, 64) == cudaSuccess && cudaMallocHost(&h->h_ready, 64) == cudaSuccess;
     if (ok) *h->h_status = 0;
+    ok = ok && bfm::tensor_init() == 0;
     for (int i = 0; ok && i < N_TABLE_SLOTS; ++i) {
         ok = cudaEventCreateWithFlags(&h->table_ev[i], cudaEventDisableTiming) == cudaSuccess;
         if (ok) ok = cudaEventRecord(h->table_ev[i], h->stream) == cudaSuccess;
@@ -938,7 +1076,7 @@ int bfm_destroy(bfm_handle_t h) {
     if (!h) return BFM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins, &h->finc})
+    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins, &h->finc, &h->xq, &h->xt})
         if (b->p) cudaFree(b->p);
     if (h->d_ready) cudaFree(h->d_ready);
     if (h->d_prog) cudaFree(h->d_prog);
@@ -953,7 +1091,7 @@ int bfm_destroy(bfm_handle_t h) {
         if (h->table_ev[i]) cudaEventDestroy(h->table_ev[i]);
     }
     if (h->h_out) cudaFreeHost(h->h_out);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->last_ev) cudaEventDestroy(h->last_ev);
     if (h->in_stream) cudaStreamDestroy(h->in_stream);
@@ -1095,6 +1233,9 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "persistent") {
         if (value < 0 || value > 2) return fail(h, BFM_ERR_INVALID, "persistent must be 0 (auto), 1 (off) or 2 (always, for resident inputs)");
         h->persistent = value;
+    } else if (k == "tensor") {
+        if (value < 0 || value > 2) return fail(h, BFM_ERR_INVALID, "tensor must be 0 (auto), 1 (off) or 2 (whenever the call is eligible)");
+        h->tensor = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");
         h->waves = value;

@@ -1456,4 +1456,24 @@ ScanFn pick_scan_r4_m0(int mask, int pm, bool bound, bool dyn);
 ScanFn pick_scan_r4_m1(int mask, int pm, bool bound, bool dyn);
 ScanFn pick_scan_r4_m2(int mask, int pm, bool bound, bool dyn);
 
+// defined in bfm_tensor.cu: the matching kernel on the tensor cores (tcgen05; resident inputs, k <= 2, no mask, no
+// cross-check).  Work items are Segments with 256-row query blocks whose q_row0 / t_row0 are rows of the EXPANDED planes.
+constexpr int TC_BQ = 256;               // query rows per work item
+constexpr int TC_BT = 128;               // train rows per tile: segment lengths are multiples of it
+constexpr int TC_SLACK_ROWS = 512;       // rows past the end of a plane that a tile may read (they only have to exist)
+struct TensorLaunch {
+    const void *q, *t;                   // packed descriptors (32 bytes per row)
+    const Problem *probs;                // device table: pad = first expanded query row, col0 = first expanded train row
+    int n_problems, max_rows;            // max_rows: the longest query / train set (grid of the expansion); 0 = planes are current
+    void *xq, *xt;                       // expanded planes [2][rows + slack][128]
+    unsigned long long xq_plane, xt_plane;   // bytes per plane
+    const Segment *items;
+    int n_items, grid;
+    unsigned long long *rowstate;
+    uint32_t *status;                    // pinned host word or NULL
+    cudaEvent_t ev_scan[2];              // timing knob: recorded around the scan kernel alone (NULL otherwise)
+};
+int tensor_init();
+int tensor_launch(const TensorLaunch &L, cudaStream_t st);
+
 }  // namespace bfm

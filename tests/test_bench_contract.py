@@ -58,17 +58,18 @@ def test_b200_arm_line_has_every_contract_key():
     assert len(lines) == 1, lines
     d = json.loads(lines[0])
     assert "impl" not in d and d["metric"] == "hamming_pairs_per_s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3
-    assert d["scaling"] == "strong" and d["vs_baseline"] is None and d["dtype"] == "u32" and d["data"] == "synthetic"
+    assert d["scaling"] == "strong" and d["vs_baseline"] is None and d["dtype"] == "s8" and d["data"] == "synthetic"
     assert d["config"]["workload"] == "loop_closing" and "l2" in d["config"] and d["config"]["pairs"] == 256
-    assert d["gpu_launches"] == 3                                    # one kernel per step
+    assert d["gpu_launches"] == 3 * 3                                # expansion, tcgen05 scan, finalize tiles: three kernels per step
+    assert d["launch"]["form"].startswith("tensor")
     r = d["roofline"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in r, k
-    assert r["frac"] > 0.5 and r["hbm"]["peak"] > 0
-    assert abs(r["kernel_ms"] - d["ms_per_step"]) < 1e-9             # measured live, over the timed region
+    assert r["bound"] == "tensor" and r["unit"] == "TOP/s" and r["frac"] > 0.3 and r["hbm"]["peak"] > 0
+    assert 0 < r["kernel_ms"] < d["ms_per_step"] and 0.5 < r["kernel_share_of_step"] < 1.0   # the scan alone, measured live
     assert d["verify"]["tables_crc32"] > 0 and d["cpu_baseline"]["tables_equal_cv2"] is True
     assert d["sustained"]["seconds"] >= 2.0 and d["sustained"]["value"] > 0
-    assert 0.5 < r["frac_issued"] <= 1.0 and r["popc_issued_per_pair"] == 4     # against the POPCs really issued
+    assert 0.2 < r["epilogue_alu"]["frac"] <= 1.0                    # the pipe that binds the scan in practice
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 30e6 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
     c = d["clocks"]

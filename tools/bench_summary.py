@@ -3,7 +3,7 @@ import json, sys
 for f in sys.argv[1:]:
     d = json.loads(open(f).read().strip().splitlines()[-1])
     e, r = d.get("e2e") or {}, d.get("e2e_resident") or {}
-    print(f"{f}: N={d['n_gpus']} value {d['value'] / 1e9:.1f} G pairs/s ({d['ms_per_step'] * 1e3:.1f} us/step) frac_issued {d['roofline']['frac_issued']:.3f} | "
+    print(f"{f}: N={d['n_gpus']} value {d['value'] / 1e9:.1f} G pairs/s ({d['ms_per_step'] * 1e3:.1f} us/step) roofline {d['roofline']['bound']} frac {d['roofline']['frac']:.3f} | "
           f"e2e {e.get('value', 0) / 1e9:.1f} G ({e.get('ms_per_step', 0) * 1e3:.1f} us) | resident {r.get('value', 0) / 1e9:.1f} G ({r.get('ms_per_step', 0) * 1e3:.1f} us) | "
           f"verified {d.get('gather_verified_full')} launch {d['launch']}")
     if d.get("weak"):
