@@ -702,23 +702,28 @@ def main():
         # tile-parallel finalize.  The dominant kernel is the scan; its duration comes from the library's events around
         # that launch alone (CUDA events on the launching stream, every step of a separate loop), its share of the step
         # is reported next to it.  Algorithmic work: 256 multiply-adds per pair = 512 ops.
-        int8_peak = 2.0 * peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62))
+        # (the 20-step loop lasts a few milliseconds: the burst figure is the honest denominator; `sustained` carries
+        # the long-loop throughput next to the sustained peak)
+        int8_peak = 2.0 * peaks.get("bf16_tflops", 2250.0 * 0.62)
+        int8_peak_sustained = 2.0 * peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0 * 0.62))
         tops = pairs_per_launch * 512 / (scan_iso * 1e-3) / 1e12
-        alu_pairs = 64 * 148 * clocks.get("sm_mhz", 1965.0) * 1e6 / 3.0 if isinstance(clocks, dict) and clocks.get("sm_mhz") else None
+        alu_pairs = 64 * 148 * clocks.get("sm_mhz", 1965.0) * 1e6 / 1.25 if isinstance(clocks, dict) and clocks.get("sm_mhz") else None
         roofline = {
             "bound": "tensor", "kernel": "bfm_tc::scan_kernel (tcgen05.mma kind::i8, TMEM accumulators)",
             "achieved": tops, "peak": int8_peak, "unit": "TOP/s", "frac": tops / int8_peak,
             "traffic": from_file.get("tensor_dram_bytes_per_launch") if world == 1 else None,
             "traffic_source": from_file.get("tensor_source") if world == 1 else None,
             "algorithmic": f"512 s8 ops (256 multiply-adds) per descriptor pair x {pairs_per_launch:.4g} pairs per launch",
-            "peak_source": ("2 x the dense bf16 figure of MEASURED_PEAKS.json (sustained: the kernel is timed inside a long step); B200's s8 "
-                            "tensor rate is twice its bf16 rate, the file holds no s8 measurement" if "bf16_tflops" in peaks else "fallback"),
+            "peak_source": ("2 x the dense bf16 BURST figure of MEASURED_PEAKS.json (cuBLAS, best of 10; the kernel is timed in a loop of a few "
+                            "milliseconds); B200's s8 tensor rate is twice its bf16 rate, the file holds no s8 measurement" if "bf16_tflops" in peaks else "fallback"),
+            "peak_sustained": int8_peak_sustained,
             "kernel_ms": scan_iso, "kernel_ms_how": "library events around the scan launch alone, every step of a separate loop",
             "step_ms": ms / args.steps, "kernel_share_of_step": scan_iso / (ms / args.steps) if world == 1 else None,
-            # what binds it in practice: the epilogue turns every distance into a key and keeps the two smallest per row,
-            # 1 IMAD + 3 VIMNMX per pair and thread; the ALU pipe issues 64 lanes per clock and SM
+            # the other pipe the kernel leans on: the epilogue turns every distance into a 16-bit key (two to a register) and
+            # keeps the two smallest per row, 1 IMAD + 1.25 VIMNMX.U16x2 per pair and thread; the ALU pipe issues 64 lanes
+            # per clock and SM (profiles/r02_tensor_scan.md: MMA alone 205 us, epilogue alone 168 us, both 228 us)
             "epilogue_alu": ({"pairs_per_s_bound": alu_pairs, "frac": pairs_per_launch / (scan_iso * 1e-3) / alu_pairs,
-                              "how": "3 min/max per pair on the 64-lane ALU pipe x 148 SMs x SM clock under load"} if alu_pairs else None),
+                              "how": "1.25 min/max per pair on the 64-lane ALU pipe x 148 SMs x SM clock under load"} if alu_pairs else None),
             "popc_form": {"peak_pairs_per_s": popc["ops_per_s"] / 4.0, "note": "bound of the POPC kernel this form replaces (4 POPC per pair on the XU pipe)"},
             "from_file": from_file or None,
             "hbm": {"achieved": (hbm_bytes + 2 * 256 * 2 * n_out) / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -791,9 +796,14 @@ def main():
                "tuning": tune or None,
                "copy_chunks": eng.launch_info().get("copy_chunks"), "exchange_in_timed_region": fe is not None,
                "exchange_verified": e2e_ok,
-               "how": "numpy (pinned) in -> numpy (pinned) out through Engine.plan_batch(...).run: ONE kernel launch per step whose "
-                      "first CTAs stream the step's inputs from pinned host memory into HBM (copy_chunks = feed rounds) while the "
-                      "others match; results written by the kernel into pinned host memory" +
+               "kernels_per_step": eng.launch_info().get("kernels_launched"),
+               "how": ("numpy (pinned) in -> numpy (pinned) out through Engine.plan_batch(...).run: the copy engine uploads the step's "
+                       "descriptors in copy_chunks chunks of whole problems and every chunk is matched by the tensor form (expansion, "
+                       "tcgen05 scan, finalize: three launches) as soon as it has landed; results written by the finalize kernel "
+                       "into pinned host memory" if eng.launch_info().get("popc_mode") == 0 else
+                       "numpy (pinned) in -> numpy (pinned) out through Engine.plan_batch(...).run: ONE kernel launch per step whose "
+                       "first CTAs stream the step's inputs from pinned host memory into HBM (copy_chunks = feed rounds) while the "
+                       "others match; results written by the kernel into pinned host memory") +
                       (" AND, by the same epilogue, into every rank's symmetric table (NVSwitch multicast / peer stores), then "
                        "the symmetric-memory barrier (overlapping the next step's kernel; the last one is waited for inside the "
                        "timed region)" if fe is not None else "") + "; one stream sync per step"}

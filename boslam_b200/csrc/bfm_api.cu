@@ -94,6 +94,8 @@ struct bfm_handle_s {
     int queue_phase = 0;
     DevBuf bins;     // binned window search: train rows in grid-cell order + cell table
     DevBuf xq, xt;   // tensor form: the descriptors expanded to one s8 per bit, two planes of [rows + slack][128] bytes
+    int tensor_chunks = 0;           // tuning: copy chunks of the chunked host path (0 = auto)
+    bool tables_by_kernel = false;   // set by the chunked host path around its launches
     int tensor = 0;  // tuning: 0 auto (large resident batches without mask / cross-check), 1 off, 2 whenever eligible
     long long x_rows[2] = {0, 0};   // rows of the expanded planes the cached plan was made for (queries, train)
     int bins_problems = 0;   // problems the counters of `bins` are laid out for
@@ -145,10 +147,19 @@ struct bfm_handle_s {
     std::vector<bfm_problem_t> plan_problems;
     // pipelined host path: the copy-in stream
     cudaStream_t in_stream = nullptr;
+    cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // tensor form from host memory: one per copy chunk
+    cudaEvent_t chunk_done_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // ... and one per matched chunk
+    cudaStream_t out_stream = nullptr;   // ... whose results a third stream copies to the host
+    DevBuf d_res;                        // ... out of this device block
     int occ_cache[3][3][3][6];  // [R idx][mode][mask][pm idx] -> CTAs per SM (0 = unknown)
 };
 
 namespace {
+
+// the device tables of a launch, fetched from their pinned staging slot by the SMs (see run_device)
+__global__ void upload_tables_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 
 int fail(bfm_handle_t h, int code, const std::string &msg) {
     if (h) h->err = msg;
@@ -791,7 +802,14 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
         }
         // NOTE: the device table is shared by consecutive calls on one handle; stream order keeps the
         // upload of call n+1 behind the kernel of call n when both use the same stream (the contract).
-        CU_TRY(h, cudaMemcpyAsync(h->tables.p, h->h_tables[slot], table_bytes, cudaMemcpyHostToDevice, st));
+        if (h->tables_by_kernel && table_bytes <= ((size_t)1 << 20)) {
+            // (chunked host path: a copy-engine upload on `st` would queue behind the descriptor chunks of `in_stream` -
+            // the engine serves that stream while it has copies ready - so a few threads fetch the pinned table instead)
+            upload_tables_kernel<<<8, 256, 0, st>>>(static_cast<const uint4 *>(h->h_tables[slot]), static_cast<uint4 *>(h->tables.p), (table_bytes + 15) / 16);
+            CU_TRY(h, cudaGetLastError());
+        } else {
+            CU_TRY(h, cudaMemcpyAsync(h->tables.p, h->h_tables[slot], table_bytes, cudaMemcpyHostToDevice, st));
+        }
         CU_TRY(h, cudaEventRecord(h->table_ev[slot], st));
         std::memcpy(h->plan_sig, plan_sig, sizeof(plan_sig));
         h->plan_problems.assign(problems, problems + n_problems);
@@ -978,7 +996,7 @@ int run_device(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t 
     h->launches += binned ? 3 : passes * (defer ? 2 : 1) + (tensor ? 1 : 0);
     h->info.kernels_launched = binned ? 3 : passes * (defer ? 2 : 1) + (tensor ? 1 : 0);
     h->info.scan_grid = binned ? bin_grid : (tensor ? (int32_t)std::min<size_t>(n_segs, (size_t)h->sm_count) : persistent ? (int32_t)n_ctas_p : (int32_t)n_segs);
-    h->info.scan_block = tensor ? 320 : NT;
+    h->info.scan_block = tensor ? bfm::TC_THREADS : NT;
     h->info.queries_per_thread = tensor ? 0 : r;   // (tensor form: a thread of the epilogue owns one query row)
     h->info.popc_mode = tensor ? 0 : pm;           // 0: no POPC at all - distances come from tcgen05.mma
     h->info.segments = (int32_t)n_segs;
@@ -1076,7 +1094,7 @@ int bfm_destroy(bfm_handle_t h) {
     if (!h) return BFM_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins, &h->finc, &h->xq, &h->xt})
+    for (DevBuf *b : {&h->state, &h->tables, &h->d_in, &h->lower, &h->bins, &h->finc, &h->xq, &h->xt, &h->d_res})
         if (b->p) cudaFree(b->p);
     if (h->d_ready) cudaFree(h->d_ready);
     if (h->d_prog) cudaFree(h->d_prog);
@@ -1094,6 +1112,11 @@ int bfm_destroy(bfm_handle_t h) {
     for (int i = 0; i < 4; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->last_ev) cudaEventDestroy(h->last_ev);
+    for (cudaEvent_t e : h->chunk_ev)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->chunk_done_ev)
+        if (e) cudaEventDestroy(e);
+    if (h->out_stream) cudaStreamDestroy(h->out_stream);
     if (h->in_stream) cudaStreamDestroy(h->in_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1236,6 +1259,9 @@ int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value) {
     } else if (k == "tensor") {
         if (value < 0 || value > 2) return fail(h, BFM_ERR_INVALID, "tensor must be 0 (auto), 1 (off) or 2 (whenever the call is eligible)");
         h->tensor = value;
+    } else if (k == "tensor_chunks") {
+        if (value < 0 || value > 8) return fail(h, BFM_ERR_INVALID, "tensor_chunks must be 0 (auto) .. 8 (copy chunks of a host batch that takes the tensor form)");
+        h->tensor_chunks = value;
     } else if (k == "waves") {
         if (value < 0) return fail(h, BFM_ERR_INVALID, "waves must be >= 0");
         h->waves = value;

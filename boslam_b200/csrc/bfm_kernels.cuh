@@ -1460,6 +1460,7 @@ ScanFn pick_scan_r4_m2(int mask, int pm, bool bound, bool dyn);
 // cross-check).  Work items are Segments with 256-row query blocks whose q_row0 / t_row0 are rows of the EXPANDED planes.
 constexpr int TC_BQ = 256;               // query rows per work item
 constexpr int TC_BT = 128;               // train rows per tile: segment lengths are multiples of it
+constexpr int TC_THREADS = 608;          // threads of a CTA of the tensor scan (bfm_tensor.cuh)
 constexpr int TC_SLACK_ROWS = 512;       // rows past the end of a plane that a tile may read (they only have to exist)
 struct TensorLaunch {
     const void *q, *t;                   // packed descriptors (32 bytes per row)

@@ -142,7 +142,155 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
     auto feedable = [](const void *p) { return host_ptr_is_pinned(p) && (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     const bool feed = G > 1 && h->feeders >= 0 && feedable(q) && feedable(t) &&
                       (!window || (feedable(o->q_xy) && feedable(o->t_xy))) && o->k <= 2;
-    if (feed) {
+    // Tensor form for a batch from pinned host memory: the copy engine brings the descriptors in a few chunks on
+    // `in_stream` (55 GB/s here, against ~30 GB/s of zero-copy reads by feeder CTAs) and every chunk is matched by the
+    // tensor kernels (expansion, tcgen05 scan, finalize) as soon as it has landed.  The batch is then bound by the
+    // upload alone: the last chunk's 50 us of matching is all that is not hidden.  Chunks are whole problems; with
+    // equal shapes a chunk is a whole number of rounds of the persistent scan (its items divide by the SM count).
+    long long total_pairs_h = 0;
+    for (int p = 0; p < n_problems; ++p) total_pairs_h += (long long)std::max(0, problems[p].q_count) * std::max(0, problems[p].t_count);
+    const bool tchunks = h->tensor != 1 && h->feeders >= 0 && h->pipeline_chunks == 0 && o->mask_kind == BFM_MASK_NONE && !o->cross_check && o->k <= 2 &&
+                         n_problems >= 8 && qb + tb >= ((size_t)4 << 20) && total_pairs_h >= 16 * TENSOR_MIN_PAIRS && feedable(q) && feedable(t);
+    if (tchunks) {
+        int C = h->tensor_chunks > 0 ? std::min(h->tensor_chunks, n_problems) : (int)std::min<size_t>(8, std::max<size_t>(2, (qb + tb) / ((size_t)8 << 20)));
+        int per = (n_problems + C - 1) / C;
+        bool uniform = true;
+        for (int p = 1; p < n_problems && uniform; ++p) uniform = problems[p].q_count == problems[0].q_count && problems[p].t_count == problems[0].t_count;
+        if (uniform && problems[0].q_count > 0) {
+            const int ipp = (problems[0].q_count + bfm::TC_BQ - 1) / bfm::TC_BQ;   // work items per problem
+            int a = h->sm_count, b = ipp;
+            while (b) { const int r = a % b; a = b; b = r; }
+            const int unit = h->sm_count / a;                                      // problems per round of the scan
+            if (unit <= 2 * per) per = std::max(1, (per + unit / 2) / unit) * unit;
+        }
+        C = (n_problems + per - 1) / per;
+        for (int c = 0; c < C; ++c) {
+            if (!h->chunk_ev[c]) CU_TRY(h, cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
+            if (!h->chunk_done_ev[c]) CU_TRY(h, cudaEventCreateWithFlags(&h->chunk_done_ev[c], cudaEventDisableTiming));
+        }
+        if (!h->out_stream) CU_TRY(h, cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+        *h->h_status = 0;
+        // Results: the finalize kernel of a chunk writes into a device block and a third stream copies the chunk's rows to
+        // the host (pinned caller arrays or the staging block) - stores over PCIe by the kernel itself, which the one-launch
+        // paths hide under a millisecond of matching, would cost a chunk as much again as its scan (measured: 206 us per
+        // 74 pairs instead of ~100), and the copy engine of the other direction is idle anyway.
+        rc = ensure(h, h->d_res, out_total);
+        if (rc) return rc;
+        char *dr = static_cast<char *>(h->d_res.p);
+        bfm_outputs_t ddst = dst;
+        ddst.knn_idx = want_knn ? reinterpret_cast<int32_t *>(dr) : nullptr;
+        ddst.knn_dist = want_knn ? reinterpret_cast<int32_t *>(dr + knn_b) : nullptr;
+        ddst.m_query = want_m ? reinterpret_cast<int32_t *>(dr + 2 * knn_b) : nullptr;
+        ddst.m_train = want_m ? reinterpret_cast<int32_t *>(dr + 2 * knn_b + m_b) : nullptr;
+        ddst.m_dist = want_m ? reinterpret_cast<int32_t *>(dr + 2 * knn_b + 2 * m_b) : nullptr;
+        ddst.m_count = want_m ? reinterpret_cast<int32_t *>(dr + 2 * knn_b + 3 * m_b) : nullptr;
+        const cudaStream_t sout = h->out_stream;
+        // The copy engine serves `in_stream` for as long as that stream has copies ready: a small table upload of a
+        // chunk's launch on `st` waited until the whole descriptor upload was over (measured: the first kernel started
+        // 0.4 ms late).  So the launches fetch their tables with a few threads instead (tables_by_kernel), and the copy of
+        // chunk c + 1 is queued right after the launch of chunk c (~25 us of host time against ~85 us on the wire).
+        int32_t q_mark = 0, t_mark = 0;
+        cudaEvent_t tev0 = nullptr, tev_copy[8] = {nullptr}, tev_comp[8] = {nullptr};   // BFM_TRACE: the device's own timeline
+        auto copy_chunk = [&](int c) -> int {
+            const int p0 = c * per, p1 = std::min(n_problems, p0 + per);
+            int32_t q_need = q_mark, t_need = t_mark;
+            for (int p = p0; p < p1; ++p) {
+                if (problems[p].q_count <= 0 || problems[p].t_count <= 0) continue;
+                q_need = std::max(q_need, problems[p].q_begin + problems[p].q_count);
+                t_need = std::max(t_need, problems[p].t_begin + problems[p].t_count);
+            }
+            if (q_need > q_mark) CU_TRY(h, cudaMemcpyAsync(din + o_q + (size_t)q_mark * 32, q + (size_t)q_mark * 32, (size_t)(q_need - q_mark) * 32, cudaMemcpyHostToDevice, sin));
+            if (t_need > t_mark) CU_TRY(h, cudaMemcpyAsync(din + o_t + (size_t)t_mark * 32, t + (size_t)t_mark * 32, (size_t)(t_need - t_mark) * 32, cudaMemcpyHostToDevice, sin));
+            q_mark = q_need; t_mark = t_need;
+            CU_TRY(h, cudaEventRecord(h->chunk_ev[c], sin));
+            if (trace) cudaEventRecord(tev_copy[c], sin);
+            return BFM_OK;
+        };
+        if (trace) {
+            cudaEventCreate(&tev0);
+            for (int c = 0; c < C; ++c) { cudaEventCreate(&tev_copy[c]); cudaEventCreate(&tev_comp[c]); }
+            cudaEventRecord(tev0, sin);
+        }
+        rc = copy_chunk(0);
+        const double t_copies = cpu_ms();
+        const int saved_tensor = h->tensor;
+        h->tensor = 2;   // every chunk takes the tensor form, whatever its size
+        h->tables_by_kernel = true;
+        int launched = 0;
+        double t_chunk[16] = {0};
+        for (int c = 0; c < C && rc == BFM_OK; ++c) {
+            const int p0 = c * per, p1 = std::min(n_problems, p0 + per);
+            bfm_outputs_t cd[bfm::MAX_DEST];
+            for (int d = 0; d < n_dests; ++d) {
+                cd[d] = d == 0 ? ddst : dests[d];
+                if (cd[d].m_count) cd[d].m_count += p0;   // per problem of the call; everything else is indexed by output row
+            }
+            if (cudaStreamWaitEvent(st, h->chunk_ev[c], 0) != cudaSuccess) { rc = fail(h, BFM_ERR_CUDA, "cudaStreamWaitEvent failed"); break; }
+            rc = run_device(h, reinterpret_cast<const uint8_t *>(din + o_q), nq_rows, reinterpret_cast<const uint8_t *>(din + o_t), nt_rows,
+                            problems + p0, p1 - p0, n_out_rows, &od, cd, n_dests, st);
+            launched += h->info.kernels_launched;
+            if (rc == BFM_OK) {
+                // this chunk's output rows (any order of out_begin is fine: a row copied again later carries the same bits)
+                long long r0 = n_out_rows, r1 = 0;
+                for (int p = p0; p < p1; ++p) {
+                    if (problems[p].q_count <= 0) continue;
+                    r0 = std::min<long long>(r0, problems[p].out_begin);
+                    r1 = std::max<long long>(r1, (long long)problems[p].out_begin + problems[p].q_count);
+                }
+                CU_TRY(h, cudaEventRecord(h->chunk_done_ev[c], st));
+                CU_TRY(h, cudaStreamWaitEvent(sout, h->chunk_done_ev[c], 0));
+                if (r1 > r0) {
+                    const size_t b = (size_t)r0, n = (size_t)(r1 - r0);
+                    if (want_knn) {
+                        CU_TRY(h, cudaMemcpyAsync(dst.knn_idx + b * k, ddst.knn_idx + b * k, n * k * 4, cudaMemcpyDeviceToHost, sout));
+                        CU_TRY(h, cudaMemcpyAsync(dst.knn_dist + b * k, ddst.knn_dist + b * k, n * k * 4, cudaMemcpyDeviceToHost, sout));
+                    }
+                    if (want_m) {
+                        CU_TRY(h, cudaMemcpyAsync(dst.m_query + b, ddst.m_query + b, n * 4, cudaMemcpyDeviceToHost, sout));
+                        CU_TRY(h, cudaMemcpyAsync(dst.m_train + b, ddst.m_train + b, n * 4, cudaMemcpyDeviceToHost, sout));
+                        CU_TRY(h, cudaMemcpyAsync(dst.m_dist + b, ddst.m_dist + b, n * 4, cudaMemcpyDeviceToHost, sout));
+                    }
+                }
+                if (want_m) CU_TRY(h, cudaMemcpyAsync(dst.m_count + p0, ddst.m_count + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, sout));
+            }
+            if (trace) cudaEventRecord(tev_comp[c], st);
+            t_chunk[2 * c] = cpu_ms();
+            if (rc == BFM_OK && c + 1 < C) rc = copy_chunk(c + 1);
+            t_chunk[2 * c + 1] = cpu_ms();
+        }
+        h->tensor = saved_tensor;
+        h->tables_by_kernel = false;
+        const double t_launched = cpu_ms();
+        if (rc) {
+            cudaDeviceSynchronize();
+            h->state_clean = false;
+            return rc;
+        }
+        CU_TRY(h, cudaStreamSynchronize(sout));   // (behind the last chunk's kernels on st)
+        if (*h->h_status != 0) {
+            h->state_clean = false;
+            return fail(h, BFM_ERR_CUDA, "tensor scan timed out on a barrier");
+        }
+        h->info.copy_chunks = C;
+        h->info.kernels_launched = launched;
+        if (trace) std::fprintf(stderr, "[bfm trace] tensor form, %d copy-engine chunks of %d problems: copies queued %.3f, kernels queued %.3f, done %.3f ms (direct=%d)\n",
+                                C, per, t_copies, t_launched, cpu_ms(), (int)direct);
+        if (trace) {
+            std::fprintf(stderr, "[bfm trace]   per chunk (launch queued / next copy queued, ms):");
+            for (int c = 0; c < C; ++c) std::fprintf(stderr, " %.3f/%.3f", t_chunk[2 * c], t_chunk[2 * c + 1]);
+            std::fprintf(stderr, "\n[bfm trace]   on the device (copy landed / chunk matched, ms after the first copy was queued):");
+            for (int c = 0; c < C; ++c) {
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, tev0, tev_copy[c]);
+                cudaEventElapsedTime(&b, tev0, tev_comp[c]);
+                std::fprintf(stderr, " %.3f/%.3f", a, b);
+                cudaEventDestroy(tev_copy[c]);
+                cudaEventDestroy(tev_comp[c]);
+            }
+            cudaEventDestroy(tev0);
+            std::fprintf(stderr, "\n");
+        }
+    } else if (feed) {
         Gate gate;
         gate.status = h->h_status;
         *h->h_status = 0;

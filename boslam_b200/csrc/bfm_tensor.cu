@@ -7,19 +7,21 @@
 
 namespace bfm {
 
+constexpr int TC_STAGES = 3;   // B stages in shared memory
+
 static_assert(sizeof(Segment) == sizeof(bfm_tc::Item), "work items of the tensor form are the planner's segments");
 static_assert(offsetof(Problem, col0) == 5 * 4 && offsetof(Problem, pad) == 7 * 4 && sizeof(Problem) == 8 * 4,
               "expand_kernel reads the problem table by word offsets");
-static_assert(TC_BQ == bfm_tc::BQ && TC_BT == bfm_tc::BT && DIST_SHIFT == bfm_tc::DIST_SHIFT_TC, "planner and kernel agree on the tile sizes");
+static_assert(TC_BQ == bfm_tc::BQ && TC_BT == bfm_tc::BT && TC_THREADS == bfm_tc::NTHREADS && DIST_SHIFT == bfm_tc::DIST_SHIFT_TC, "planner and kernel agree on the tile sizes");
 
 int tensor_init() {
-    return (int)cudaFuncSetAttribute(bfm_tc::scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfm_tc::SMEM_BYTES);
+    return (int)cudaFuncSetAttribute(bfm_tc::scan_kernel<TC_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bfm_tc::smem_bytes(TC_STAGES));
 }
 
 int tensor_launch(const TensorLaunch &L, cudaStream_t st) {
     if (L.n_items <= 0) return 0;
     if (L.max_rows > 0) {
-        const dim3 egrid((unsigned)(((long long)L.max_rows * 16 + 255) / 256), (unsigned)L.n_problems, 2);
+        const dim3 egrid((unsigned)((L.max_rows + bfm_tc::EXPAND_ROWS - 1) / bfm_tc::EXPAND_ROWS), (unsigned)L.n_problems, 2);
         // Problem: first expanded query row in `pad` (word 7), first expanded train row in `col0` (word 5)
         bfm_tc::expand_kernel<<<egrid, 256, 0, st>>>(static_cast<const uint16_t *>(L.q), static_cast<const uint16_t *>(L.t),
                                                     reinterpret_cast<const int32_t *>(L.probs), 8, 7, 5, static_cast<uint4 *>(L.xq), static_cast<uint4 *>(L.xt),
@@ -36,9 +38,11 @@ int tensor_launch(const TensorLaunch &L, cudaStream_t st) {
     pa.n_items = L.n_items;
     pa.rowstate = L.rowstate;
     pa.status = L.status;
-    pa.mul = -(1 << 21);
+    pa.dbg = 0;
+    pa.mul_lo = (uint32_t)(-64);
+    pa.mul_hi = (uint32_t)(-64) << 16;
     if (L.ev_scan[0]) cudaEventRecord(L.ev_scan[0], st);
-    bfm_tc::scan_kernel<<<(unsigned)L.grid, bfm_tc::NTHREADS, bfm_tc::SMEM_BYTES, st>>>(pa);
+    bfm_tc::scan_kernel<TC_STAGES><<<(unsigned)L.grid, bfm_tc::NTHREADS, bfm_tc::smem_bytes(TC_STAGES), st>>>(pa);
     if (L.ev_scan[1]) cudaEventRecord(L.ev_scan[1], st);
     return (int)cudaGetLastError();
 }

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <string>
 #include <algorithm>
+#define BFM_TC_HARNESS 1
 #include "../boslam_b200/csrc/bfm_tensor.cuh"
 using namespace bfm_tc;
 
@@ -28,7 +30,8 @@ __global__ void ref_kernel(const uint32_t *q, const uint32_t *t, int nq, int nt,
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
 
-static int run_case(int P, int nq, int nt, bool check, int reps) {
+template <int NST, int NA = 2>
+static int run_case(int P, int nq, int nt, bool check, int reps, int dbg = 0) {
     const size_t QR = (size_t)P * nq, TR = (size_t)P * nt;
     std::vector<uint32_t> hq(QR * 8), ht(TR * 8);
     srand(7 + P + nq + nt);
@@ -58,10 +61,10 @@ static int run_case(int P, int nq, int nt, bool check, int reps) {
     CK(cudaMemcpy(dq, hq.data(), hq.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dp, probs.data(), P * sizeof(XProblem), cudaMemcpyHostToDevice)); CK(cudaMemcpy(di, items.data(), items.size() * sizeof(Item), cudaMemcpyHostToDevice));
     CK(cudaMemset(xq, 0, 2 * xq_plane)); CK(cudaMemset(xt, 0, 2 * xt_plane)); CK(cudaMemset(status, 0, 4));
-    CK(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    Params pa{xq, xt, xq_plane, xt_plane, di, (int)items.size(), state, status, -(1 << 21)};
+    CK(cudaFuncSetAttribute(scan_kernel<NST, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(NST, NA)));
+    Params pa{xq, xt, xq_plane, xt_plane, di, (int)items.size(), state, status, dbg, (uint32_t)(-64), (uint32_t)(-64) << 16};
     const int grid = std::min<int>((int)items.size(), 148);
-    const dim3 egrid((std::max(nq, nt) * 16 + 255) / 256, P, 2);
+    const dim3 egrid((std::max(nq, nt) + EXPAND_ROWS - 1) / EXPAND_ROWS, P, 2);
     cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
     float best_x = 1e9, best_s = 1e9;
     for (int rep = 0; rep < reps; ++rep) {
@@ -69,7 +72,7 @@ static int run_case(int P, int nq, int nt, bool check, int reps) {
         CK(cudaEventRecord(e0));
         expand_kernel<<<egrid, 256>>>((const uint16_t *)dq, (const uint16_t *)dt, (const int32_t *)dp, 6, 4, 5, (uint4 *)xq, (uint4 *)xt, xq_plane / 16, xt_plane / 16);
         CK(cudaEventRecord(e1));
-        scan_kernel<<<grid, NTHREADS, SMEM_BYTES>>>(pa);
+        scan_kernel<NST, NA><<<grid, NTHREADS, smem_bytes(NST, NA)>>>(pa);
         CK(cudaEventRecord(e2));
         CK(cudaDeviceSynchronize());
         float mx, ms; cudaEventElapsedTime(&mx, e0, e1); cudaEventElapsedTime(&ms, e1, e2);
@@ -77,7 +80,7 @@ static int run_case(int P, int nq, int nt, bool check, int reps) {
     }
     uint32_t st = 0; CK(cudaMemcpy(&st, status, 4, cudaMemcpyDeviceToHost));
     const double pairs = (double)P * nq * nt;
-    printf("P=%d %dx%d: %zu items on %d CTAs | expand %.1f us, scan %.1f us -> %.0f G pairs/s (scan), %.0f G pairs/s (both) | status %u\n", P, nq, nt, items.size(), grid,
+    printf("[stages %d A x%d dbg %d] P=%d %dx%d: %zu items on %d CTAs | expand %.1f us, scan %.1f us -> %.0f G pairs/s (scan), %.0f G pairs/s (both) | status %u\n", NST, NA, dbg, P, nq, nt, items.size(), grid,
            best_x * 1e3, best_s * 1e3, pairs / best_s / 1e6, pairs / (best_s + best_x) / 1e6, st);
     if (check) {
         for (int p = 0; p < P; ++p)
@@ -95,14 +98,21 @@ static int run_case(int P, int nq, int nt, bool check, int reps) {
 }
 
 int main(int argc, char **argv) {
-    if (run_case(1, 256, 128, true, 1)) return 1;
-    if (run_case(1, 300, 1000, true, 1)) return 1;
-    if (run_case(3, 2000, 2000, true, 2)) return 1;
-    if (run_case(2, 777, 1234, true, 1)) return 1;
-    if (argc > 1) return 0;
-    if (run_case(20, 2000, 2000, false, 5)) return 1;
-    if (run_case(256, 2000, 2000, true, 5)) return 1;
-    if (run_case(1, 2000, 20000, false, 5)) return 1;
-    if (run_case(1, 8192, 8192, false, 5)) return 1;
+    const std::string mode = argc > 1 ? argv[1] : "all";
+    if (mode == "ncu") return run_case<3>(256, 2000, 2000, false, 2);   // one shape, for a profiler capture
+    if (run_case<2>(1, 256, 128, true, 1)) return 1;
+    if (run_case<2>(1, 300, 1000, true, 1)) return 1;
+    if (run_case<3>(3, 2000, 2000, true, 2)) return 1;
+    if (run_case<3>(2, 777, 1234, true, 1)) return 1;
+    if (mode == "quick") return 0;
+    if (run_case<3>(20, 2000, 2000, false, 5)) return 1;
+    if (run_case<3>(256, 2000, 2000, true, 5)) return 1;
+    if (run_case<3>(1, 2000, 20000, false, 5)) return 1;
+    if (run_case<3>(1, 8192, 8192, false, 5)) return 1;
+    if (mode != "probes") return 0;
+    // which of the three engines binds: each alone, and pairs (bits: 1 no folds, 2 no MMA, 4 no B loads)
+    for (int dbg : {5, 6, 7}) if (run_case<3>(256, 2000, 2000, false, 5, dbg)) return 1;
+    if (run_case<2>(256, 2000, 2000, false, 5, 0)) return 1;        // two B stages
+    if (run_case<5, 1>(256, 2000, 2000, false, 5, 0)) return 1;     // five B stages, one A buffer
     return 0;
 }
