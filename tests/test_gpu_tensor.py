@@ -160,3 +160,87 @@ def test_large_batches_take_the_tensor_form_by_default(eng):
         n = int(res[0]["count"][p])
         want = orc.match(q[p * N:(p + 1) * N], t[p * N:(p + 1) * N], k=2, ratio=0.8)
         _eq((res[0]["m"][0, p * N:p * N + n], res[0]["m"][1, p * N:p * N + n], res[0]["m"][2, p * N:p * N + n]), want, p)
+
+
+def _pinned(a):
+    b = bb.PinnedBuffer(a.shape, a.dtype)
+    b.array[...] = a
+    return b
+
+
+@pytest.mark.parametrize("chunks", [0, 3, 8])
+def test_host_batches_in_pinned_memory_take_copy_chunks_and_equal_the_popc_path(eng, chunks):
+    """bfm_pipeline.cuh: a large unmasked batch from pinned host arrays is uploaded by the copy engine in chunks of whole
+    problems, every chunk is matched by the tensor launches, results come back through a device block and a third
+    stream.  Ragged shapes (chunks are not whole rounds), an empty problem inside, match lists and knn tables, into
+    pinned result buffers and into plain arrays - against the one-launch POPC path (tensor=1) and the oracle."""
+    rng = np.random.default_rng(31)
+    P = 56
+    nq = [int(x) for x in rng.integers(1200, 2100, P)]
+    nt = [int(x) for x in rng.integers(1500, 2300, P)]
+    nq[17] = 0
+    nt[40] = 1
+    qo, to = np.cumsum([0] + nq), np.cumsum([0] + nt)
+    q, t = synth.uniform(int(qo[-1]), 51), synth.uniform(int(to[-1]), 52)
+    for p in range(P):
+        if nq[p] and nt[p]:
+            src = rng.integers(0, nt[p], nq[p])
+            q[qo[p]:qo[p + 1]] = t[to[p] + src] ^ np.packbits(rng.random((nq[p], 256)) < 0.04, axis=1)
+    tab = bb.make_problems(nq, nt)
+    pq, pt = _pinned(q), _pinned(t)
+    n_out = int(qo[-1])
+    res = {}
+    try:
+        for tensor in (1, 0):
+            eng.set_tuning(tensor=tensor, tensor_chunks=chunks)
+            idx, dist, r = eng.match_batched(pq.array, pt.array, tab, k=2, ratio=0.8, want_knn=True)       # plain result arrays
+            li = eng.launch_info()
+            if tensor == 0:
+                assert li["popc_mode"] == 0 and li["copy_chunks"] >= 2, li
+                assert chunks == 0 or li["copy_chunks"] == chunks, li
+            else:
+                assert li["popc_mode"] != 0, li
+            res[tensor] = (idx.copy(), dist.copy(), r.counts.copy(), [np.concatenate(x) for x in zip(*[r[p] for p in range(P)])])
+            hb = bb.HostBatchBuffers(n_out, P, k=2)                                                         # pinned result buffers
+            r2 = eng.match_batched(pq.array, pt.array, tab, k=2, ratio=0.8, out=hb)
+            assert np.array_equal(r2.counts, r.counts)
+            for p in (0, 16, 17, 18, 40, P - 1):
+                _eq(r2[p], r[p], ("pinned out", p))
+    finally:
+        eng.set_tuning(tensor=0, tensor_chunks=0)
+    a, b = res[1], res[0]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), "knn tables"
+    assert np.array_equal(a[2], b[2]), "counts"
+    _eq(a[3], b[3], "match lists")
+    for p in (0, 17, 33, 40, P - 1):
+        want = orc.match(q[qo[p]:qo[p + 1]], t[to[p]:to[p + 1]], k=2, ratio=0.8)
+        n0 = int(np.sum(b[2][:p]))
+        n = int(b[2][p])
+        _eq([x[n0:n0 + n] for x in b[3]], want, ("oracle", p))
+
+
+def test_one_frame_against_many_keyframes_from_pinned_memory(eng):
+    """Shared query rows (every problem reads the same frame): the chunked upload copies them once, with the first chunk."""
+    P, n = 70, 2000
+    q, _, _ = synth.correlated(n, 10, 7)
+    t = synth.uniform(P * n, 8)
+    rng = np.random.default_rng(9)
+    for p in range(P):
+        rows = rng.integers(0, n, 600)
+        t[p * n + rows] = q[rng.integers(0, n, 600)] ^ np.packbits(rng.random((600, 256)) < 0.03, axis=1)
+    tab = bb.make_problems([n] * P, [n] * P, shared_query=True)
+    pq, pt = _pinned(q), _pinned(t)
+    try:
+        eng.set_tuning(tensor=0)
+        r = eng.match_batched(pq.array, pt.array, tab, k=2, ratio=0.8)
+        li = eng.launch_info()
+        assert li["popc_mode"] == 0 and li["copy_chunks"] >= 2, li
+        eng.set_tuning(tensor=1)
+        r1 = eng.match_batched(pq.array, pt.array, tab, k=2, ratio=0.8)
+    finally:
+        eng.set_tuning(tensor=0)
+    assert np.array_equal(r.counts, r1.counts) and int(r.counts.sum()) > 1000
+    for p in range(P):
+        _eq(r[p], r1[p], p)
+    for p in (0, 37, P - 1):
+        _eq(r[p], orc.match(q, t[p * n:(p + 1) * n], k=2, ratio=0.8), ("oracle", p))
