@@ -57,7 +57,7 @@ struct Params {
     int32_t n_items;
     unsigned long long *rowstate;        // [out rows] (best << 32) | second, all-ones when idle
     uint32_t *status;                    // set non-zero when a wait timed out
-    int32_t dbg;                         // harness only (TC_DBG), bits: 1 epilogue without folds (one load per tile), 2 no MMA, 4 no B loads; 0 in the library
+    int32_t dbg;                         // harness only (TC_DBG), bits: 1 epilogue without folds (one load per tile), 2 no MMA, 4 no B loads, 8 no row-state commit; 0 in the library
     uint32_t mul_lo, mul_hi;             // -64 and -64 << 16 (two's complement), passed as data so that the keys stay IMADs (FMA pipe)
 };
 
@@ -198,18 +198,25 @@ __global__ void __launch_bounds__(256) expand_kernel(const uint16_t *__restrict_
 // the previous chunk is folded; the accumulator half goes back to the MMA warp as soon as the last load has returned,
 // and - before the last fold - the first load of the NEXT tile is issued (its accumulator is normally complete by
 // then: the wait costs nothing and the load's latency disappears under the fold).
-template <bool MASKED>
+// (the last tile of a train range: chunks that lie inside the range take the plain fold, the one the range ends in the
+// masked fold - columns past the range hold garbage and become all-ones -, chunks past it nothing; ncols is the same for
+// the whole warp, so the choice is a uniform branch)
+template <int CH>
+__device__ __forceinline__ void fold_any(const uint32_t (&v)[32], uint32_t (&p1)[2], uint32_t (&p2)[2], uint32_t m_lo, uint32_t m_hi, int ncols) {
+    if (ncols >= CH * 32 + 32) fold_chunk<CH, false>(v, p1, p2, m_lo, m_hi, BT);
+    else if (ncols > CH * 32) fold_chunk<CH, true>(v, p1, p2, m_lo, m_hi, ncols);
+}
 __device__ __forceinline__ void fold_tile(uint32_t taddr, uint32_t (&va)[32], uint32_t (&vb)[32], uint32_t (&p1)[2], uint32_t (&p2)[2], uint32_t m_lo, uint32_t m_hi,
                                           int ncols) {
     tmem_wait_ld(va);
     tmem_ld32(taddr + 32, vb);
-    fold_chunk<0, MASKED>(va, p1, p2, m_lo, m_hi, ncols);
+    fold_any<0>(va, p1, p2, m_lo, m_hi, ncols);
     tmem_wait_ld(vb);
     tmem_ld32(taddr + 64, va);
-    fold_chunk<1, MASKED>(vb, p1, p2, m_lo, m_hi, ncols);
+    fold_any<1>(vb, p1, p2, m_lo, m_hi, ncols);
     tmem_wait_ld(va);
     tmem_ld32(taddr + 96, vb);
-    fold_chunk<2, MASKED>(va, p1, p2, m_lo, m_hi, ncols);
+    fold_any<2>(va, p1, p2, m_lo, m_hi, ncols);
     tmem_wait_ld(vb);
 }
 
@@ -289,8 +296,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const __grid_constant
         const uint32_t a_lo0 = desc_lo(smem_u32(sA)) + at * (32768 >> 4), b_lo0 = desc_lo(smem_u32(sB));
         uint32_t it = 0, T = 0;
         bool ok = true;
+        int t_count_next = (int)blockIdx.x < p.n_items ? p.items[blockIdx.x].t_count : 0;
         for (int item = blockIdx.x; item < p.n_items && !*abortp && ok; item += gridDim.x, ++it) {
-            const int t_count = p.items[item].t_count;
+            const int t_count = t_count_next;
+            if (item + (int)gridDim.x < p.n_items) t_count_next = p.items[item + gridDim.x].t_count;   // (a round trip to L2, off the issue path)
             const uint32_t ab = it % NA;
             if (!mbar_wait(&a_full[ab], (it / NA) & 1, abortp)) break;
             const uint32_t a_lo = a_lo0 + ab * (A_BYTES >> 4);
@@ -360,10 +369,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const __grid_constant
             if (TC_DBG(p, 1)) {
                 tmem_wait_ld(va);
                 p1[0] = va[0] ^ va[31];
-            } else if (ncols == BT) {
-                fold_tile<false>(taddr, va, vb, p1, p2, m_lo, m_hi, BT);
             } else {
-                fold_tile<true>(taddr, va, vb, p1, p2, m_lo, m_hi, ncols);   // (columns past the range hold garbage: masked to all-ones)
+                fold_tile(taddr, va, vb, p1, p2, m_lo, m_hi, ncols);
             }
             // every load of this accumulator half has returned: hand it back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -378,10 +385,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const __grid_constant
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (ok) tmem_ld32(taddr, va);
             }
-            if (!TC_DBG(p, 1)) {
-                if (ncols == BT) fold_chunk<3, false>(vb, p1, p2, m_lo, m_hi, BT);
-                else fold_chunk<3, true>(vb, p1, p2, m_lo, m_hi, ncols);
-            }
+            if (!TC_DBG(p, 1)) fold_any<3>(vb, p1, p2, m_lo, m_hi, ncols);
             // the tile's two smallest keys -> 32-bit keys with the train index inside the problem
             const uint32_t n1 = __vminu2(p1[0], p1[1]);
             const uint32_t n2 = __vminu2(__vmaxu2(p1[0], p1[1]), __vminu2(p2[0], p2[1]));
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) scan_kernel(const __grid_constant
             if (!more || nxt.item != cur.item) {
                 // this group's last tile of the item: the row-state protocol of the POPC kernel (bfm_kernels.cuh, "commit");
                 // the other group commits its tiles of the same rows the same way
-                if (ok && lr < cur.q_valid && best != 0xFFFFFFFFu) {
+                if (ok && lr < cur.q_valid && best != 0xFFFFFFFFu && !TC_DBG(p, 8)) {
                     uint32_t *half = reinterpret_cast<uint32_t *>(p.rowstate + (size_t)(cur.out_row0 + lr));
                     const uint32_t displaced = atomicMin(half + 1, best);
                     const uint32_t cand = min(max(displaced, best), second);

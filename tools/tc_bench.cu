@@ -111,7 +111,7 @@ int main(int argc, char **argv) {
     if (run_case<3>(1, 8192, 8192, false, 5)) return 1;
     if (mode != "probes") return 0;
     // which of the three engines binds: each alone, and pairs (bits: 1 no folds, 2 no MMA, 4 no B loads)
-    for (int dbg : {5, 6, 7}) if (run_case<3>(256, 2000, 2000, false, 5, dbg)) return 1;
+    for (int dbg : {8, 5, 6, 7}) if (run_case<3>(256, 2000, 2000, false, 5, dbg)) return 1;
     if (run_case<2>(256, 2000, 2000, false, 5, 0)) return 1;        // two B stages
     if (run_case<5, 1>(256, 2000, 2000, false, 5, 0)) return 1;     // five B stages, one A buffer
     return 0;
