@@ -213,9 +213,13 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
         }
         rc = copy_chunk(0);
         const double t_copies = cpu_ms();
-        const int saved_tensor = h->tensor;
-        h->tensor = 2;   // every chunk takes the tensor form, whatever its size
-        h->tables_by_kernel = true;
+        // every chunk takes the tensor form, whatever its size, and fetches its tables by kernel; restored on every way out
+        struct ChunkMode {
+            bfm_handle_t h;
+            int saved;
+            explicit ChunkMode(bfm_handle_t h_) : h(h_), saved(h_->tensor) { h->tensor = 2; h->tables_by_kernel = true; }
+            ~ChunkMode() { h->tensor = saved; h->tables_by_kernel = false; }
+        } chunk_mode(h);
         int launched = 0;
         double t_chunk[16] = {0};
         for (int c = 0; c < C && rc == BFM_OK; ++c) {
@@ -258,8 +262,6 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
             if (rc == BFM_OK && c + 1 < C) rc = copy_chunk(c + 1);
             t_chunk[2 * c + 1] = cpu_ms();
         }
-        h->tensor = saved_tensor;
-        h->tables_by_kernel = false;
         const double t_launched = cpu_ms();
         if (rc) {
             cudaDeviceSynchronize();

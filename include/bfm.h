@@ -254,7 +254,8 @@ typedef struct bfm_launch_info {
     int32_t segments;           /* (query block, train range) work items */
     int32_t train_rows_per_segment;
     int32_t copy_chunks;        /* BFM_MEM_HOST: slices the upload was delivered in while the kernel ran - feed rounds
-                                   (pinned inputs) or copy-engine chunks (pageable inputs); 1 = no overlap */
+                                   (pinned inputs, POPC kernel), copy-engine chunks (pageable inputs; pinned inputs of the
+                                   tensor form, where every chunk has its own launches); 1 = no overlap */
     float scan_ms;              /* device time of the kernel of the last call when timing is on */
     float total_ms;             /* same (kept for ABI stability) */
 } bfm_launch_info_t;
@@ -274,7 +275,13 @@ int bfm_get_launch_info(bfm_handle_t h, bfm_launch_info_t *out);
  *                     local-mapping batch, a rank's share of a sharded loop-closing batch) and the static form (one
  *                     work item per CTA, the CTA that completes a problem finalizes it) for longer ones and on the
  *                     gated host path,
- *       "taper" = 16 with "gss_div" / "gss_min": guided item lengths (an experiment, see profiles/r02_kernel_forms.md) */
+ *       "taper" = 16 with "gss_div" / "gss_min": guided item lengths (an experiment, see profiles/r02_kernel_forms.md),
+ *       "tensor" {0=auto, 1=off, 2=whenever eligible}: calls without mask / window / cross-check and k <= 2 can take the
+ *                     tensor form (bfm_tensor.cuh: the descriptors expanded to one s8 per bit, distances as dot products
+ *                     on tcgen05, the same finalize) - the same integers out; auto uses it from 8 M pairs per launch on.
+ *                     A BFM_MEM_HOST batch of >= 8 problems and >= 4 MB in pinned memory that is eligible is uploaded by
+ *                     the copy engine in chunks of whole problems, each matched by the tensor launches as it lands,
+ *       "tensor_chunks" {0=auto, 2..8}: number of those chunks */
 int bfm_set_tuning(bfm_handle_t h, const char *knob, int32_t value);
 /* Wait until everything queued on the handle's own stream (BFM_STREAM_OWN calls) has completed. */
 int bfm_synchronize(bfm_handle_t h);
