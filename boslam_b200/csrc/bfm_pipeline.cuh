@@ -1,7 +1,11 @@
 // bfm_pipeline.cuh - the BFM_MEM_HOST path.
 // (included by bfm_api.cu inside its anonymous namespace, after run_device)
 //
-// One kernel launch per call, however large the batch.  What overlaps with it:
+// POPC kernel: one kernel launch per call, however large the batch (what overlaps with it is listed below).  Tensor form
+// (large unmasked batches in pinned memory): copy-engine chunks of whole problems, each matched by its own three launches
+// as it lands, results staged on the device and copied out by a third stream - see the `tchunks` branch of run_host.
+//
+// One launch, and what overlaps with it:
 //
 //   inputs   (a) pinned caller arrays - SM-fed upload: the first 24 CTAs of the matching kernel stream the
 //            arrays from pinned host memory into HBM themselves (zero-copy loads over PCIe, bfm_kernels.cuh:
