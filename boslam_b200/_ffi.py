@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "bfm_match", "bfm_match_batched_multi", "bfm_match_batched_host_multi", "bfm_get_launch_info", "bfm_set_tuning", "bfm_kernel_launch_count", "bfm_microbench",
     "bfm_device_info", "bfm_host_alloc", "bfm_host_free", "bfm_map_create", "bfm_map_destroy", "bfm_map_update",
     "bfm_track_local_map", "bfm_select_representative", "bfm_plan_preview", "bfm_debug_timeline", "bfm_plan_preview_tiles", "bfm_keyframe_vote", "bfm_synchronize",
+    "bfm_plan_preview_tensor", "bfm_plan_preview_host_chunks",
 )
 
 
@@ -201,3 +202,38 @@ def plan_preview_tiles(problems, n_ctas: int = 148 * 8):
     if rc != BFM_OK:
         raise BfmError(rc, "bfm_plan_preview_tiles failed")
     return tiles, tile_cta
+
+
+def plan_preview_tensor(problems, n_sms: int = 148):
+    """Work items of the tensor form - host only.  Returns (items int32[n, 8] as in :func:`plan_preview`, but with
+    q_row0 / t_row0 in rows of the expanded planes; train rows per item; (query plane rows, train plane rows))."""
+    import numpy as np
+    L = lib()
+    tab = np.ascontiguousarray(problems, dtype=np.int32).reshape(-1, 6)
+    pp = tab.ctypes.data_as(ctypes.POINTER(Problem))
+    n, rows = ctypes.c_int32(), ctypes.c_int32()
+    planes = (ctypes.c_int32 * 2)()
+    L.bfm_plan_preview_tensor.argtypes = [ctypes.POINTER(Problem), ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    rc = L.bfm_plan_preview_tensor(pp, len(tab), n_sms, None, 0, ctypes.byref(n), ctypes.byref(rows), planes)
+    if rc != BFM_OK:
+        raise BfmError(rc, "bfm_plan_preview_tensor: invalid arguments")
+    items = np.empty((n.value, 8), np.int32)
+    rc = L.bfm_plan_preview_tensor(pp, len(tab), n_sms, items.ctypes.data, n.value, ctypes.byref(n), ctypes.byref(rows), planes)
+    if rc != BFM_OK:
+        raise BfmError(rc, "bfm_plan_preview_tensor failed")
+    return items, rows.value, (planes[0], planes[1])
+
+
+def plan_preview_host_chunks(problems, n_query_rows: int, n_train_rows: int, n_sms: int = 148, forced: int = 0):
+    """(number of copy chunks, problems per chunk) of a host batch that takes the tensor form - host only."""
+    import numpy as np
+    L = lib()
+    tab = np.ascontiguousarray(problems, dtype=np.int32).reshape(-1, 6)
+    pp = tab.ctypes.data_as(ctypes.POINTER(Problem))
+    c, per = ctypes.c_int32(), ctypes.c_int32()
+    L.bfm_plan_preview_host_chunks.argtypes = [ctypes.POINTER(Problem)] + [ctypes.c_int32] * 5 + [ctypes.c_void_p, ctypes.c_void_p]
+    rc = L.bfm_plan_preview_host_chunks(pp, len(tab), n_query_rows, n_train_rows, n_sms, forced, ctypes.byref(c), ctypes.byref(per))
+    if rc != BFM_OK:
+        raise BfmError(rc, "bfm_plan_preview_host_chunks: invalid arguments")
+    return c.value, per.value

@@ -1340,6 +1340,38 @@ int bfm_plan_preview_tiles(const bfm_problem_t *problems, int32_t n_problems, in
     return BFM_OK;
 }
 
+int bfm_plan_preview_tensor(const bfm_problem_t *problems, int32_t n_problems, int32_t n_sms, int32_t *items_out, int32_t capacity,
+                            int32_t *n_items, int32_t *segment_rows_out, int32_t *plane_rows_out) {
+    if (!problems || n_problems <= 0 || !n_items || n_sms <= 0 || capacity < 0 || (capacity > 0 && !items_out)) return BFM_ERR_INVALID;
+    for (int p = 0; p < n_problems; ++p)
+        if (problems[p].q_count < 0 || problems[p].t_count < 0 || problems[p].q_begin < 0 || problems[p].t_begin < 0 ||
+            problems[p].out_begin < 0 || problems[p].t_count >= BFM_MAX_TRAIN_ROWS || problems[p].q_count >= BFM_MAX_QUERY_ROWS)
+            return BFM_ERR_INVALID;
+    std::vector<int32_t> xq0, xt0;
+    long long rows[2] = {0, 0};
+    tensor_bases(problems, n_problems, xq0, xt0, rows);
+    std::vector<Segment> segs;
+    std::vector<int> seg_begin;
+    int L = 0;
+    plan_items_tensor(problems, n_problems, n_sms, xq0, xt0, segs, seg_begin, &L);
+    *n_items = (int32_t)segs.size();
+    if (segment_rows_out) *segment_rows_out = L;
+    if (plane_rows_out) { plane_rows_out[0] = (int32_t)rows[0]; plane_rows_out[1] = (int32_t)rows[1]; }
+    const size_t n = std::min(segs.size(), (size_t)capacity);
+    if (n) std::memcpy(items_out, segs.data(), n * sizeof(Segment));
+    return BFM_OK;
+}
+
+int bfm_plan_preview_host_chunks(const bfm_problem_t *problems, int32_t n_problems, int32_t n_query_rows, int32_t n_train_rows,
+                                 int32_t n_sms, int32_t forced_chunks, int32_t *n_chunks, int32_t *problems_per_chunk) {
+    if (!problems || n_problems <= 0 || n_sms <= 0 || forced_chunks < 0 || forced_chunks > 8 || n_query_rows < 0 || n_train_rows < 0 || !n_chunks || !problems_per_chunk)
+        return BFM_ERR_INVALID;
+    int per = 0;
+    *n_chunks = plan_host_chunks(problems, n_problems, ((size_t)n_query_rows + (size_t)n_train_rows) * 32, n_sms, forced_chunks, &per);
+    *problems_per_chunk = per;
+    return BFM_OK;
+}
+
 int bfm_host_alloc(uint64_t bytes, void **out) {
     if (!out) return BFM_ERR_INVALID;
     *out = nullptr;

@@ -40,6 +40,27 @@ void ensure_pool(bfm_handle_t h) {
     h->pool.reset(new WorkerPool(std::min(std::max(n, 2), 8) - 1));   // the calling thread works too
 }
 
+// Copy chunks of a host batch that takes the tensor form: whole problems, about 8 MB of descriptors each (2 .. 8 chunks;
+// `forced` > 0 overrides the count); when all problems have one shape a chunk is rounded to a whole number of rounds of
+// the persistent scan - its work items (256-row query blocks) divide by the SM count.  Returns the number of chunks,
+// *per = problems per chunk (the last chunk takes what is left).
+int plan_host_chunks(const bfm_problem_t *problems, int n_problems, size_t bytes, int sm_count, int forced, int *per_out) {
+    int C = forced > 0 ? std::min(forced, n_problems) : (int)std::min<size_t>(8, std::max<size_t>(2, bytes / ((size_t)8 << 20)));
+    C = std::max(1, std::min(C, n_problems));
+    int per = (n_problems + C - 1) / C;
+    bool uniform = true;
+    for (int p = 1; p < n_problems && uniform; ++p) uniform = problems[p].q_count == problems[0].q_count && problems[p].t_count == problems[0].t_count;
+    if (uniform && problems[0].q_count > 0 && sm_count > 0) {
+        const int ipp = (problems[0].q_count + bfm::TC_BQ - 1) / bfm::TC_BQ;   // work items per problem
+        int a = sm_count, b = ipp;
+        while (b) { const int r = a % b; a = b; b = r; }
+        const int unit = sm_count / a;                                         // problems per round of the scan
+        if (unit <= 2 * per) per = std::max(1, (per + unit / 2) / unit) * unit;
+    }
+    *per_out = per;
+    return (n_problems + per - 1) / per;
+}
+
 bool host_ptr_is_pinned(const void *p) {
     if (!p) return false;
     cudaPointerAttributes a;
@@ -156,18 +177,8 @@ int run_host(bfm_handle_t h, const uint8_t *q, int32_t nq_rows, const uint8_t *t
     const bool tchunks = h->tensor != 1 && h->feeders >= 0 && h->pipeline_chunks == 0 && o->mask_kind == BFM_MASK_NONE && !o->cross_check && o->k <= 2 &&
                          n_problems >= 8 && qb + tb >= ((size_t)4 << 20) && total_pairs_h >= 16 * TENSOR_MIN_PAIRS && feedable(q) && feedable(t);
     if (tchunks) {
-        int C = h->tensor_chunks > 0 ? std::min(h->tensor_chunks, n_problems) : (int)std::min<size_t>(8, std::max<size_t>(2, (qb + tb) / ((size_t)8 << 20)));
-        int per = (n_problems + C - 1) / C;
-        bool uniform = true;
-        for (int p = 1; p < n_problems && uniform; ++p) uniform = problems[p].q_count == problems[0].q_count && problems[p].t_count == problems[0].t_count;
-        if (uniform && problems[0].q_count > 0) {
-            const int ipp = (problems[0].q_count + bfm::TC_BQ - 1) / bfm::TC_BQ;   // work items per problem
-            int a = h->sm_count, b = ipp;
-            while (b) { const int r = a % b; a = b; b = r; }
-            const int unit = h->sm_count / a;                                      // problems per round of the scan
-            if (unit <= 2 * per) per = std::max(1, (per + unit / 2) / unit) * unit;
-        }
-        C = (n_problems + per - 1) / per;
+        int per = 0;
+        const int C = plan_host_chunks(problems, n_problems, qb + tb, h->sm_count, h->tensor_chunks, &per);
         for (int c = 0; c < C; ++c) {
             if (!h->chunk_ev[c]) CU_TRY(h, cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
             if (!h->chunk_done_ev[c]) CU_TRY(h, cudaEventCreateWithFlags(&h->chunk_done_ev[c], cudaEventDisableTiming));

@@ -311,6 +311,18 @@ int bfm_plan_preview(const bfm_problem_t *problems, int32_t n_problems, int32_t 
 int bfm_plan_preview_tiles(const bfm_problem_t *problems, int32_t n_problems, int32_t n_ctas, int32_t *tiles_out,
                            int32_t *tile_cta_out, int32_t tile_capacity, int32_t *n_tiles);
 
+/* Host-only preview of the work items of the tensor form (bfm_tensor.cuh): blocks of 256 query rows against train ranges
+ * that are multiples of 128 rows (the last range of a problem ends where the problem ends), walked by one persistent CTA
+ * per SM (`n_sms`).  items_out as in bfm_plan_preview, except that q_row0 / t_row0 are rows of the EXPANDED planes, where
+ * every problem has an 8-row-aligned base; plane_rows_out[2] = rows of the query / train planes. */
+int bfm_plan_preview_tensor(const bfm_problem_t *problems, int32_t n_problems, int32_t n_sms, int32_t *items_out, int32_t capacity,
+                            int32_t *n_items, int32_t *segment_rows_out, int32_t *plane_rows_out);
+
+/* Host-only preview of the copy chunks a BFM_MEM_HOST batch of the tensor form is uploaded in (whole problems; with equal
+ * shapes a chunk is a whole number of rounds of the persistent scan).  forced_chunks = the "tensor_chunks" knob. */
+int bfm_plan_preview_host_chunks(const bfm_problem_t *problems, int32_t n_problems, int32_t n_query_rows, int32_t n_train_rows,
+                                 int32_t n_sms, int32_t forced_chunks, int32_t *n_chunks, int32_t *problems_per_chunk);
+
 /* Integer-pipe micro-benchmark: the roofline denominator.
  * test: 0 POPC, 1 LOP3, 2 IADD3, 3 POPC+LOP3 1:1, 4 POPC+2xLOP3, 5 REDUX.MIN, 6 IMAD, 7 VIMNMX,
  *       8 POPC+IMAD 1:1, 9 XOR+POPC+IADD pair loop (8:8:4, the plain per-pair mix).

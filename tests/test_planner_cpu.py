@@ -151,3 +151,77 @@ def test_tile_owners_are_the_lowest_quarter_of_the_grid():
     tiles, tile_cta = _ffi.plan_preview_tiles(one, 64)               # more tiles than CTAs: consecutive tiles share a CTA, in order
     _check_tiles(one, tiles, tile_cta, 64)
     assert len(tiles) == 137 and tile_cta.max() == 15 and np.bincount(tile_cta).max() <= 9
+
+
+# ---- the tensor form's planner (plan_items_tensor) and the copy chunks of its host path ---------------------------------
+
+def _check_tensor_plan(tab, n_sms=148):
+    items, seg_rows, planes = _ffi.plan_preview_tensor(tab, n_sms)
+    assert seg_rows % 128 == 0
+    xq = xt = 0
+    by_problem = {}
+    for it in items:
+        by_problem.setdefault(int(it[7]), []).append(it)
+    for p, (qb, qc, tb, tc, ob, _) in enumerate(np.asarray(tab)):
+        if qc == 0 or tc == 0:
+            assert p not in by_problem            # empty problems have no work item
+        else:
+            its = by_problem[p]
+            blocks = {}
+            for q_row0, q_valid, q_local0, out_row0, t_row0, t_count, t_local0, _ in its:
+                assert q_local0 % 256 == 0 and q_valid == min(256, qc - q_local0) and q_valid > 0
+                assert q_row0 == xq + q_local0 and out_row0 == ob + q_local0
+                assert t_row0 == xt + t_local0 and t_row0 % 8 == 0 and q_row0 % 8 == 0      # 1024-byte swizzle atoms
+                assert 0 < t_count <= seg_rows
+                assert t_local0 % 128 == 0 and (t_count % 128 == 0 or t_local0 + t_count == tc)
+                blocks.setdefault(int(q_local0), []).append((int(t_local0), int(t_count)))
+            assert sorted(blocks) == list(range(0, qc, 256))                                  # every query block, once
+            for ranges in blocks.values():                                                    # ... against the whole train set, once
+                pos = 0
+                for t0, n in sorted(ranges):
+                    assert t0 == pos
+                    pos += n
+                assert pos == tc
+        xq += (qc + 7) // 8 * 8
+        xt += (tc + 7) // 8 * 8
+    assert planes == (xq, xt)
+    return items
+
+
+def test_tensor_plan_tiles_every_problem_exactly_once():
+    rng = np.random.default_rng(5)
+    _check_tensor_plan(bb.make_problems([2000] * 256, [2000] * 256))
+    _check_tensor_plan(bb.make_problems([1], [1]))
+    _check_tensor_plan(bb.make_problems([300, 0, 257, 2000, 5, 640, 1, 900, 0, 1300], [500, 40, 0, 2000, 2500, 129, 1, 7, 0, 1111]))
+    for _ in range(20):
+        P = int(rng.integers(1, 40))
+        _check_tensor_plan(bb.make_problems(rng.integers(0, 3000, P), rng.integers(0, 5000, P)), n_sms=int(rng.choice([1, 8, 148])))
+    _check_tensor_plan(bb.make_problems([2000] * 20, [2000] * 20, shared_query=True))
+
+
+def test_tensor_plan_cuts_long_train_ranges_to_fill_the_sms():
+    """One large problem: whole train ranges per item would leave most SMs idle, so the ranges are cut (multiples of 128
+    rows); a batch that already fills the machine keeps whole ranges (one A-tile load and one commit per query block)."""
+    items = _check_tensor_plan(bb.make_problems([8192], [8192]))
+    assert len(items) >= 96 and len(items) <= 148                  # 32 query blocks x 3-4 train ranges: one round
+    items = _check_tensor_plan(bb.make_problems([65536], [65536]))
+    assert len(items) % 256 == 0 and len(items) >= 1024            # 256 query blocks x >= 4 ranges
+    items = _check_tensor_plan(bb.make_problems([2000] * 256, [2000] * 256))
+    assert len(items) == 2048 and set(items[:, 5]) == {2000}
+
+
+def test_host_chunks_are_whole_rounds_of_the_scan_for_equal_shapes():
+    tab = bb.make_problems([2000] * 256, [2000] * 256)
+    assert _ffi.plan_preview_host_chunks(tab, 512000, 512000) == (4, 74)          # 74 pairs = 592 items = 4 x 148
+    assert _ffi.plan_preview_host_chunks(tab[:128], 256000, 256000) == (2, 74)    # a rank's share at 2 GPUs
+    assert _ffi.plan_preview_host_chunks(tab[:32], 64000, 64000) == (2, 16)       # ... at 8 GPUs: shorter than a round
+    assert _ffi.plan_preview_host_chunks(tab, 512000, 512000, forced=7) == (7, 37)
+    for forced in range(1, 9):
+        c, per = _ffi.plan_preview_host_chunks(tab, 512000, 512000, forced=forced)
+        assert 1 <= c <= 8 and (c - 1) * per < 256 <= c * per
+    rng = np.random.default_rng(6)
+    rag = bb.make_problems(rng.integers(1200, 2100, 56), rng.integers(1500, 2300, 56))
+    c, per = _ffi.plan_preview_host_chunks(rag, int(rag[:, 1].sum()), int(rag[:, 3].sum()))
+    assert (c, per) == (2, 28)                                                     # ragged: equal numbers of problems
+    with pytest.raises(_ffi.BfmError):
+        _ffi.plan_preview_host_chunks(tab, 512000, 512000, forced=9)
